@@ -1,0 +1,137 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point of include/deepaco_b200.h).
+
+Tensors are torch CUDA tensors; a leading colony dimension is optional (a 2-D matrix is one colony).
+Nothing here computes: it validates shapes, allocates outputs and forwards raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, f32c, lib, ptr, require_cuda, stream_ptr
+
+
+def _colonies(mat: torch.Tensor):
+    """-> (B, n) for a [n, n] or [B, n, n] matrix."""
+    if mat.dim() == 2:
+        return 1, mat.shape[0]
+    if mat.dim() == 3:
+        return mat.shape[0], mat.shape[1]
+    raise _lib.DeepAcoError(f"expected [n,n] or [B,n,n] matrix, got shape {tuple(mat.shape)}")
+
+
+def aten_sum_plan(row_len: int, n_rows: int):
+    bw, vec, exact = C.c_int(), C.c_int(), C.c_int()
+    check(lib().deepaco_aten_sum_plan(row_len, n_rows, C.byref(bw), C.byref(vec), C.byref(exact)), "aten_sum_plan")
+    return bw.value, bool(vec.value), bool(exact.value)
+
+
+def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False, seed=0, offset=0, rng=None,
+               noise=None, start=None, want_paths=True, want_logp=False, want_tours=False):
+    """deepaco_tsp_sample.  Returns (paths|None, log_probs|None, tours|None) shaped like the inputs'
+    batching: single colony -> paths [n, A]; batched -> [B, n, A]."""
+    pheromone = f32c(require_cuda(pheromone, "pheromone"))
+    B, n = _colonies(pheromone)
+    batched = pheromone.dim() == 3
+    dev = pheromone.device
+    if heuristic is not None:
+        heuristic = f32c(require_cuda(heuristic, "heuristic"))
+        if heuristic.shape != pheromone.shape:
+            raise _lib.DeepAcoError("heuristic / pheromone shape mismatch")
+    if noise is not None:
+        noise = f32c(require_cuda(noise, "noise"))
+        if noise.numel() != B * (n - 1) * n_ants * n:
+            raise _lib.DeepAcoError(f"noise must hold [B][n-1][A][n] = {B * (n - 1) * n_ants * n} values")
+    if start is not None:
+        start = require_cuda(start, "start").to(torch.int64).contiguous()
+    paths = torch.empty((B, n, n_ants), dtype=torch.int64, device=dev) if want_paths else None
+    logp = torch.empty((B, n - 1, n_ants), dtype=torch.float32, device=dev) if want_logp else None
+    tours = torch.empty((B, n_ants, n), dtype=torch.uint16, device=dev) if want_tours else None
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_sample(ptr(pheromone), ptr(heuristic), n, n_ants, B, int(start_node), int(double_norm),
+                                       int(seed), int(offset), ptr(rng), ptr(noise), ptr(start), ptr(paths), ptr(logp),
+                                       ptr(tours), stream_ptr(dev)), "deepaco_tsp_sample")
+    if not batched:
+        paths = None if paths is None else paths[0]
+        logp = None if logp is None else logp[0]
+        tours = None if tours is None else tours[0]
+    return paths, logp, tours
+
+
+def tsp_sample_offset_increment(n, n_ants, start_node=-1) -> int:
+    return int(lib().deepaco_tsp_sample_offset_increment(n, n_ants, int(start_node)))
+
+
+def tsp_cost(distances, paths=None, tours=None, *, want_costs=True, want_neighbours=False):
+    """deepaco_tsp_cost -> (costs [A] | [B, A], neighbours uint32 [n, A] | [B, n, A])."""
+    distances = f32c(require_cuda(distances, "distances"))
+    B, n = _colonies(distances)
+    batched = distances.dim() == 3
+    dev = distances.device
+    if (paths is None) == (tours is None):
+        raise _lib.DeepAcoError("pass exactly one of paths / tours")
+    if paths is not None:
+        paths = require_cuda(paths, "paths")
+        if paths.dtype != torch.int64:
+            paths = paths.to(torch.int64)
+        paths = paths.contiguous()
+        n_ants = paths.shape[-1]
+        if paths.shape[-2] != n:
+            raise _lib.DeepAcoError(f"paths has {paths.shape[-2]} rows, expected problem_size {n}")
+    else:
+        tours = require_cuda(tours, "tours").contiguous()
+        if tours.dtype != torch.uint16:
+            raise _lib.DeepAcoError("tours must be uint16")
+        n_ants = tours.shape[-2]
+    costs = torch.empty((B, n_ants), dtype=torch.float32, device=dev) if want_costs else None
+    nbr = torch.empty((B, n, n_ants), dtype=torch.int32, device=dev) if want_neighbours else None
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_cost(ptr(distances), ptr(paths), ptr(tours), n, n_ants, B, ptr(costs), ptr(nbr),
+                                     stream_ptr(dev)), "deepaco_tsp_cost")
+    if not batched:
+        costs = None if costs is None else costs[0]
+        nbr = None if nbr is None else nbr[0]
+    return costs, nbr
+
+
+def tsp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_max=False, ph_min=0.0, ph_max=None):
+    """deepaco_tsp_update, in place on `pheromone` (must be fp32 contiguous CUDA)."""
+    require_cuda(pheromone, "pheromone")
+    if pheromone.dtype != torch.float32 or not pheromone.is_contiguous():
+        raise _lib.DeepAcoError("pheromone must be contiguous fp32 for the in-place update")
+    B, n = _colonies(pheromone)
+    n_ants = costs.shape[-1]
+    costs = f32c(costs)
+    dev = pheromone.device
+    if min_max:
+        ph_max = f32c(torch.as_tensor(ph_max, device=dev).reshape(-1))
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_update(ptr(pheromone), ptr(neighbours), ptr(costs), n, n_ants, B, float(decay),
+                                       int(elitist), int(min_max), float(ph_min), ptr(ph_max) if min_max else None,
+                                       stream_ptr(dev)), "deepaco_tsp_update")
+    return pheromone
+
+
+# ---- probes ------------------------------------------------------------------------------------
+def debug_exponential(seed, offset, numel, device):
+    out = torch.empty((numel,), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        check(lib().deepaco_debug_exponential(int(seed), int(offset), numel, ptr(out), stream_ptr(out.device)), "debug_exponential")
+    return out
+
+
+def debug_randint(seed, offset, numel, high, device):
+    out = torch.empty((numel,), dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        check(lib().deepaco_debug_randint(int(seed), int(offset), numel, int(high), ptr(out), stream_ptr(out.device)), "debug_randint")
+    return out
+
+
+def debug_row_sum(x):
+    x = f32c(require_cuda(x, "x"))
+    out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().deepaco_debug_row_sum(ptr(x), x.shape[0], x.shape[1], ptr(out), stream_ptr(x.device)), "debug_row_sum")
+    return out

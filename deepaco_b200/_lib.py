@@ -1,0 +1,97 @@
+"""ctypes binding of libdeepaco_b200.so (the C ABI declared in include/deepaco_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an exception is
+raised.  torch is used for device memory, streams and the Philox generator state only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeepaco_b200.so")
+
+_u64, _i64, _i32, _f32, _vp = C.c_uint64, C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+_SIGNATURES = {
+    # name: (restype, [argtypes])
+    "deepaco_last_error": (C.c_char_p, []),
+    "deepaco_version": (_i32, []),
+    "deepaco_torch_draw_geometry": (_i32, [_i64, C.POINTER(C.c_uint32), C.POINTER(_u64)]),
+    "deepaco_aten_sum_plan": (_i32, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "deepaco_tsp_sample": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "deepaco_tsp_sample_offset_increment": (_u64, [_i32, _i32, _i32]),
+    "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
+    "deepaco_debug_exponential": (_i32, [_u64, _u64, _i64, _vp, _vp]),
+    "deepaco_debug_randint": (_i32, [_u64, _u64, _i64, _i64, _vp, _vp]),
+    "deepaco_debug_row_sum": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+class DeepAcoError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Names the header declares; tests check each resolves in the built library."""
+    return list(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DeepAcoError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C deepaco_b200/csrc`). deepaco_b200 has no CPU fallback.")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().deepaco_last_error().decode(errors="replace")
+        raise DeepAcoError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise DeepAcoError(f"deepaco_b200: `{name}` must live on a CUDA device (got {t.device}); "
+                           "this engine has no CPU path")
+    return t
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous view/copy (no-op for the tensors the reference drivers pass)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def generator_state(device):
+    """(seed, offset) of torch's default CUDA generator on `device`."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    g = torch.cuda.default_generators[idx]
+    return g, int(g.initial_seed()), int(g.get_offset())

@@ -1,0 +1,74 @@
+// Probe entry points: regenerate torch's CUDA `exponential_` / `randint` streams and ATen's row sum so
+// the tests can confirm, on the box, the parity assumptions of SURVEY.md Appendix A before relying on them.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace deepaco {
+
+__global__ void debug_exponential_kernel(uint64_t seed, uint64_t offset, int64_t numel, DrawGeom g, float* out) {
+    for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < numel; li += (int64_t)gridDim.x * blockDim.x)
+        out[li] = exp1_from_word(torch_philox_word(seed, offset, (uint64_t)li, g));
+}
+
+__global__ void debug_randint_kernel(uint64_t seed, uint64_t offset, int64_t numel, uint32_t high, DrawGeom g, int64_t* out) {
+    for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < numel; li += (int64_t)gridDim.x * blockDim.x)
+        out[li] = (int64_t)(torch_philox_word(seed, offset, (uint64_t)li, g) % high);
+}
+
+template <typename F>
+__device__ __forceinline__ float row_sum_fn(F f, int len, int lbw, bool vec, int lane) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+        for (int base = 4 * lane; base + 3 < len; base += 128)
+            for (int i = 0; i < 4; ++i) acc[i] = __fadd_rn(acc[i], f(base + i));
+        if (lane < (len & 3)) acc[0] = __fadd_rn(acc[0], f(len - (len & 3) + lane));
+    } else if (lane < (1 << lbw)) {
+        int i = 0;
+        for (int k = lane; k < len; k += (1 << lbw), ++i) acc[i & 3] = __fadd_rn(acc[i & 3], f(k));
+    }
+    return warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
+}
+
+__global__ void debug_row_sum_kernel(const float* x, int rows, int len, int lbw, int vec, float* out) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* row = x + (size_t)r * len;
+    const float s = row_sum_fn([&](int k) { return row[k]; }, len, lbw, vec != 0, threadIdx.x & 31);
+    if ((threadIdx.x & 31) == 0) out[r] = s;
+}
+
+}  // namespace deepaco
+
+using namespace deepaco;
+
+extern "C" int deepaco_debug_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out, void* stream) {
+    const DeviceInfo* di = device_info();
+    if (!di) return DEEPACO_ENODEV;
+    DACO_CHECK_ARG(numel > 0 && out, "deepaco_debug_exponential: bad arguments");
+    const DrawPlan dp = torch_draw_plan(numel, *di);
+    debug_exponential_kernel<<<(unsigned)std::min<int64_t>((numel + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(
+        seed, offset, numel, DrawGeom{dp.threads, dp.single}, out);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+extern "C" int deepaco_debug_randint(uint64_t seed, uint64_t offset, int64_t numel, int64_t high, int64_t* out, void* stream) {
+    const DeviceInfo* di = device_info();
+    if (!di) return DEEPACO_ENODEV;
+    DACO_CHECK_ARG(numel > 0 && out && high > 0 && high < (1ll << 28), "deepaco_debug_randint: bad arguments");
+    const DrawPlan dp = torch_draw_plan(numel, *di);
+    debug_randint_kernel<<<(unsigned)std::min<int64_t>((numel + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(
+        seed, offset, numel, (uint32_t)high, DrawGeom{dp.threads, dp.single}, out);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+extern "C" int deepaco_debug_row_sum(const float* x, int n_rows, int row_len, float* out, void* stream) {
+    DACO_CHECK_ARG(x && out && n_rows > 0 && row_len > 0, "deepaco_debug_row_sum: bad arguments");
+    const SumPlan sp = aten_sum_plan(row_len, n_rows);
+    int bw = sp.block_width > 32 ? 32 : sp.block_width, lbw = 0;
+    while ((1 << lbw) < bw) ++lbw;
+    debug_row_sum_kernel<<<(n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, n_rows, row_len, lbw, sp.vectorized, out);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}

@@ -1,0 +1,57 @@
+// host-side helpers shared by the C-ABI translation units
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/deepaco_b200.h"
+
+namespace deepaco {
+
+void set_error(const char* fmt, ...);
+
+struct DeviceInfo {
+    int device;
+    int sm_count;
+    int max_threads_per_sm;
+    int max_smem_optin;
+    int cc_major;
+};
+// properties of the CURRENT device (cached per device ordinal); returns nullptr on failure
+const DeviceInfo* device_info();
+
+// ATen sum plan for sum over the last dim of a contiguous [n_rows][row_len] fp32 tensor
+struct SumPlan {
+    int block_width;   // lanes cooperating on one row (power of two)
+    int vectorized;    // ATen "vectorize along input" path (row_len >= 128)
+    int exact;         // 1 if our kernels reproduce this order exactly
+};
+SumPlan aten_sum_plan(int row_len, int n_rows);
+
+struct DrawPlan {
+    uint32_t threads;
+    uint32_t single;
+    uint64_t increment;
+};
+DrawPlan torch_draw_plan(int64_t numel, const DeviceInfo& di);
+
+#define DACO_CHECK_ARG(cond, ...)            \
+    do {                                     \
+        if (!(cond)) {                       \
+            deepaco::set_error(__VA_ARGS__); \
+            return DEEPACO_EINVAL;           \
+        }                                    \
+    } while (0)
+
+#define DACO_CHECK_CUDA(expr)                                                                        \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            deepaco::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DEEPACO_ECUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define DACO_CHECK_LAUNCH() DACO_CHECK_CUDA(cudaGetLastError())
+
+}  // namespace deepaco

@@ -1,0 +1,86 @@
+/* deepaco_b200 -- C ABI of the B200-native DeepACO rollout engine (libdeepaco_b200.so).
+ *
+ * The reference (henry-yeh/DeepACO) has no FFI of its own: its boundary is the duck-typed Python
+ * class `ACO` of each problem directory.  Every entry point below replaces the ATen call sequence
+ * of one reference method; the Python classes in deepaco_b200/{tsp,tsp_nls,cvrp}/aco.py bind them
+ * with ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - matrices are dense row-major fp32, batched over `n_colonies` independent instances:
+ *       pheromone / heuristic / distances : [n_colonies][n][n]
+ *       paths  (reference layout)          : [n_colonies][n_rows][n_ants] int64, step-major
+ *       tours  (compact layout)            : [n_colonies][n_ants][n] uint16, ant-major
+ *   - return value 0 on success, negative DEEPACO_E* otherwise; deepaco_last_error() gives the text;
+ *   - no call synchronises the device unless documented ("host" entry points do).
+ */
+#ifndef DEEPACO_B200_H_
+#define DEEPACO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEEPACO_OK 0
+#define DEEPACO_EINVAL (-1)   /* bad argument / unsupported size */
+#define DEEPACO_ECUDA (-2)    /* CUDA runtime error */
+#define DEEPACO_ENODEV (-3)   /* no sm_100 device */
+
+#define DEEPACO_MAX_NODES 1024 /* largest n the sampling kernels are instantiated for */
+
+const char* deepaco_last_error(void);
+int deepaco_version(void);
+
+/* Geometry of torch's Philox draw for a tensor of `numel` elements on the current device
+ * (ATen/native/cuda/DistributionTemplates.h:50-62): returns grid*256 threads and the generator
+ * offset increment one such draw consumes.  Host helper, no device work. */
+int deepaco_torch_draw_geometry(int64_t numel, uint32_t* threads_out, uint64_t* offset_increment_out);
+
+/* block_width ATen picks for sum(x[n_rows][row_len], dim=-1) (ATen/native/cuda/Reduce.cuh
+ * setReduceConfig); the kernels reproduce that summation order.  *exact_out = 1 when the order is
+ * reproduced exactly for this shape. */
+int deepaco_aten_sum_plan(int row_len, int n_rows, int* block_width_out, int* vectorized_out, int* exact_out);
+
+/* ---- tour construction ----------------------------------------------------------------------
+ * Replaces ACO.gen_path + pick_move: tsp/aco.py:134-177 (start_node = -1, double_norm = 0) and
+ * tsp_nls/aco.py:184-220 (start_node = 0, double_norm = 1).
+ * Noise: when `noise` is NULL the kernel regenerates, in registers, exactly the Philox words torch's
+ * `randint` / `exponential_` kernels would draw from (seed, offset) -- per colony from rng[b] =
+ * {seed, offset} (device, may be NULL) else from the by-value pair.  The caller advances its
+ * generator by deepaco_tsp_sample_offset_increment().
+ * With `noise` != NULL ([B][n-1][A][n] Exp(1) draws) and `start` ([B][A], or start_node >= 0) the
+ * result is a pure function of its inputs (cross-device parity mode).
+ * Outputs (each may be NULL): paths int64 [B][n][A]; log_probs fp32 [B][n-1][A]; tours u16 [B][A][n]. */
+int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                       int start_node, int double_norm, uint64_t seed, uint64_t offset,
+                       const uint64_t* rng, const float* noise, const int64_t* start, int64_t* paths,
+                       float* log_probs, uint16_t* tours, void* stream);
+uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int start_node);
+
+/* ---- tour cost  (ACO.gen_path_costs, tsp/aco.py:120-132) --------------------------------------
+ * costs[b][a] = sum_k dist[u_k][u_{k-1}] in ATen's summation order.  Input tours either as
+ * `paths` (int64 [B][n][A]) or `tours` (u16 [B][A][n]); exactly one non-NULL.  `costs` may be NULL.  Optionally emits
+ * neighbours[b][u][a] = (pred << 16) | succ of node u in ant a's tour (uint32 [B][n][A]). */
+int deepaco_tsp_cost(const float* distances, const int64_t* paths, const uint16_t* tours, int n, int n_ants,
+                     int n_colonies, float* costs, uint32_t* neighbours, void* stream);
+
+/* ---- evaporate + deposit  (ACO.update_pheronome, tsp/aco.py:94-118) ---------------------------
+ * In place on `pheromone`.  Deposit order = ant order per matrix cell (bit-exact with the reference's
+ * sequential index_put loop).  elitist: only the first arg-min ant deposits.  min_max: clamp to
+ * [ph_min, ph_max[b]] afterwards (ph_max device fp32 [B]). */
+int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants,
+                       int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
+                       void* stream);
+
+/* ---- debug / probe entry points (used by tests to validate the torch-parity assumptions) ------ */
+int deepaco_debug_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out, void* stream);
+int deepaco_debug_randint(uint64_t seed, uint64_t offset, int64_t numel, int64_t high, int64_t* out, void* stream);
+int deepaco_debug_row_sum(const float* x, int n_rows, int row_len, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPACO_B200_H_ */
