@@ -114,6 +114,84 @@ def tsp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_m
     return pheromone
 
 
+# ---- CVRP -------------------------------------------------------------------------------------
+def cvrp_sample(pheromone, heuristic, demand, capacity, n_ants, *, seed=0, offset=0, rng=None, noise=None,
+                want_paths=True, want_logp=False, want_tours=False):
+    """deepaco_cvrp_sample -> dict(paths, logp, tours, lens, tmax); buffers have 2N rows (not yet sliced)."""
+    pheromone = f32c(require_cuda(pheromone, "pheromone"))
+    B, N = _colonies(pheromone)
+    dev = pheromone.device
+    if heuristic is not None:
+        heuristic = f32c(require_cuda(heuristic, "heuristic"))
+    demand = f32c(require_cuda(demand, "demand"))
+    if demand.numel() != B * N:
+        raise _lib.DeepAcoError("demand must hold n_nodes values per colony")
+    R = 2 * N
+    if noise is not None:
+        noise = f32c(require_cuda(noise, "noise"))
+        if noise.numel() != B * (R - 1) * n_ants * N:
+            raise _lib.DeepAcoError("noise must hold [B][2N-1][A][N] values")
+    paths = torch.empty((B, R, n_ants), dtype=torch.int64, device=dev) if want_paths else None
+    logp = torch.empty((B, R - 1, n_ants), dtype=torch.float32, device=dev) if want_logp else None
+    tours = torch.empty((B, n_ants, R), dtype=torch.uint16, device=dev) if want_tours else None
+    lens = torch.empty((B, n_ants), dtype=torch.int32, device=dev)
+    tmax = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().deepaco_cvrp_sample(ptr(pheromone), ptr(heuristic), ptr(demand), float(capacity), N, n_ants, B,
+                                        int(seed), int(offset), ptr(rng), ptr(noise), R, ptr(paths), ptr(logp),
+                                        ptr(tours), ptr(lens), ptr(tmax), stream_ptr(dev)), "deepaco_cvrp_sample")
+    return {"paths": paths, "logp": logp, "tours": tours, "lens": lens, "tmax": tmax, "batched": pheromone.dim() == 3}
+
+
+def cvrp_step_offset_increment(n_nodes, n_ants) -> int:
+    return int(lib().deepaco_cvrp_step_offset_increment(n_nodes, n_ants))
+
+
+def cvrp_cost(distances, paths=None, tours=None, *, tmax=None, T=None, want_costs=True, want_neighbours=False):
+    """deepaco_cvrp_cost.  paths: int64 [rows, A] | [B, rows, A]; tours: uint16 [A, rows] | [B, A, rows].
+    Path length either from the device tensor `tmax` ([B] int32) or the host int `T` (= rows - 1)."""
+    distances = f32c(require_cuda(distances, "distances"))
+    B, N = _colonies(distances)
+    batched = distances.dim() == 3
+    dev = distances.device
+    if (paths is None) == (tours is None):
+        raise _lib.DeepAcoError("pass exactly one of paths / tours")
+    if paths is not None:
+        paths = require_cuda(paths, "paths").to(torch.int64).contiguous()
+        rows_in, n_ants = paths.shape[-2], paths.shape[-1]
+    else:
+        tours = require_cuda(tours, "tours").contiguous()
+        n_ants, rows_in = tours.shape[-2], tours.shape[-1]
+    if tmax is None and T is None:
+        T = rows_in - 1
+    costs = torch.empty((B, n_ants), dtype=torch.float32, device=dev) if want_costs else None
+    nbr = torch.empty((B, N, n_ants), dtype=torch.int32, device=dev) if want_neighbours else None
+    with torch.cuda.device(dev):
+        check(lib().deepaco_cvrp_cost(ptr(distances), ptr(paths), ptr(tours), N, n_ants, B, rows_in, ptr(tmax),
+                                      int(T or 0), ptr(costs), ptr(nbr), stream_ptr(dev)), "deepaco_cvrp_cost")
+    if not batched:
+        costs = None if costs is None else costs[0]
+        nbr = None if nbr is None else nbr[0]
+    return costs, nbr
+
+
+def cvrp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_max=False, ph_min=0.0, ph_max=None):
+    require_cuda(pheromone, "pheromone")
+    if pheromone.dtype != torch.float32 or not pheromone.is_contiguous():
+        raise _lib.DeepAcoError("pheromone must be contiguous fp32 for the in-place update")
+    B, N = _colonies(pheromone)
+    n_ants = costs.shape[-1]
+    costs = f32c(costs)
+    dev = pheromone.device
+    if min_max:
+        ph_max = f32c(torch.as_tensor(ph_max, device=dev).reshape(-1))
+    with torch.cuda.device(dev):
+        check(lib().deepaco_cvrp_update(ptr(pheromone), ptr(neighbours), ptr(costs), N, n_ants, B, float(decay),
+                                        int(elitist), int(min_max), float(ph_min), ptr(ph_max) if min_max else None,
+                                        stream_ptr(dev)), "deepaco_cvrp_update")
+    return pheromone
+
+
 # ---- probes ------------------------------------------------------------------------------------
 def debug_exponential(seed, offset, numel, device):
     out = torch.empty((numel,), dtype=torch.float32, device=device)

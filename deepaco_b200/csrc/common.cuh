@@ -70,11 +70,51 @@ __device__ __forceinline__ uint32_t torch_philox_word(uint64_t seed, uint64_t of
     return comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w));
 }
 
+// Fast path used by the sampling kernels when every element of the draw is component .x of call 0
+// (numel <= grid*256, true for every configuration of BASELINE.json): the ten round keys are hoisted
+// by the caller, the subsequence fits 32 bits and only output word .x is produced (38 instructions).
+struct PhiloxRoundKeys {
+    uint32_t a[10], b[10];
+    __device__ __forceinline__ void init(uint64_t seed) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            a[r] = (uint32_t)seed + (uint32_t)r * kPhiloxW0;
+            b[r] = (uint32_t)(seed >> 32) + (uint32_t)r * kPhiloxW1;
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t philox_word_x(uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub, const PhiloxRoundKeys& K) {
+    uint32_t c0 = ctr_lo, c1 = ctr_hi, c2 = sub, c3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const uint32_t h0 = __umulhi(kPhiloxM0, c0), l0 = kPhiloxM0 * c0;
+        const uint32_t h1 = __umulhi(kPhiloxM1, c2), l1 = kPhiloxM1 * c2;
+        c0 = h1 ^ c1 ^ K.a[r];
+        c2 = h0 ^ c3 ^ K.b[r];
+        c1 = l1;
+        c3 = l0;
+    }
+    return __umulhi(kPhiloxM1, c2) ^ c1 ^ K.a[9];
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // curand_uniform (curand_uniform.h:69-72) followed by transformation::exponential, lambda = 1.
+// at::log<float> on device is the fast `__logf` (ATen/NumericUtils.h:149-160) = lg2.approx.f32 * ln2.
+// u >= 2^-33 is never denormal, so the .ftz form of the MUFU instruction returns the same bits without
+// the denormal pre-scaling code the non-ftz intrinsic expands to.
 __device__ __forceinline__ float exp1_from_word(uint32_t x) {
-    const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
-    const float lg = (u >= 1.0f - 1.1920928955078125e-07f / 2.0f) ? -(1.1920928955078125e-07f / 2.0f) : logf(u);
-    return (-1.0f / 1.0f) * lg;
+    const float u = fmaf((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f);   // product is exact: fma == mul + add
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+    const float lg = (u >= 1.0f - 1.1920928955078125e-07f / 2.0f) ? -(1.1920928955078125e-07f / 2.0f)
+                                                                   : __fmul_rn(l2, 0.693147182464599609375f);
+    return -lg;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -109,6 +149,52 @@ __device__ __forceinline__ float aten_sum_vec4(const float (&x)[EPL]) {
         for (int i = 0; i < 4; ++i) acc[i] = acc[i] + x[4 * m + i];
     }
     return warp_tree_sum(((acc[0] + acc[1]) + acc[2]) + acc[3]);
+}
+
+// Run-time-length version: ATen-ordered sum of f(k), k in [0, len), by one warp; result in every lane.
+// `vec` selects the vectorised order (len >= 128), `lbw` = log2(block_width) for the strided order.
+// `shift` = (element offset of the row start from a 16-byte boundary) & 3 -- ATen peels 4-shift head
+// elements into accumulator 0 of lanes shift..3 before the aligned float4 loop
+// (Reduce.cuh input_vectorized_thread_reduce_impl); rows of a fresh contiguous [rows][len] tensor have
+// shift = (row * len) & 3.
+template <typename F>
+__device__ __forceinline__ float aten_row_sum_fn(F f, int len, int lbw, bool vec, int lane, int shift = 0) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+        int head = 0, end = len;
+        if (shift > 0) {
+            if (lane >= shift && lane < 4) acc[0] = __fadd_rn(acc[0], f(lane - shift));
+            head = 4 - shift;
+            end = len - head;
+        }
+        for (int idx = lane; idx * 4 + 3 < end; idx += 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = __fadd_rn(acc[i], f(head + 4 * idx + i));
+        }
+        const int t = end - (end & 3) + lane;                       // ATen tail -> accumulator 0
+        if (t < end) acc[0] = __fadd_rn(acc[0], f(head + t));
+    } else if (lane < (1 << lbw)) {
+        int i = 0;
+        for (int k = lane; k < len; k += (1 << lbw), ++i) acc[i & 3] = __fadd_rn(acc[i & 3], f(k));
+    }
+    return warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
+}
+
+// Device copy of host aten_sum_plan() for row lengths only known on the device (CVRP path length).
+__device__ __forceinline__ void aten_sum_plan_dev(int row_len, int n_rows, int* lbw, int* vec) {
+    int dim0 = row_len;
+    *vec = row_len >= 128;
+    if (*vec) dim0 >>= 2;
+    auto lp2 = [](int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; };
+    const int d0 = dim0 < 512 ? lp2(dim0) : 512;
+    const int d1 = n_rows < 512 ? lp2(n_rows) : 512;
+    int bw = d0 < 32 ? d0 : 32;
+    const int bh = d1 < 512 / bw ? d1 : 512 / bw;
+    bw = d0 < 512 / bh ? d0 : 512 / bh;
+    if (bw > 32) bw = 32;   // wider blocks (n_rows < 16) are not reproduced exactly
+    int l = 0;
+    while ((1 << l) < bw) ++l;
+    *lbw = l;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,25 +15,12 @@ __global__ void debug_randint_kernel(uint64_t seed, uint64_t offset, int64_t num
         out[li] = (int64_t)(torch_philox_word(seed, offset, (uint64_t)li, g) % high);
 }
 
-template <typename F>
-__device__ __forceinline__ float row_sum_fn(F f, int len, int lbw, bool vec, int lane) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec) {
-        for (int base = 4 * lane; base + 3 < len; base += 128)
-            for (int i = 0; i < 4; ++i) acc[i] = __fadd_rn(acc[i], f(base + i));
-        if (lane < (len & 3)) acc[0] = __fadd_rn(acc[0], f(len - (len & 3) + lane));
-    } else if (lane < (1 << lbw)) {
-        int i = 0;
-        for (int k = lane; k < len; k += (1 << lbw), ++i) acc[i & 3] = __fadd_rn(acc[i & 3], f(k));
-    }
-    return warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
-}
-
 __global__ void debug_row_sum_kernel(const float* x, int rows, int len, int lbw, int vec, float* out) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
     const float* row = x + (size_t)r * len;
-    const float s = row_sum_fn([&](int k) { return row[k]; }, len, lbw, vec != 0, threadIdx.x & 31);
+    const float s = aten_row_sum_fn([&](int k) { return row[k]; }, len, lbw, vec != 0, threadIdx.x & 31,
+                                    vec ? (int)(((unsigned)r * (unsigned)len) & 3u) : 0);
     if ((threadIdx.x & 31) == 0) out[r] = s;
 }
 

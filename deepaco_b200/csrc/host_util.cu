@@ -61,7 +61,7 @@ SumPlan aten_sum_plan(int row_len, int n_rows) {
     sp.block_width = bw;
     const int vpt = (row_len + bw - 1) / bw;
     const bool split_warps = vpt >= std::min(bh * 16, 256);
-    sp.exact = !split_warps && bw <= 32 && (!sp.vectorized || row_len % 4 == 0);
+    sp.exact = !split_warps && bw <= 32;
     return sp;
 }
 

@@ -1,0 +1,307 @@
+// Tour-construction kernel shared by TSP and CVRP (included by tsp_sample.cu and cvrp.cu).
+//
+// One warp per ant.  The product matrix P = pheromone (.) heuristic of the ant's colony sits in shared
+// memory (TMA bulk copy per CTA).  The ant's candidate list (unvisited nodes; for CVRP slot 0 is the depot)
+// lives in REGISTERS: lane l owns slots l, l+32, ...; removing the chosen node moves the last list entry
+// into its slot.  Per step and candidate j the score is x_j / q_j with x_j = P[cur][j] and q_j the Exp(1)
+// variate torch's `exponential_` would have written at element (ant, j) of that step's [n_ants, n] draw
+// (Philox4x32-10 regenerated in registers).  Because q depends only on (step, ant, j) and not on the
+// previous choice, the reciprocal noise of step t+1 is computed while the warp reductions of step t are
+// in flight: the dependent chain per step is LDS -> FMUL -> REDUX -> VOTE -> SHFL.
+//
+// Exactness.  The reference takes argmax_j fl(fl(x_j / S) / q_j) (S = ATen row sum).  We rank by
+// A_j = x_j * rcp.approx(q_j) (relative error < 2^-21 against the reference value scaled by S) and accept
+// the top candidate only when no other lies within 2^-18 relative -- then the exactly-rounded ranking
+// provably has the same winner.  Otherwise (probability ~1e-6 per step, or an all-zero row) the step is
+// replayed by exact_step() with the reference's arithmetic.  S is computed only for log-probs.
+#pragma once
+#include "common.cuh"
+#include "sample_common.cuh"
+
+namespace deepaco {
+
+struct ListParams {
+    const float* ph;        // [B][n][n]
+    const float* heu;       // [B][n][n] or null (then `ph` already is the product)
+    int n, A, B;
+    int rows;               // rows of the path buffers: n (TSP) or 2n (CVRP)
+    int start_node;         // TSP: >= 0 fixed start; -1 -> `start` tensor or torch randint stream
+    int double_norm;        // TSP-NLS pre-normalisation
+    uint64_t seed, offset;
+    const uint64_t* rng;    // [B][2] or null
+    const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
+    const int64_t* start;   // [B][A] or null
+    int64_t* paths;         // [B][rows][A] or null
+    float* logp;            // [B][rows-1][A] or null
+    uint16_t* tours;        // [B][A][rows] or null
+    int32_t* lens;          // CVRP [B][A]
+    int32_t* tmax;          // CVRP [B]
+    const float* demand;    // CVRP [B][n]
+    float capacity;
+    int lbw, vec;           // ATen summation plan for a length-n row
+    DrawGeom g_noise, g_start;
+    uint32_t start_increment, step_increment;
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+
+// reciprocal Exp(1) noise of element `sub` of the draw at Philox counter (ctr_lo, ctr_hi)
+__device__ __forceinline__ float noise_rcp(uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub, const PhiloxRoundKeys& K) {
+    return rcp_approx(exp1_from_word(philox_word_x(ctr_lo, ctr_hi, sub, K)));
+}
+
+template <int EPL, bool CVRP, bool WANT_LOGP>
+__global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const int n = p.n, R = p.rows;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int W = nthreads >> 5, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int a0 = blockIdx.x * W;
+    const int a = a0 + warp;
+    // shared layout: P [n*n f32] | demand [n f32] (CVRP) | tours [W][R] u16 | cand [W][n] u16 | alive [W][32] u32
+    float* Psm = reinterpret_cast<float*>(smem);
+    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
+    const size_t dbytes = CVRP ? ((((size_t)n * 4) + 15) & ~(size_t)15) : 0;
+    float* dem = reinterpret_cast<float*>(smem + pbytes);
+    uint16_t* tour_all = reinterpret_cast<uint16_t*>(smem + pbytes + dbytes);
+    uint16_t* cand_all = tour_all + (size_t)W * R;
+    uint32_t* alive_all = reinterpret_cast<uint32_t*>(smem + pbytes + dbytes + (((size_t)W * (R + n) * 2 + 15) & ~(size_t)15));
+    uint16_t* tour_sm = tour_all + (size_t)warp * R;
+    uint32_t* alive = alive_all + warp * 32;
+    const uint32_t P_addr = smem_u32(Psm);
+    const uint32_t dem_addr = smem_u32(dem);
+    const uint32_t cand_addr = smem_u32(cand_all + (size_t)warp * n);
+    const uint32_t tour_addr = smem_u32(tour_sm);
+
+    if (CVRP)
+        for (int i = tid; i < n; i += nthreads) dem[i] = p.demand[(size_t)b * n + i];
+    stage_product(Psm, p.ph, p.heu, n, b, &bar);   // ends with __syncthreads()
+
+    if (a < p.A) {
+        const uint64_t seed = p.rng ? p.rng[2 * b] : p.seed;
+        const uint64_t offset0 = p.rng ? p.rng[2 * b + 1] : p.offset;
+        PhiloxRoundKeys K;
+        K.init(seed);
+        const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
+        const float eps = 1.1920928955078125e-07f;
+        const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
+
+        int cur = 0;
+        uint64_t off_noise = offset0;
+        if (!CVRP) {
+            if (p.start_node >= 0) {
+                cur = p.start_node;
+            } else if (p.start) {
+                cur = (int)p.start[(size_t)b * p.A + a];
+            } else {
+                // torch.randint(0, n, (A,)): element a <- curand4().x % n  (random_from_to_kernel, 32-bit branch)
+                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
+                off_noise += p.start_increment;
+            }
+        }
+        // candidate list: TSP = all nodes but the start (index order); CVRP = depot in slot 0, then customers
+        int cnt = CVRP ? n : n - 1;
+        uint32_t cj[EPL];
+        float r[EPL];
+        const uint32_t ctr0_lo = (uint32_t)(off_noise >> 2), ctr0_hi = (uint32_t)(off_noise >> 34);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int s = lane + 32 * k;
+            cj[k] = CVRP ? (uint32_t)s : (uint32_t)(s < cur ? s : s + 1);
+            if (s < cnt) sts_u16(cand_addr + 2 * s, cj[k]);
+            r[k] = 0.f;
+            if (s < cnt && !p.noise) r[k] = noise_rcp(ctr0_lo, ctr0_hi, sub_base + cj[k], K);
+        }
+        if (WANT_LOGP && !CVRP) {
+            uint32_t m = 0;
+            for (int k = 0; k < 32; ++k) {
+                const int j = lane * 32 + k;
+                if (j < n && j != cur) m |= 1u << k;
+            }
+            alive[lane] = m;
+        }
+        if (lane == 0) sts_u16(tour_addr, (uint32_t)cur);
+        __syncwarp();
+
+        float used = 0.f;
+        if (CVRP) used = __fadd_rn(0.f, lds_f32(dem_addr));   // update_capacity_mask(cur = depot)
+        int step = 0;
+        const int max_steps = R - 1;
+#pragma unroll 1
+        while (CVRP ? (!(cnt == 1 && cur == 0) && step < max_steps) : (step < n - 1)) {
+            const uint32_t row_addr = P_addr + (uint32_t)cur * (uint32_t)n * 4u;
+            const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
+            const float* nz = p.noise ? p.noise + (((size_t)b * (R - 1) + step) * p.A + a) * (size_t)n : nullptr;
+            const uint32_t lastj = lds_u16(cand_addr + 2 * (cnt - 1));   // entry that fills the freed slot
+            const float remaining = CVRP ? __fsub_rn(p.capacity, used) : 0.f;
+            const bool depot_ok = CVRP && ((cur != 0) || (cnt == 1));
+
+            // ---- scores of this step
+            float bestA = 0.f, second = 0.f, bestx = 0.f;
+            uint32_t bestsj = 0xffffffffu;   // (slot << 16) | node
+            bool okk[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const int s = lane + 32 * k;
+                bool ok = s < cnt;
+                if (CVRP && ok) ok = (s == 0) ? depot_ok : !(lds_f32(dem_addr + 4 * cj[k]) > remaining);
+                okk[k] = ok;
+                const float x = ok ? lds_f32(row_addr + 4 * cj[k]) : 0.f;
+                const float rr = nz ? (ok ? rcp_approx(nz[cj[k]]) : 0.f) : r[k];
+                const float A = __fmul_rn(x, rr);
+                if (A > bestA) {
+                    second = bestA;
+                    bestA = A;
+                    bestsj = ((uint32_t)s << 16) | cj[k];
+                    bestx = x;
+                } else if (A > second) {
+                    second = A;
+                }
+            }
+            const uint32_t mybits = __float_as_uint(bestA);
+            const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+
+            // ---- noise of the NEXT step for the current list (independent of this step's outcome)
+            float rn[EPL];
+            {
+                const uint64_t off_next = off_step + p.step_increment;
+                const uint32_t nlo = (uint32_t)(off_next >> 2), nhi = (uint32_t)(off_next >> 34);
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) {
+                    rn[k] = 0.f;
+                    if (32 * k < cnt && !p.noise) rn[k] = noise_rcp(nlo, nhi, sub_base + cj[k], K);
+                }
+            }
+            const int kl = (cnt - 1) >> 5;
+            float lastr = 0.f;
+#pragma unroll
+            for (int k = 0; k < EPL; ++k)
+                if (k == kl) lastr = __shfl_sync(DACO_FULL, rn[k], (cnt - 1) & 31);
+
+            const float thr = __fmul_rn(__uint_as_float(topbits), kGap);
+            const bool is_top = mybits == topbits;
+            const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
+            const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
+            uint32_t jstar, sstar;
+            float pn_win = 0.f;
+            const bool need_exact = (nears != 0u) || (__popc(tops) != 1);
+            if (need_exact || (WANT_LOGP && CVRP)) {
+                // bitmap of this step's admissible nodes
+                alive[lane] = 0u;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < EPL; ++k)
+                    if (okk[k]) atomicOr(&alive[cj[k] >> 5], 1u << (cj[k] & 31));
+                __syncwarp();
+            }
+            if (need_exact) {
+                jstar = exact_step(Psm + (size_t)cur * n, alive, n, p.lbw, p.vec, p.double_norm, nz, seed, off_step,
+                                   sub_base, p.g_noise, &pn_win);
+                uint32_t found = 0;
+#pragma unroll
+                for (int k = 0; k < EPL; ++k)
+                    if (lane + 32 * k < cnt && cj[k] == jstar) found = (uint32_t)(lane + 32 * k) + 1;
+                sstar = __reduce_max_sync(DACO_FULL, found);
+                // an all-masked argmax can land on a visited node (reference quirk): leave the list untouched
+                sstar = sstar ? sstar - 1 : 0xffffffffu;
+            } else {
+                const int winner = __ffs(tops) - 1;
+                const uint32_t sj = __shfl_sync(DACO_FULL, bestsj, winner);
+                jstar = sj & 0xffffu;
+                sstar = sj >> 16;
+                if (WANT_LOGP) {
+                    const float* row = Psm + (size_t)cur * n;
+                    auto xval = [&](int k) -> float { return ((alive[k >> 5] >> (k & 31)) & 1u) ? row[k] : 0.f; };
+                    const int shift = p.vec ? (int)(sub_base & 3u) : 0;
+                    const float S = aten_row_sum_fn(xval, n, p.lbw, p.vec != 0, lane, shift);
+                    float pn = __fdiv_rn(__shfl_sync(DACO_FULL, bestx, winner), S);
+                    if (p.double_norm) {
+                        const float S2 = aten_row_sum_fn([&](int k) { return __fdiv_rn(xval(k), S); }, n, p.lbw,
+                                                         p.vec != 0, lane, shift);
+                        pn = __fdiv_rn(pn, S2);
+                    }
+                    pn_win = pn;
+                }
+            }
+            if (WANT_LOGP && lane == 0)   // Categorical.log_prob: log(clamp(probs, eps, 1 - eps))[action]
+                p.logp[((size_t)b * (R - 1) + step) * p.A + a] = logf(fminf(fmaxf(pn_win, eps), 1.0f - eps));
+
+            // ---- state update
+            bool remove = sstar < (uint32_t)cnt;
+            if (CVRP) {
+                if (jstar == 0u) {
+                    used = __fadd_rn(0.f, lds_f32(dem_addr));
+                    remove = false;
+                } else {
+                    used = __fadd_rn(used, lds_f32(dem_addr + 4 * jstar));
+                }
+            }
+            if (remove) {
+#pragma unroll
+                for (int k = 0; k < EPL; ++k)
+                    if ((uint32_t)(lane + 32 * k) == sstar) {
+                        cj[k] = lastj;
+                        rn[k] = lastr;
+                    }
+                if (lane == 0) sts_u16(cand_addr + 2 * sstar, lastj);
+                --cnt;
+                if (WANT_LOGP && !CVRP && lane == 0) alive[jstar >> 5] &= ~(1u << (jstar & 31));
+            }
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) r[k] = rn[k];
+            ++step;
+            if (lane == 0) sts_u16(tour_addr + 2 * step, jstar);
+            __syncwarp();
+            cur = (int)jstar;
+        }
+        if (CVRP) {
+            // finished ants sit at the depot; the reference keeps drawing node 0 with probability exactly 1
+            for (int k = step + 1 + lane; k < R; k += 32) sts_u16(tour_addr + 2 * k, 0u);
+            if (WANT_LOGP) {
+                const float lp1 = logf(1.0f - eps);
+                for (int k = step + lane; k < R - 1; k += 32) p.logp[((size_t)b * (R - 1) + k) * p.A + a] = lp1;
+            }
+            if (lane == 0) {
+                p.lens[(size_t)b * p.A + a] = step;
+                atomicMax(&p.tmax[b], step);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- cooperative output: reference layout paths[b][s][a] (int64, step-major) and compact tours
+    const int wvalid = min(W, p.A - a0);
+    if (p.paths) {
+        int64_t* out = p.paths + (size_t)b * R * p.A;
+        for (int i = tid; i < R * W; i += nthreads) {
+            const int s = i / W, w = i - s * W;
+            if (w < wvalid) out[(size_t)s * p.A + a0 + w] = (int64_t)tour_all[(size_t)w * R + s];
+        }
+    }
+    if (p.tours) {
+        uint16_t* out = p.tours + ((size_t)b * p.A + a0) * R;
+        for (int i = tid; i < R * wvalid; i += nthreads) out[i] = tour_all[i];
+    }
+}
+
+inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp) {
+    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
+    const size_t dbytes = cvrp ? ((((size_t)n * 4) + 15) & ~(size_t)15) : 0;
+    return pbytes + dbytes + (((size_t)W * (rows + n) * 2 + 15) & ~(size_t)15) + (size_t)W * 128;
+}
+
+}  // namespace deepaco

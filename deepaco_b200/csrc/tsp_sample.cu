@@ -4,11 +4,23 @@
 // fixed-start variant tsp_nls/aco.py:184-220): per step the reference gathers the pheromone and
 // heuristic rows of the current node, multiplies them with the visited mask, normalises
 // (`Categorical`), and draws with `torch.multinomial(probs, 1)` == argmax(probs / q), q ~ Exp(1)
-// from `exponential_`.  Here a warp owns an ant: the product matrix is staged once per CTA into shared
-// memory with TMA bulk copies, the row sum uses ATen's exact summation order (common.cuh), the Exp(1)
-// noise is regenerated in registers from torch's Philox stream, and arg-max is two warp REDUX ops.
+// from `exponential_`.
+//
+// Two kernels:
+//   tsp_sample_list_kernel  (n*n*4 bytes fit in shared memory, the benchmark sizes n <= ~230)
+//     The product matrix P = pheromone (.) heuristic is staged once per CTA into shared memory with
+//     TMA bulk copies.  Each warp keeps the list of its ant's unvisited nodes; per step only those
+//     are evaluated: Philox word -> Exp(1) noise in registers, score x/q.  The arg-max is decided on
+//     approximate scores (one MUFU.RCP + FMUL per candidate); the winner is certain -- identical to the
+//     reference's exactly rounded argmax((x/S)/q) -- unless a second candidate lies within 2^-18
+//     relative, in which case (probability ~1e-6 per step) the step is redone by exact_step() with
+//     ATen's exact arithmetic.  The row normaliser S is only computed when log-probs are requested.
+//   tsp_sample_dense_kernel (larger n: rows come from L2; also any draw geometry)
+//     Dense register layout, every step evaluated with the exact arithmetic.
 #include "common.cuh"
 #include "host_util.h"
+#include "sample_common.cuh"
+#include "list_kernel.cuh"
 
 #include <stdlib.h>
 
@@ -27,11 +39,15 @@ struct TspSampleParams {
     int64_t* paths;       // [B][n][A] or null
     float* logp;          // [B][n-1][A] or null
     uint16_t* tours;      // [B][A][n] or null
-    int lbw;              // log2(ATen block_width) for the strided layout
+    int lbw;              // log2(ATen block_width) for the strided summation order
+    int vec;              // ATen vectorised summation order (n >= 128)
     DrawGeom g_noise, g_start;
-    uint32_t start_increment;
+    uint32_t start_increment, step_increment;
 };
 
+// ---------------------------------------------------------------------------------------------
+// dense kernel (exact arithmetic every step)
+// ---------------------------------------------------------------------------------------------
 template <int EPL, bool VEC>
 __device__ __forceinline__ uint32_t elem_index(int k, int lane, int lbw) {
     if (VEC) return 4u * (uint32_t)(lane + 32 * (k >> 2)) + (uint32_t)(k & 3);
@@ -39,7 +55,7 @@ __device__ __forceinline__ uint32_t elem_index(int k, int lane, int lbw) {
 }
 
 template <int EPL, bool VEC, bool SMEMP>
-__global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p) {
+__global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSampleParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const int n = p.n;
@@ -54,33 +70,7 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
     uint16_t* tour_all = reinterpret_cast<uint16_t*>(smem + pbytes);
     uint16_t* tour_sm = tour_all + (size_t)warp * n;
 
-    if (SMEMP) {
-        // ---- stage P = pheromone (.) heuristic of colony b into shared memory (TMA bulk + mbarrier)
-        const float* src = p.ph + (size_t)b * nn;
-        const uint32_t total = (uint32_t)(nn * 4);
-        const uint32_t bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (total & ~15u) : 0u;
-        if (tid == 0) {
-            mbar_init(&bar, 1);
-            fence_barrier_init();
-        }
-        __syncthreads();
-        if (tid == 0 && bulk) {
-            mbar_expect_tx(&bar, bulk);
-            constexpr uint32_t kChunk = 32768;
-            for (uint32_t off = 0; off < bulk; off += kChunk) {
-                const uint32_t sz = (bulk - off < kChunk) ? (bulk - off) : kChunk;
-                tma_bulk_g2s(reinterpret_cast<char*>(Psm) + off, reinterpret_cast<const char*>(src) + off, sz, &bar);
-            }
-        }
-        for (size_t i = bulk / 4 + tid; i < nn; i += nthreads) Psm[i] = src[i];
-        if (bulk) mbar_wait(&bar, 0);
-        __syncthreads();
-        if (p.heu) {
-            const float* h = p.heu + (size_t)b * nn;
-            for (size_t i = tid; i < nn; i += nthreads) Psm[i] = __fmul_rn(Psm[i], __ldg(h + i));
-            __syncthreads();
-        }
-    }
+    if (SMEMP) stage_product(Psm, p.ph, p.heu, n, b, &bar);
 
     if (a < p.A) {
         const int lbw = p.lbw;
@@ -96,7 +86,6 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
         } else if (p.start) {
             cur = (int)p.start[(size_t)b * p.A + a];
         } else {
-            // torch.randint(0, n, (A,)): element a <- curand4().x % n  (random_from_to_kernel, 32-bit branch)
             cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
             off_noise += p.start_increment;
         }
@@ -107,6 +96,7 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
             if (elem_index<EPL, VEC>(k, lane, lbw) == (uint32_t)cur && lane_on) vis |= 1u << k;
         if (lane == 0) tour_sm[0] = (uint16_t)cur;
 
+#pragma unroll 1
         for (int step = 0; step < n - 1; ++step) {
             const float* row = Pg + (size_t)cur * n;
             float x[EPL];
@@ -139,7 +129,7 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
 
             float best = 0.f, bestp = 0.f;
             uint32_t bestj = 0xffffffffu;
-            const uint64_t off_step = off_noise + 4ull * (uint64_t)step;
+            const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
             const float* nz = p.noise ? p.noise + (((size_t)b * (n - 1) + step) * p.A + a) * (size_t)n : nullptr;
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
@@ -158,10 +148,8 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
             }
             const uint32_t jstar = warp_argmax_nonneg(best, bestj);
             if (p.logp && bestj == jstar) {
-                // Categorical.log_prob: log(clamp(probs, eps, 1 - eps))[action]
                 const float eps = 1.1920928955078125e-07f;
-                const float c = fminf(fmaxf(bestp, eps), 1.0f - eps);
-                p.logp[((size_t)b * (n - 1) + step) * p.A + a] = logf(c);
+                p.logp[((size_t)b * (n - 1) + step) * p.A + a] = logf(fminf(fmaxf(bestp, eps), 1.0f - eps));
             }
             if (lane == 0) tour_sm[step + 1] = (uint16_t)jstar;
 #pragma unroll
@@ -172,7 +160,6 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
     }
     __syncthreads();
 
-    // ---- cooperative output: reference layout paths[b][s][a] (int64, step-major) and compact tours
     const int wvalid = min(W, p.A - a0);
     if (p.paths) {
         int64_t* out = p.paths + (size_t)b * n * p.A;
@@ -187,9 +174,8 @@ __global__ void __launch_bounds__(512) tsp_sample_kernel(const TspSampleParams p
     }
 }
 
-template <int EPL, bool VEC, bool SMEMP>
-static int launch_variant(const TspSampleParams& p, int W, size_t smem, cudaStream_t st) {
-    auto kfn = tsp_sample_kernel<EPL, VEC, SMEMP>;
+template <typename KFn, typename P>
+static int launch_kernel(KFn kfn, const P& p, int W, size_t smem, cudaStream_t st) {
     DACO_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((p.A + W - 1) / W, p.B);
     kfn<<<grid, W * 32, smem, st>>>(p);
@@ -244,16 +230,13 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
     int lbw = 0;
     while ((1 << lbw) < bw) ++lbw;
     p.lbw = lbw;
+    p.vec = sp.vectorized ? 1 : 0;   // runtime ATen sums handle n % 4 != 0 through the row shift
     const DrawPlan dn = torch_draw_plan((int64_t)n_ants * n, *di);
     const DrawPlan ds = torch_draw_plan(n_ants, *di);
     p.g_noise = {dn.threads, dn.single};
     p.g_start = {ds.threads, ds.single};
     p.start_increment = (uint32_t)ds.increment;
-
-    int epl_needed = vec ? 4 * ((n + 127) / 128) : (n + bw - 1) / bw;
-    int epl = vec ? 8 : 1;
-    while (epl < epl_needed) epl *= 2;
-    DACO_CHECK_ARG(epl <= 32, "deepaco_tsp_sample: n=%d needs %d elements per lane (max 32)", n, epl);
+    p.step_increment = (uint32_t)dn.increment;
 
     // warps per CTA: one warp per SM sub-partition while the job is small, 8-16 when it is not
     const long total_ants = (long)n_ants * n_colonies;
@@ -263,15 +246,40 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
         if (w >= 1 && w <= 16) W = w;
     }
     const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
-    size_t smem = pbytes + (size_t)W * n * 2;
-    bool smemp = smem + 1024 <= (size_t)di->max_smem_optin;
-    if (smemp && W < 16 && total_ants > (long)di->sm_count * 4) {
+    auto list_smem = [&](int w) { return list_kernel_smem(n, n, w, false); };
+    const size_t cap = (size_t)di->max_smem_optin - 1024;
+    const bool force_dense = getenv("DEEPACO_TSP_DENSE") != nullptr;
+    if (!force_dense && dn.single && (uint64_t)n_ants * n < (1ull << 32) && n <= 256 && list_smem(W) <= cap) {
         // keep >= 32 resident warps per SM when shared memory allows only few CTAs
-        const size_t per_sm = (size_t)di->max_smem_optin;
-        while (W < 16 && (per_sm / (pbytes + (size_t)W * n * 2 + 1024)) * W < 32) W *= 2;
-        smem = pbytes + (size_t)W * n * 2;
-        smemp = smem + 1024 <= per_sm;
+        if (total_ants > (long)di->sm_count * 4)
+            while (W < 16 && (cap / list_smem(W)) * W < 32 && list_smem(W * 2) <= cap) W *= 2;
+        ListParams q{};
+        q.ph = pheromone; q.heu = heuristic; q.n = n; q.A = n_ants; q.B = n_colonies; q.rows = n;
+        q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.rng = rng;
+        q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
+        q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
+        q.start_increment = p.start_increment; q.step_increment = p.step_increment;
+        const int epl = (n - 1 + 31) / 32;
+        const size_t sm = list_smem(W);
+#define DACO_LIST(E)                                                                            \
+        do {                                                                                    \
+            if (log_probs) return launch_kernel(aco_list_kernel<E, false, true>, q, W, sm, st); \
+            return launch_kernel(aco_list_kernel<E, false, false>, q, W, sm, st);               \
+        } while (0)
+        if (epl <= 1) DACO_LIST(1);
+        if (epl <= 2) DACO_LIST(2);
+        if (epl <= 4) DACO_LIST(4);
+        DACO_LIST(8);
+#undef DACO_LIST
     }
+
+    // ---- dense exact kernel
+    int epl_needed = vec ? 4 * ((n + 127) / 128) : (n + bw - 1) / bw;
+    int epl = vec ? 8 : 1;
+    while (epl < epl_needed) epl *= 2;
+    DACO_CHECK_ARG(epl <= 32, "deepaco_tsp_sample: n=%d needs %d elements per lane (max 32)", n, epl);
+    size_t smem = pbytes + (size_t)W * n * 2;
+    bool smemp = smem <= cap;
     if (!smemp) {
         smem = (size_t)W * n * 2;
         if (heuristic) {   // product once per call into a scratch matrix, rows then come from L2
@@ -289,7 +297,7 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
         }
     }
 
-#define DACO_LAUNCH(E, V, S) return launch_variant<E, V, S>(p, W, smem, st)
+#define DACO_LAUNCH(E, V, S) return launch_kernel(tsp_sample_dense_kernel<E, V, S>, p, W, smem, st)
     if (vec) {
         if (epl == 8) { if (smemp) DACO_LAUNCH(8, true, true); else DACO_LAUNCH(8, true, false); }
         if (epl == 16) DACO_LAUNCH(16, true, false);

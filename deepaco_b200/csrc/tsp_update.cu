@@ -22,24 +22,6 @@ struct TourView {
     }
 };
 
-// ATen-ordered sum of f(k), k in [0, len): one warp, result in every lane
-template <typename F>
-__device__ __forceinline__ float aten_row_sum_fn(F f, int len, int lbw, bool vec, int lane) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec) {
-        for (int base = 4 * lane; base + 3 < len; base += 128) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = __fadd_rn(acc[i], f(base + i));
-        }
-        const int tail = len - (len & 3) + lane;   // ATen tail handling (len % 4 leftovers -> acc[0])
-        if (lane < (len & 3)) acc[0] = __fadd_rn(acc[0], f(tail));
-    } else if (lane < (1 << lbw)) {
-        int i = 0;
-        for (int k = lane; k < len; k += (1 << lbw), ++i) acc[i & 3] = __fadd_rn(acc[i & 3], f(k));
-    }
-    return warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
-}
-
 __global__ void __launch_bounds__(256) tsp_cost_kernel(const float* __restrict__ dist, const int64_t* __restrict__ paths,
                                                        const uint16_t* __restrict__ tours, int n, int A, int lbw, int vec,
                                                        float* __restrict__ costs, uint32_t* __restrict__ nbr) {
@@ -55,7 +37,7 @@ __global__ void __launch_bounds__(256) tsp_cost_kernel(const float* __restrict__
         return __ldg(D + (size_t)u * n + v);
     };
     if (costs) {
-        const float c = aten_row_sum_fn(edge, n, lbw, vec != 0, lane);
+        const float c = aten_row_sum_fn(edge, n, lbw, vec != 0, lane, vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
         if (lane == 0) costs[(size_t)b * A + a] = c;
     }
     if (nbr) {

@@ -75,6 +75,34 @@ int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, const float
                        int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
                        void* stream);
 
+/* ---- CVRP (cvrp/aco.py:106-205, adaptive = False) ----------------------------------------------
+ * Node 0 is the depot; n_nodes = customers + 1; demand fp32 [B][n_nodes] (demand[0] = 0).
+ * deepaco_cvrp_sample replaces ACO.gen_path + pick_move + update_visit_mask + update_capacity_mask +
+ * check_done (cvrp/aco.py:138-205).  Path buffers have path_rows = 2 * n_nodes rows (upper bound of the
+ * data-dependent length); rows past an ant's end are 0.  lens[b][a] = steps the ant took, tmax[b] = max over
+ * ants = (rows of the reference's `paths`) - 1.  The reference consumes one [n_ants, n_nodes] exponential_
+ * draw per step until the slowest ant is done: advance the generator by tmax * step_offset_increment.
+ * noise (optional): [B][path_rows-1][n_ants][n_nodes]. */
+int deepaco_cvrp_sample(const float* pheromone, const float* heuristic, const float* demand, float capacity,
+                        int n_nodes, int n_ants, int n_colonies, uint64_t seed, uint64_t offset,
+                        const uint64_t* rng, const float* noise, int path_rows, int64_t* paths,
+                        float* log_probs, uint16_t* tours, int32_t* lens, int32_t* tmax, void* stream);
+uint64_t deepaco_cvrp_step_offset_increment(int n_nodes, int n_ants);
+
+/* ACO.gen_path_costs (cvrp/aco.py:132-136): costs[b][a] = sum_{k<T} dist[u_k][u_{k+1}] over the padded
+ * path, T = tmax[b] (device) or T_fixed when tmax is NULL; rows_in = rows of the supplied paths/tours.
+ * neighbours (uint32 [B][n_nodes][n_ants], optional): per customer (pred << 16) | succ; row 0 = 1 if the
+ * ant's padded path contains a (0,0) pair. */
+int deepaco_cvrp_cost(const float* distances, const int64_t* paths, const uint16_t* tours, int n_nodes,
+                      int n_ants, int n_colonies, int rows_in, const int32_t* tmax, int T_fixed, float* costs,
+                      uint32_t* neighbours, void* stream);
+
+/* ACO.update_pheronome (cvrp/aco.py:106-130): in place; one-directional deposit in ant order, repeated
+ * (0,0) pairs count once per ant, optional min_max clamp, final floor at 1e-10. */
+int deepaco_cvrp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n_nodes, int n_ants,
+                        int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
+                        void* stream);
+
 /* ---- debug / probe entry points (used by tests to validate the torch-parity assumptions) ------ */
 int deepaco_debug_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out, void* stream);
 int deepaco_debug_randint(uint64_t seed, uint64_t offset, int64_t numel, int64_t high, int64_t* out, void* stream);
