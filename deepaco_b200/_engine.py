@@ -22,13 +22,23 @@ def _colonies(mat: torch.Tensor):
     raise _lib.DeepAcoError(f"expected [n,n] or [B,n,n] matrix, got shape {tuple(mat.shape)}")
 
 
+def _offsets(offsets, B, dev):
+    """Per-colony Philox offsets as a device int64 [B] tensor (None -> NULL: by-value offset for all)."""
+    if offsets is None:
+        return None
+    t = torch.as_tensor(offsets, dtype=torch.int64, device=dev).contiguous()
+    if t.numel() != B:
+        raise _lib.DeepAcoError(f"offsets must hold one Philox offset per colony ({B})")
+    return t
+
+
 def aten_sum_plan(row_len: int, n_rows: int):
     bw, vec, exact = C.c_int(), C.c_int(), C.c_int()
     check(lib().deepaco_aten_sum_plan(row_len, n_rows, C.byref(bw), C.byref(vec), C.byref(exact)), "aten_sum_plan")
     return bw.value, bool(vec.value), bool(exact.value)
 
 
-def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False, seed=0, offset=0, rng=None,
+def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False, seed=0, offset=0, offsets=None,
                noise=None, start=None, want_paths=True, want_logp=False, want_tours=False):
     """deepaco_tsp_sample.  Returns (paths|None, log_probs|None, tours|None) shaped like the inputs'
     batching: single colony -> paths [n, A]; batched -> [B, n, A]."""
@@ -51,7 +61,7 @@ def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False
     tours = torch.empty((B, n_ants, n), dtype=torch.uint16, device=dev) if want_tours else None
     with torch.cuda.device(dev):
         check(lib().deepaco_tsp_sample(ptr(pheromone), ptr(heuristic), n, n_ants, B, int(start_node), int(double_norm),
-                                       int(seed), int(offset), ptr(rng), ptr(noise), ptr(start), ptr(paths), ptr(logp),
+                                       int(seed), int(offset), ptr(_offsets(offsets, B, dev)), ptr(noise), ptr(start), ptr(paths), ptr(logp),
                                        ptr(tours), stream_ptr(dev)), "deepaco_tsp_sample")
     if not batched:
         paths = None if paths is None else paths[0]
@@ -115,7 +125,7 @@ def tsp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_m
 
 
 # ---- CVRP -------------------------------------------------------------------------------------
-def cvrp_sample(pheromone, heuristic, demand, capacity, n_ants, *, seed=0, offset=0, rng=None, noise=None,
+def cvrp_sample(pheromone, heuristic, demand, capacity, n_ants, *, seed=0, offset=0, offsets=None, noise=None,
                 want_paths=True, want_logp=False, want_tours=False):
     """deepaco_cvrp_sample -> dict(paths, logp, tours, lens, tmax); buffers have 2N rows (not yet sliced)."""
     pheromone = f32c(require_cuda(pheromone, "pheromone"))
@@ -138,7 +148,7 @@ def cvrp_sample(pheromone, heuristic, demand, capacity, n_ants, *, seed=0, offse
     tmax = torch.empty((B,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(lib().deepaco_cvrp_sample(ptr(pheromone), ptr(heuristic), ptr(demand), float(capacity), N, n_ants, B,
-                                        int(seed), int(offset), ptr(rng), ptr(noise), R, ptr(paths), ptr(logp),
+                                        int(seed), int(offset), ptr(_offsets(offsets, B, dev)), ptr(noise), R, ptr(paths), ptr(logp),
                                         ptr(tours), ptr(lens), ptr(tmax), stream_ptr(dev)), "deepaco_cvrp_sample")
     return {"paths": paths, "logp": logp, "tours": tours, "lens": lens, "tmax": tmax, "batched": pheromone.dim() == 3}
 

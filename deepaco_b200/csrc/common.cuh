@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t torch_philox_word(uint64_t seed, uint64_t of
 // by the caller, the subsequence fits 32 bits and only output word .x is produced (38 instructions).
 struct PhiloxRoundKeys {
     uint32_t a[10], b[10];
-    __device__ __forceinline__ void init(uint64_t seed) {
+    __host__ __device__ __forceinline__ void init(uint64_t seed) {
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
             a[r] = (uint32_t)seed + (uint32_t)r * kPhiloxW0;

@@ -133,7 +133,7 @@ using namespace deepaco;
 
 extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristic, const float* demand, float capacity,
                                    int n_nodes, int n_ants, int n_colonies, uint64_t seed, uint64_t offset,
-                                   const uint64_t* rng, const float* noise, int path_rows, int64_t* paths,
+                                   const uint64_t* offsets, const float* noise, int path_rows, int64_t* paths,
                                    float* log_probs, uint16_t* tours, int32_t* lens, int32_t* tmax, void* stream) {
     const DeviceInfo* di = device_info();
     if (!di) return DEEPACO_ENODEV;
@@ -145,7 +145,8 @@ extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristi
     p.ph = pheromone; p.heu = heuristic; p.demand = demand; p.capacity = capacity;
     p.n = n_nodes; p.A = n_ants; p.B = n_colonies; p.rows = path_rows;
     p.start_node = 0; p.double_norm = 0;
-    p.seed = seed; p.offset = offset; p.rng = rng; p.noise = noise;
+    p.seed = seed; p.offset = offset; p.offsets = offsets; p.noise = noise;
+    p.keys.init(seed);
     p.paths = paths; p.logp = log_probs; p.tours = tours; p.lens = lens; p.tmax = tmax;
     const SumPlan sp = aten_sum_plan(n_nodes, n_ants);
     int bw = sp.block_width > 32 ? 32 : sp.block_width, lbw = 0;
@@ -173,22 +174,28 @@ extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristi
     dim3 grid((n_ants + W - 1) / W, n_colonies);
     const int epl = (n_nodes + 31) / 32;
     const size_t sm = need(W);
-#define DACO_LIST(E)                                                                                                       \
-    do {                                                                                                                   \
-        if (log_probs) {                                                                                                   \
-            DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_list_kernel<E, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  \
-            aco_list_kernel<E, true, true><<<grid, W * 32, sm, st>>>(p);                                                   \
-        } else {                                                                                                           \
-            DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_list_kernel<E, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            aco_list_kernel<E, true, false><<<grid, W * 32, sm, st>>>(p);                                                  \
-        }                                                                                                                  \
-        DACO_CHECK_LAUNCH();                                                                                               \
-        return DEEPACO_OK;                                                                                                 \
+#define DACO_LAUNCH1(KFN)                                                                                          \
+    do {                                                                                                           \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(KFN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));          \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(KFN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        KFN<<<grid, W * 32, sm, st>>>(p);                                                                          \
+        DACO_CHECK_LAUNCH();                                                                                       \
+        return DEEPACO_OK;                                                                                         \
+    } while (0)
+#define DACO_LIST(E)                                                              \
+    do {                                                                          \
+        if (noise) {                                                              \
+            if (log_probs) DACO_LAUNCH1((aco_list_kernel<E, true, true, true>));  \
+            DACO_LAUNCH1((aco_list_kernel<E, true, false, true>));                \
+        }                                                                         \
+        if (log_probs) DACO_LAUNCH1((aco_list_kernel<E, true, true, false>));     \
+        DACO_LAUNCH1((aco_list_kernel<E, true, false, false>));                   \
     } while (0)
     if (epl <= 1) DACO_LIST(1);
     if (epl <= 2) DACO_LIST(2);
     if (epl <= 4) DACO_LIST(4);
     DACO_LIST(8);
+#undef DACO_LAUNCH1
 #undef DACO_LIST
 }
 

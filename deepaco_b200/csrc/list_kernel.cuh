@@ -27,8 +27,9 @@ struct ListParams {
     int rows;               // rows of the path buffers: n (TSP) or 2n (CVRP)
     int start_node;         // TSP: >= 0 fixed start; -1 -> `start` tensor or torch randint stream
     int double_norm;        // TSP-NLS pre-normalisation
-    uint64_t seed, offset;
-    const uint64_t* rng;    // [B][2] or null
+    uint64_t seed, offset;  // one seed for the launch; per-colony Philox offsets from `offsets` when non-null
+    const uint64_t* offsets;   // [B] or null
+    PhiloxRoundKeys keys;   // round keys of `seed`, host-computed: read straight from the constant bank
     const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
     const int64_t* start;   // [B][A] or null
     int64_t* paths;         // [B][rows][A] or null
@@ -62,8 +63,14 @@ __device__ __forceinline__ float noise_rcp(uint32_t ctr_lo, uint32_t ctr_hi, uin
     return rcp_approx(exp1_from_word(philox_word_x(ctr_lo, ctr_hi, sub, K)));
 }
 
-template <int EPL, bool CVRP, bool WANT_LOGP>
-__global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
+// opaque register copy: stops the compiler from re-deriving a shared-memory address inside the step loop
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+
+template <int EPL, bool CVRP, bool WANT_LOGP, bool EXT_NOISE>
+__global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant__ ListParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const int n = p.n, R = p.rows;
@@ -82,20 +89,19 @@ __global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
     uint32_t* alive_all = reinterpret_cast<uint32_t*>(smem + pbytes + dbytes + (((size_t)W * (R + n) * 2 + 15) & ~(size_t)15));
     uint16_t* tour_sm = tour_all + (size_t)warp * R;
     uint32_t* alive = alive_all + warp * 32;
-    const uint32_t P_addr = smem_u32(Psm);
-    const uint32_t dem_addr = smem_u32(dem);
-    const uint32_t cand_addr = smem_u32(cand_all + (size_t)warp * n);
-    const uint32_t tour_addr = smem_u32(tour_sm);
+    const uint32_t P_addr = pin_u32(smem_u32(Psm));
+    const uint32_t dem_addr = pin_u32(smem_u32(dem));
+    const uint32_t cand_addr = pin_u32(smem_u32(cand_all + (size_t)warp * n));
+    const uint32_t tour_addr = pin_u32(smem_u32(tour_sm));
 
     if (CVRP)
         for (int i = tid; i < n; i += nthreads) dem[i] = p.demand[(size_t)b * n + i];
     stage_product(Psm, p.ph, p.heu, n, b, &bar);   // ends with __syncthreads()
 
     if (a < p.A) {
-        const uint64_t seed = p.rng ? p.rng[2 * b] : p.seed;
-        const uint64_t offset0 = p.rng ? p.rng[2 * b + 1] : p.offset;
-        PhiloxRoundKeys K;
-        K.init(seed);
+        const uint64_t seed = p.seed;
+        const uint64_t offset0 = p.offsets ? p.offsets[b] : p.offset;
+        const PhiloxRoundKeys& K = p.keys;
         const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
         const float eps = 1.1920928955078125e-07f;
         const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
             cj[k] = CVRP ? (uint32_t)s : (uint32_t)(s < cur ? s : s + 1);
             if (s < cnt) sts_u16(cand_addr + 2 * s, cj[k]);
             r[k] = 0.f;
-            if (s < cnt && !p.noise) r[k] = noise_rcp(ctr0_lo, ctr0_hi, sub_base + cj[k], K);
+            if (s < cnt && !EXT_NOISE) r[k] = noise_rcp(ctr0_lo, ctr0_hi, sub_base + cj[k], K);
         }
         if (WANT_LOGP && !CVRP) {
             uint32_t m = 0;
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
         while (CVRP ? (!(cnt == 1 && cur == 0) && step < max_steps) : (step < n - 1)) {
             const uint32_t row_addr = P_addr + (uint32_t)cur * (uint32_t)n * 4u;
             const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
-            const float* nz = p.noise ? p.noise + (((size_t)b * (R - 1) + step) * p.A + a) * (size_t)n : nullptr;
+            const float* nz = EXT_NOISE ? p.noise + (((size_t)b * (R - 1) + step) * p.A + a) * (size_t)n : nullptr;
             const uint32_t lastj = lds_u16(cand_addr + 2 * (cnt - 1));   // entry that fills the freed slot
             const float remaining = CVRP ? __fsub_rn(p.capacity, used) : 0.f;
             const bool depot_ok = CVRP && ((cur != 0) || (cnt == 1));
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
                 if (CVRP && ok) ok = (s == 0) ? depot_ok : !(lds_f32(dem_addr + 4 * cj[k]) > remaining);
                 okk[k] = ok;
                 const float x = ok ? lds_f32(row_addr + 4 * cj[k]) : 0.f;
-                const float rr = nz ? (ok ? rcp_approx(nz[cj[k]]) : 0.f) : r[k];
+                const float rr = EXT_NOISE ? (ok ? rcp_approx(nz[cj[k]]) : 0.f) : r[k];
                 const float A = __fmul_rn(x, rr);
                 if (A > bestA) {
                     second = bestA;
@@ -183,14 +189,14 @@ __global__ void __launch_bounds__(512) aco_list_kernel(const ListParams p) {
 #pragma unroll
                 for (int k = 0; k < EPL; ++k) {
                     rn[k] = 0.f;
-                    if (32 * k < cnt && !p.noise) rn[k] = noise_rcp(nlo, nhi, sub_base + cj[k], K);
+                    if (32 * k < cnt && !EXT_NOISE) rn[k] = noise_rcp(nlo, nhi, sub_base + cj[k], K);
                 }
             }
-            const int kl = (cnt - 1) >> 5;
-            float lastr = 0.f;
+            const int kl = (cnt - 1) >> 5;   // warp-uniform: pick the register, then one shuffle
+            float lastr = rn[0];
 #pragma unroll
-            for (int k = 0; k < EPL; ++k)
-                if (k == kl) lastr = __shfl_sync(DACO_FULL, rn[k], (cnt - 1) & 31);
+            for (int k = 1; k < EPL; ++k) lastr = (k == kl) ? rn[k] : lastr;
+            lastr = __shfl_sync(DACO_FULL, lastr, (cnt - 1) & 31);
 
             const float thr = __fmul_rn(__uint_as_float(topbits), kGap);
             const bool is_top = mybits == topbits;

@@ -29,7 +29,30 @@ __device__ __forceinline__ void stage_product(float* Psm, const float* ph, const
     __syncthreads();
     if (heu) {
         const float* h = heu + (size_t)b * nn;
-        for (size_t i = tid; i < nn; i += nthreads) Psm[i] = __fmul_rn(Psm[i], __ldg(h + i));
+        if (((reinterpret_cast<uintptr_t>(h) & 15) == 0) && (nn & 3) == 0) {
+            // float4 loads, four in flight per thread, so the L2 latency of the heuristic read is overlapped
+            const float4* h4 = reinterpret_cast<const float4*>(h);
+            float4* P4 = reinterpret_cast<float4*>(Psm);
+            const int n4 = (int)(nn >> 2);
+            for (int i = tid; i < n4; i += 4 * nthreads) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * nthreads < n4) v[u] = __ldg(h4 + i + u * nthreads);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * nthreads < n4) {
+                        float4 q = P4[i + u * nthreads];
+                        q.x = __fmul_rn(q.x, v[u].x);
+                        q.y = __fmul_rn(q.y, v[u].y);
+                        q.z = __fmul_rn(q.z, v[u].z);
+                        q.w = __fmul_rn(q.w, v[u].w);
+                        P4[i + u * nthreads] = q;
+                    }
+            }
+        } else {
+            for (size_t i = tid; i < nn; i += nthreads) Psm[i] = __fmul_rn(Psm[i], __ldg(h + i));
+        }
         __syncthreads();
     }
 }

@@ -33,7 +33,7 @@ struct TspSampleParams {
     int start_node;       // >= 0 fixed; -1 -> `start` tensor or torch randint stream
     int double_norm;
     uint64_t seed, offset;
-    const uint64_t* rng;  // [B][2] or null
+    const uint64_t* offsets;  // [B] per-colony Philox offsets or null
     const float* noise;   // [B][n-1][A][n] or null
     const int64_t* start; // [B][A] or null
     int64_t* paths;       // [B][n][A] or null
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
     if (a < p.A) {
         const int lbw = p.lbw;
         const bool lane_on = VEC || lane < (1 << lbw);
-        const uint64_t seed = p.rng ? p.rng[2 * b] : p.seed;
-        const uint64_t offset0 = p.rng ? p.rng[2 * b + 1] : p.offset;
+        const uint64_t seed = p.seed;
+        const uint64_t offset0 = p.offsets ? p.offsets[b] : p.offset;
         const float* Pg = SMEMP ? Psm : (p.ph + (size_t)b * nn);   // !SMEMP: caller passes the product in `ph`
 
         int cur;
@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
 template <typename KFn, typename P>
 static int launch_kernel(KFn kfn, const P& p, int W, size_t smem, cudaStream_t st) {
     DACO_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DACO_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     dim3 grid((p.A + W - 1) / W, p.B);
     kfn<<<grid, W * 32, smem, st>>>(p);
     DACO_CHECK_LAUNCH();
@@ -206,7 +207,7 @@ extern "C" uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int s
 
 extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
                                   int start_node, int double_norm, uint64_t seed, uint64_t offset,
-                                  const uint64_t* rng, const float* noise, const int64_t* start, int64_t* paths,
+                                  const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
                                   float* log_probs, uint16_t* tours, void* stream) {
     const DeviceInfo* di = device_info();
     if (!di) return DEEPACO_ENODEV;
@@ -220,7 +221,7 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
     p.ph = pheromone; p.heu = heuristic;
     p.n = n; p.A = n_ants; p.B = n_colonies;
     p.start_node = start_node; p.double_norm = double_norm;
-    p.seed = seed; p.offset = offset; p.rng = rng;
+    p.seed = seed; p.offset = offset; p.offsets = offsets;
     p.noise = noise; p.start = start;
     p.paths = paths; p.logp = log_probs; p.tours = tours;
 
@@ -255,16 +256,21 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
             while (W < 16 && (cap / list_smem(W)) * W < 32 && list_smem(W * 2) <= cap) W *= 2;
         ListParams q{};
         q.ph = pheromone; q.heu = heuristic; q.n = n; q.A = n_ants; q.B = n_colonies; q.rows = n;
-        q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.rng = rng;
+        q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.offsets = offsets;
+        q.keys.init(seed);
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
         const int epl = (n - 1 + 31) / 32;
         const size_t sm = list_smem(W);
-#define DACO_LIST(E)                                                                            \
-        do {                                                                                    \
-            if (log_probs) return launch_kernel(aco_list_kernel<E, false, true>, q, W, sm, st); \
-            return launch_kernel(aco_list_kernel<E, false, false>, q, W, sm, st);               \
+#define DACO_LIST(E)                                                                                        \
+        do {                                                                                                \
+            if (noise) {                                                                                    \
+                if (log_probs) return launch_kernel(aco_list_kernel<E, false, true, true>, q, W, sm, st);   \
+                return launch_kernel(aco_list_kernel<E, false, false, true>, q, W, sm, st);                 \
+            }                                                                                               \
+            if (log_probs) return launch_kernel(aco_list_kernel<E, false, true, false>, q, W, sm, st);      \
+            return launch_kernel(aco_list_kernel<E, false, false, false>, q, W, sm, st);                    \
         } while (0)
         if (epl <= 1) DACO_LIST(1);
         if (epl <= 2) DACO_LIST(2);

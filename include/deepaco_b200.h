@@ -48,15 +48,17 @@ int deepaco_aten_sum_plan(int row_len, int n_rows, int* block_width_out, int* ve
  * Replaces ACO.gen_path + pick_move: tsp/aco.py:134-177 (start_node = -1, double_norm = 0) and
  * tsp_nls/aco.py:184-220 (start_node = 0, double_norm = 1).
  * Noise: when `noise` is NULL the kernel regenerates, in registers, exactly the Philox words torch's
- * `randint` / `exponential_` kernels would draw from (seed, offset) -- per colony from rng[b] =
- * {seed, offset} (device, may be NULL) else from the by-value pair.  The caller advances its
- * generator by deepaco_tsp_sample_offset_increment().
+ * `randint` / `exponential_` kernels would draw from (seed, offset); batched colonies share the seed and
+ * take their Philox offset from offsets[b] (device uint64 [B]; NULL = the by-value offset for all) --
+ * i.e. colony b sees the stream the reference would have reached had it processed the colonies one
+ * after another under one generator.  The caller advances its generator by
+ * deepaco_tsp_sample_offset_increment() per colony.
  * With `noise` != NULL ([B][n-1][A][n] Exp(1) draws) and `start` ([B][A], or start_node >= 0) the
  * result is a pure function of its inputs (cross-device parity mode).
  * Outputs (each may be NULL): paths int64 [B][n][A]; log_probs fp32 [B][n-1][A]; tours u16 [B][A][n]. */
 int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
                        int start_node, int double_norm, uint64_t seed, uint64_t offset,
-                       const uint64_t* rng, const float* noise, const int64_t* start, int64_t* paths,
+                       const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
                        float* log_probs, uint16_t* tours, void* stream);
 uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int start_node);
 
@@ -85,7 +87,7 @@ int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, const float
  * noise (optional): [B][path_rows-1][n_ants][n_nodes]. */
 int deepaco_cvrp_sample(const float* pheromone, const float* heuristic, const float* demand, float capacity,
                         int n_nodes, int n_ants, int n_colonies, uint64_t seed, uint64_t offset,
-                        const uint64_t* rng, const float* noise, int path_rows, int64_t* paths,
+                        const uint64_t* offsets, const float* noise, int path_rows, int64_t* paths,
                         float* log_probs, uint16_t* tours, int32_t* lens, int32_t* tmax, void* stream);
 uint64_t deepaco_cvrp_step_offset_increment(int n_nodes, int n_ants);
 

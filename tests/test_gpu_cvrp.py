@@ -109,9 +109,9 @@ def test_routes_valid_at_benchmark_size():
     B, n, A = 4, 100, 512
     demand, dist, heu = _instance(n, gnn_like=True)
     N = n + 1
-    rng = torch.tensor([[9 + b, 0] for b in range(B)], dtype=torch.int64, device=DEV)
+    offsets = torch.tensor([4000 * b for b in range(B)], dtype=torch.int64, device=DEV)
     out = E.cvrp_sample(torch.ones(B, N, N, device=DEV), heu.expand(B, N, N).contiguous(),
-                        demand.expand(B, N).contiguous(), 50, A, rng=rng, want_tours=True)
+                        demand.expand(B, N).contiguous(), 50, A, seed=9, offsets=offsets, want_tours=True)
     paths = out["paths"].cpu().numpy()
     dem = demand.cpu().numpy()
     lens = out["lens"].cpu().numpy()

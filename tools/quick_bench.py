@@ -31,11 +31,11 @@ for (n, A, B, nls) in [(100, 512, 1, False), (100, 512, 8, False), (100, 512, 64
     heu = torch.full_like(dist, 1e-10)
     heu.scatter_(2, idx, torch.rand(B, n, k, device=dev) * 0.9 + 0.05)
     ph = torch.ones_like(dist)
-    rng = torch.tensor([[5 + b, 0] for b in range(B)], dtype=torch.int64, device=dev)
+    offsets = torch.tensor([4000 * b for b in range(B)], dtype=torch.int64, device=dev)
     out = {}
 
     def samp():
-        out["p"], _, out["t"] = E.tsp_sample(ph, heu, A, rng=rng, start_node=0 if nls else -1, double_norm=nls,
+        out["p"], _, out["t"] = E.tsp_sample(ph, heu, A, seed=5, offsets=offsets, start_node=0 if nls else -1, double_norm=nls,
                                              want_paths=True, want_tours=True)
     t_s = timeit(samp)
 
