@@ -124,6 +124,123 @@ def tsp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_m
     return pheromone
 
 
+class TspRunner:
+    """Device-resident state of `ACO.run` for one or many TSP colonies (deepaco_tsp_run).
+
+    Owns the pheromone (a private contiguous copy), the product matrix and the per-iteration scratch, and
+    keeps lowest_cost / shortest_path on the device, so T iterations are launched without a host sync.
+    """
+
+    def __init__(self, distances, heuristic, pheromone, n_ants, *, decay=0.9, elitist=False, min_max=False,
+                 ph_min=0.0, start_node=-1, double_norm=False):
+        self.distances = f32c(require_cuda(distances, "distances"))
+        self.B, self.n = _colonies(self.distances)
+        self.batched = self.distances.dim() == 3
+        dev = self.dev = self.distances.device
+        self.heuristic = f32c(require_cuda(heuristic, "heuristic").detach())
+        self.pheromone = pheromone.detach().to(torch.float32).clone(memory_format=torch.contiguous_format)
+        shp = (self.B, self.n, self.n)
+        if self.heuristic.numel() != self.B * self.n * self.n or self.pheromone.numel() != self.B * self.n * self.n:
+            raise _lib.DeepAcoError("distances / heuristic / pheromone shape mismatch")
+        self.n_ants = int(n_ants)
+        self.product = torch.empty(shp, dtype=torch.float32, device=dev)
+        self.product_valid = False
+        self.tours = torch.empty((self.B, self.n_ants, self.n), dtype=torch.uint16, device=dev)
+        self.costs = torch.empty((self.B, self.n_ants), dtype=torch.float32, device=dev)
+        self.neighbours = torch.empty((self.B, self.n, self.n_ants), dtype=torch.int32, device=dev)
+        self.lowest_cost = torch.full((self.B,), float("inf"), dtype=torch.float32, device=dev)
+        self.shortest_path = torch.zeros((self.B, self.n), dtype=torch.int64, device=dev)
+        self.ph_max = torch.zeros((self.B,), dtype=torch.float32, device=dev)
+        self.scale = torch.ones((self.B,), dtype=torch.float32, device=dev)
+        self.decay, self.elitist, self.min_max, self.ph_min = float(decay), bool(elitist), bool(min_max), float(ph_min)
+        self.start_node, self.double_norm = int(start_node), bool(double_norm)
+        self.increment = tsp_sample_offset_increment(self.n, self.n_ants, self.start_node)
+
+    def _args(self, seed, offset, offs, events=None):
+        ev0 = events[0].cuda_event if events else None
+        ev1 = events[1].cuda_event if events else None
+        return _lib.TspRunArgs(self.n, self.n_ants, self.B, self.start_node, int(self.double_norm), self.decay,
+                               int(self.elitist), int(self.min_max), self.ph_min, int(seed), int(offset), ptr(offs),
+                               ptr(self.pheromone), ptr(self.heuristic), ptr(self.distances), ptr(self.product),
+                               int(self.product_valid), ptr(self.tours), ptr(self.costs), ptr(self.neighbours),
+                               ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.ph_max), ptr(self.scale), ev0, ev1)
+
+    def run(self, n_iterations, seed, offset=0, offsets=None, sample_events=None):
+        """Launch n_iterations ACO iterations; colony b consumes offsets[b] + offset + t * self.increment.
+        sample_events: optional (begin, end) torch.cuda.Event pair recorded around each sampling launch."""
+        offs = _offsets(offsets, self.B, self.dev)
+        a = self._args(seed, offset, offs, sample_events)
+        with torch.cuda.device(self.dev):
+            check(lib().deepaco_tsp_run(C.byref(a), int(n_iterations), stream_ptr(self.dev)), "deepaco_tsp_run")
+        if n_iterations > 0:
+            self.product_valid = True
+        return self.lowest_cost
+
+    def run_host(self, n_iterations, seed, distances_h, heuristic_h, pheromone_h, lowest_h, shortest_h, offset=0,
+                 offsets=None):
+        """deepaco_tsp_run_host: pinned HOST tensors in/out (pheromone_h is updated in place); synchronous."""
+        for t, nm in ((distances_h, "distances"), (heuristic_h, "heuristic"), (pheromone_h, "pheromone")):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.B * self.n * self.n:
+                raise _lib.DeepAcoError(f"run_host: `{nm}` must be a contiguous fp32 host tensor [B, n, n]")
+        offs = _offsets(offsets, self.B, self.dev)
+        a = self._args(seed, offset, offs)
+        with torch.cuda.device(self.dev):
+            check(lib().deepaco_tsp_run_host(C.byref(a), int(n_iterations), ptr(distances_h), ptr(heuristic_h),
+                                             ptr(pheromone_h), ptr(lowest_h), ptr(shortest_h), stream_ptr(self.dev)),
+                  "deepaco_tsp_run_host")
+        self.product_valid = n_iterations > 0
+        return lowest_h
+
+
+# ---- local search -------------------------------------------------------------------------------
+def paths_to_tours(paths):
+    """int64 [n, A] | [B, n, A] -> uint16 [A, n] | [B, A, n]."""
+    paths = require_cuda(paths, "paths").to(torch.int64).contiguous()
+    batched = paths.dim() == 3
+    B = paths.shape[0] if batched else 1
+    n, A = paths.shape[-2], paths.shape[-1]
+    tours = torch.empty((B, A, n), dtype=torch.uint16, device=paths.device)
+    with torch.cuda.device(paths.device):
+        check(lib().deepaco_paths_to_tours(ptr(paths), ptr(tours), n, A, B, stream_ptr(paths.device)), "paths_to_tours")
+    return tours if batched else tours[0]
+
+
+def tours_to_paths(tours):
+    tours = require_cuda(tours, "tours").contiguous()
+    batched = tours.dim() == 3
+    B = tours.shape[0] if batched else 1
+    A, n = tours.shape[-2], tours.shape[-1]
+    paths = torch.empty((B, n, A), dtype=torch.int64, device=tours.device)
+    with torch.cuda.device(tours.device):
+        check(lib().deepaco_tours_to_paths(ptr(tours), ptr(paths), n, A, B, stream_ptr(tours.device)), "tours_to_paths")
+    return paths if batched else paths[0]
+
+
+def two_opt_(distances, tours, max_iterations, *, want_passes=False):
+    """deepaco_two_opt in place on uint16 tours [A, n] | [B, A, n]."""
+    distances = f32c(require_cuda(distances, "distances"))
+    B, n = _colonies(distances)
+    A = tours.shape[-2]
+    passes = torch.empty((B, A), dtype=torch.int32, device=tours.device) if want_passes else None
+    with torch.cuda.device(tours.device):
+        check(lib().deepaco_two_opt(ptr(distances), ptr(tours), n, A, B, int(max_iterations), ptr(passes),
+                                    stream_ptr(tours.device)), "deepaco_two_opt")
+    return (tours, passes) if want_passes else tours
+
+
+def tsp_nls_(distances, heuristic_dist, tours, max_iterations, T_nls=10, T_p=20, *, want_passes=False):
+    """deepaco_tsp_nls in place on uint16 tours."""
+    distances = f32c(require_cuda(distances, "distances"))
+    heuristic_dist = f32c(require_cuda(heuristic_dist, "heuristic_dist"))
+    B, n = _colonies(distances)
+    A = tours.shape[-2]
+    passes = torch.empty((B, A), dtype=torch.int32, device=tours.device) if want_passes else None
+    with torch.cuda.device(tours.device):
+        check(lib().deepaco_tsp_nls(ptr(distances), ptr(heuristic_dist), ptr(tours), n, A, B, int(max_iterations),
+                                    int(T_nls), int(T_p), None, ptr(passes), stream_ptr(tours.device)), "deepaco_tsp_nls")
+    return (tours, passes) if want_passes else tours
+
+
 # ---- CVRP -------------------------------------------------------------------------------------
 def cvrp_sample(pheromone, heuristic, demand, capacity, n_ants, *, seed=0, offset=0, offsets=None, noise=None,
                 want_paths=True, want_logp=False, want_tours=False):

@@ -25,6 +25,10 @@ _SIGNATURES = {
     "deepaco_tsp_sample_offset_increment": (_u64, [_i32, _i32, _i32]),
     "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
+    "deepaco_two_opt": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "deepaco_tsp_nls": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "deepaco_paths_to_tours": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "deepaco_tours_to_paths": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "deepaco_cvrp_sample": (_i32, [_vp, _vp, _vp, _f32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "deepaco_cvrp_step_offset_increment": (_u64, [_i32, _i32]),
     "deepaco_cvrp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
@@ -33,6 +37,21 @@ _SIGNATURES = {
     "deepaco_debug_randint": (_i32, [_u64, _u64, _i64, _i64, _vp, _vp]),
     "deepaco_debug_row_sum": (_i32, [_vp, _i32, _i32, _vp, _vp]),
 }
+
+
+
+class TspRunArgs(C.Structure):
+    """deepaco_tsp_run_args (include/deepaco_b200.h)."""
+    _fields_ = [("n", _i32), ("n_ants", _i32), ("n_colonies", _i32), ("start_node", _i32), ("double_norm", _i32),
+                ("decay", _f32), ("elitist", _i32), ("min_max", _i32), ("ph_min", _f32),
+                ("seed", _u64), ("offset", _u64), ("offsets", _vp),
+                ("pheromone", _vp), ("heuristic", _vp), ("distances", _vp), ("product", _vp), ("product_valid", _i32),
+                ("tours", _vp), ("costs", _vp), ("neighbours", _vp), ("lowest_cost", _vp), ("shortest_path", _vp),
+                ("ph_max", _vp), ("scale", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
+
+
+_SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])
+_SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp])
 
 _lib = None
 

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
 
     if (a < p.A) {
         const uint64_t seed = p.seed;
-        const uint64_t offset0 = p.offsets ? p.offsets[b] : p.offset;
+        const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
         const PhiloxRoundKeys& K = p.keys;
         const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
         const float eps = 1.1920928955078125e-07f;

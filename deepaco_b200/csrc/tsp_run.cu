@@ -1,0 +1,152 @@
+// ACO.run for TSP colonies without returning to the host between iterations
+// (reference tsp/aco.py:74-92 and tsp_nls/aco.py:104-129 without local search).
+//
+// Per iteration, on one stream:  K1 sample (tours)  ->  cost + neighbour table  ->  best tracking
+// (lowest_cost / shortest_path / MMAS max, all kept on the device)  ->  K2 evaporate + deposit, which also
+// emits next iteration's product matrix P = pheromone (.) heuristic so that K1 stages a single matrix.
+// The reference's `if best_cost < self.lowest_cost` is a host-side branch on a device value (one sync per
+// iteration); here the comparison runs in best_kernel.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace deepaco {
+
+int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants, int n_colonies,
+                      float decay, int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
+                      const float* heuristic, float* product, cudaStream_t st);
+int tsp_cost_launch(const float* distances, const uint16_t* tours, int n, int n_ants, int n_colonies, float* costs,
+                    uint32_t* neighbours, cudaStream_t st);
+
+__global__ void hadamard2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        o[i] = __fmul_rn(a[i], b[i]);
+}
+
+// one CTA per colony: iteration best -> running best, MMAS bookkeeping
+__global__ void __launch_bounds__(256) tsp_best_kernel(const float* __restrict__ costs, const uint16_t* __restrict__ tours,
+                                                       const float* __restrict__ ph, int n, int A, int min_max,
+                                                       float* __restrict__ lowest, int64_t* __restrict__ shortest,
+                                                       float* __restrict__ ph_max, float* __restrict__ scale) {
+    __shared__ float s_c[32];
+    __shared__ int s_i[32];
+    __shared__ int s_improved, s_first;
+    __shared__ float s_m[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* C = costs + (size_t)b * A;
+    float bc = INFINITY;
+    int bi = 0x7fffffff;
+    for (int a = tid; a < A; a += blockDim.x) {
+        const float c = C[a];
+        if (c < bc) { bc = c; bi = a; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const float oc = __shfl_xor_sync(DACO_FULL, bc, off);
+        const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
+        if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+    }
+    if (lane == 0) { s_c[warp] = bc; s_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bc = lane < (blockDim.x >> 5) ? s_c[lane] : INFINITY;
+        bi = lane < (blockDim.x >> 5) ? s_i[lane] : 0x7fffffff;
+        for (int off = 16; off > 0; off >>= 1) {
+            const float oc = __shfl_xor_sync(DACO_FULL, bc, off);
+            const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
+            if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+        }
+        if (lane == 0) {
+            s_improved = bc < lowest[b];   // tsp/aco.py:81
+            s_first = min_max && !(ph_max[b] > 0.f);   // MMAS max not set yet (marker 0)
+            s_c[0] = bc;
+            s_i[0] = bi;
+        }
+    }
+    __syncthreads();
+    if (scale && tid == 0) scale[b] = 1.0f;
+    if (!s_improved) return;
+    bc = s_c[0];
+    bi = s_i[0];
+    const uint16_t* t = tours + ((size_t)b * A + bi) * n;
+    for (int k = tid; k < n; k += blockDim.x) shortest[(size_t)b * n + k] = (int64_t)t[k];
+    if (tid == 0) lowest[b] = bc;
+    if (min_max) {
+        // max = problem_size / lowest_cost  ==  reciprocal(lowest) * n   (Tensor.__rtruediv__)
+        const float new_max = __fmul_rn(__fdiv_rn(1.0f, bc), (float)n);
+        if (s_first) {
+            // self.pheromone *= max / self.pheromone.max()
+            float m = -INFINITY;
+            const float* P = ph + (size_t)b * n * n;
+            for (int i = tid; i < n * n; i += blockDim.x) m = fmaxf(m, P[i]);
+            for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(DACO_FULL, m, off));
+            if (lane == 0) s_m[warp] = m;
+            __syncthreads();
+            if (warp == 0) {
+                m = lane < (blockDim.x >> 5) ? s_m[lane] : -INFINITY;
+                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(DACO_FULL, m, off));
+                if (lane == 0) scale[b] = __fdiv_rn(new_max, m);
+            }
+        }
+        if (tid == 0) ph_max[b] = new_max;
+    }
+}
+
+}  // namespace deepaco
+
+using namespace deepaco;
+
+extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, void* stream) {
+    DACO_CHECK_ARG(a != nullptr && n_iterations >= 0, "deepaco_tsp_run: bad arguments");
+    DACO_CHECK_ARG(a->pheromone && a->heuristic && a->distances && a->product && a->tours && a->costs && a->neighbours &&
+                       a->lowest_cost && a->shortest_path,
+                   "deepaco_tsp_run: NULL buffer");
+    DACO_CHECK_ARG(!a->min_max || (a->ph_max && a->scale), "deepaco_tsp_run: min_max needs ph_max and scale buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = a->n, A = a->n_ants, B = a->n_colonies;
+    const uint64_t inc = deepaco_tsp_sample_offset_increment(n, A, a->start_node);
+    const size_t cnt = (size_t)B * n * n;
+    if (n_iterations > 0 && !a->product_valid) {
+        hadamard2_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(a->pheromone, a->heuristic,
+                                                                                                a->product, cnt);
+        DACO_CHECK_LAUNCH();
+    }
+    for (int it = 0; it < n_iterations; ++it) {
+        if (a->ev_sample_begin) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_begin, st));
+        int rc = deepaco_tsp_sample(a->product, nullptr, n, A, B, a->start_node, a->double_norm, a->seed,
+                                    a->offset + (uint64_t)it * inc, a->offsets, nullptr, nullptr, nullptr, nullptr, a->tours, st);
+        if (rc) return rc;
+        if (a->ev_sample_end) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_end, st));
+        rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, a->neighbours, st);
+        if (rc) return rc;
+        tsp_best_kernel<<<B, 256, 0, st>>>(a->costs, a->tours, a->pheromone, n, A, a->min_max, a->lowest_cost, a->shortest_path,
+                                           a->ph_max, a->min_max ? a->scale : nullptr);
+        DACO_CHECK_LAUNCH();
+        rc = tsp_update_launch(a->pheromone, a->neighbours, a->costs, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min,
+                               a->ph_max, a->min_max ? a->scale : nullptr, a->heuristic, a->product, st);
+        if (rc) return rc;
+    }
+    return DEEPACO_OK;
+}
+
+// Host-buffer entry point (what a CPU-side caller of the reference's ACO.run would bind): copies the three
+// matrices of every colony to the device buffers named in `a`, runs, copies the results back, synchronises.
+extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterations, const float* distances_host,
+                                    const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
+                                    int64_t* shortest_path_host, void* stream) {
+    DACO_CHECK_ARG(a && distances_host && heuristic_host && pheromone_host && lowest_cost_host && shortest_path_host,
+                   "deepaco_tsp_run_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t mat = (size_t)a->n_colonies * a->n * a->n * sizeof(float);
+    DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->distances), distances_host, mat, cudaMemcpyHostToDevice, st));
+    DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->heuristic), heuristic_host, mat, cudaMemcpyHostToDevice, st));
+    DACO_CHECK_CUDA(cudaMemcpyAsync(a->pheromone, pheromone_host, mat, cudaMemcpyHostToDevice, st));
+    deepaco_tsp_run_args b = *a;
+    b.product_valid = 0;
+    const int rc = deepaco_tsp_run(&b, n_iterations, stream);
+    if (rc) return rc;
+    DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host, a->pheromone, mat, cudaMemcpyDeviceToHost, st));
+    DACO_CHECK_CUDA(cudaMemcpyAsync(lowest_cost_host, a->lowest_cost, sizeof(float) * a->n_colonies, cudaMemcpyDeviceToHost, st));
+    DACO_CHECK_CUDA(cudaMemcpyAsync(shortest_path_host, a->shortest_path, sizeof(int64_t) * a->n_colonies * a->n,
+                                    cudaMemcpyDeviceToHost, st));
+    DACO_CHECK_CUDA(cudaStreamSynchronize(st));
+    return DEEPACO_OK;
+}

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
         const int lbw = p.lbw;
         const bool lane_on = VEC || lane < (1 << lbw);
         const uint64_t seed = p.seed;
-        const uint64_t offset0 = p.offsets ? p.offsets[b] : p.offset;
+        const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
         const float* Pg = SMEMP ? Psm : (p.ph + (size_t)b * nn);   // !SMEMP: caller passes the product in `ph`
 
         int cur;

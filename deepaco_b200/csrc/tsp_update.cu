@@ -51,27 +51,32 @@ __global__ void __launch_bounds__(256) tsp_cost_kernel(const float* __restrict__
     }
 }
 
-// grid (n rows, B colonies); dynamic smem: A * (uint32 nbr + float w)
-__global__ void __launch_bounds__(256) tsp_update_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
+// One warp per matrix row u.  The 2A deposit events of the row (ant a: first its predecessor cell, then its
+// successor cell -- the reference's statement order) are bucketed by cell with a stable counting sort in
+// shared memory, so each cell then adds its own few weights in ant order: work per row is O(A + n) instead
+// of O(A * n), and the row is read and written exactly once, coalesced.
+//   smem per warp: w_sorted[2A] f32 | start[n+1] i32 | cursor[n] i32
+__global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
                                                          const float* __restrict__ costs, int n, int A, float decay,
                                                          int elitist, int min_max, float ph_min,
-                                                         const float* __restrict__ ph_max) {
+                                                         const float* __restrict__ ph_max, const float* __restrict__ scale,
+                                                         const float* __restrict__ heu, float* __restrict__ prod) {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* nb_s = reinterpret_cast<uint32_t*>(smem);
-    float* w_s = reinterpret_cast<float*>(smem) + A;
-    __shared__ int best_ant;
-    const int u = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    const int u = blockIdx.x * W + warp, b = blockIdx.y;
+    if (u >= n) return;
+    const size_t per_warp = (size_t)2 * A * 4 + (size_t)(2 * n + 1) * 4;
+    float* w_sorted = reinterpret_cast<float*>(smem + warp * ((per_warp + 15) & ~(size_t)15));
+    int* start = reinterpret_cast<int*>(w_sorted + 2 * A);
+    int* cursor = start + n + 1;
     const uint32_t* N = nbr + ((size_t)b * n + u) * A;
     const float* C = costs + (size_t)b * A;
-    for (int a = threadIdx.x; a < A; a += blockDim.x) {
-        nb_s[a] = N[a];
-        w_s[a] = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
-    }
-    if (elitist && threadIdx.x < 32) {
-        // costs.min(dim=0): first index of the minimum
+
+    int a_lo = 0, a_hi = A;
+    if (elitist) {   // costs.min(dim=0): first index of the minimum
         float bc = INFINITY;
         int bi = 0x7fffffff;
-        for (int a = threadIdx.x; a < A; a += 32) {
+        for (int a = lane; a < A; a += 32) {
             const float c = C[a];
             if (c < bc) { bc = c; bi = a; }
         }
@@ -80,26 +85,59 @@ __global__ void __launch_bounds__(256) tsp_update_kernel(float* __restrict__ ph,
             const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
             if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
         }
-        if (threadIdx.x == 0) best_ant = bi;
+        a_lo = bi;
+        a_hi = bi + 1;
     }
-    __syncthreads();
+    const int E = 2 * (a_hi - a_lo);   // events, key e -> ant a_lo + e/2, statement e&1
+    for (int v = lane; v <= n; v += 32) start[v] = 0;
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) {
+        const uint32_t nb = N[a_lo + (e >> 1)];
+        const int cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
+        atomicAdd(&start[cell + 1], 1);
+    }
+    __syncwarp();
+    // inclusive scan of start[1..n] (start[0] = 0) -> bucket offsets
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int v = base + lane;
+        int x = (v < n) ? start[v + 1] : 0;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(DACO_FULL, x, off);
+            if (lane >= off) x += y;
+        }
+        x += carry;
+        if (v < n) { start[v + 1] = x; }
+        carry = __shfl_sync(DACO_FULL, x, 31);
+    }
+    __syncwarp();
+    for (int v = lane; v < n; v += 32) cursor[v] = start[v];
+    __syncwarp();
+    for (int e0 = 0; e0 < E; e0 += 32) {
+        const int e = e0 + lane;
+        int cell = -1 - lane;   // distinct dummies for idle lanes
+        float w = 0.f;
+        if (e < E) {
+            const int a = a_lo + (e >> 1);
+            const uint32_t nb = N[a];
+            cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
+            w = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+        }
+        const uint32_t grp = __match_any_sync(DACO_FULL, cell);
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        if (e < E) w_sorted[cursor[cell] + rank] = w;
+        __syncwarp();
+        if (e < E && rank == 0) cursor[cell] += __popc(grp);
+        __syncwarp();
+    }
     float* row = ph + ((size_t)b * n + u) * n;
     const float hi = min_max ? ph_max[b] : 0.f;
-    for (int v = threadIdx.x; v < n; v += blockDim.x) {
-        float val = __fmul_rn(row[v], decay);
-        if (elitist) {
-            const uint32_t e = nb_s[best_ant];
-            const float w = w_s[best_ant];
-            if ((int)(e >> 16) == v) val = __fadd_rn(val, w);
-            if ((int)(e & 0xffffu) == v) val = __fadd_rn(val, w);
-        } else {
-            for (int a = 0; a < A; ++a) {
-                const uint32_t e = nb_s[a];
-                const float w = w_s[a];
-                if ((int)(e >> 16) == v) val = __fadd_rn(val, w);       // statement 1: (path[k], path[k-1])
-                if ((int)(e & 0xffffu) == v) val = __fadd_rn(val, w);   // statement 2: (path[k-1], path[k])
-            }
-        }
+    const float sc = scale ? scale[b] : 1.0f;
+    for (int v = lane; v < n; v += 32) {
+        float val = row[v];
+        if (scale) val = __fmul_rn(val, sc);   // MMAS rescale on the first improvement (tsp/aco.py:86-87)
+        val = __fmul_rn(val, decay);
+        for (int i = start[v]; i < start[v + 1]; ++i) val = __fadd_rn(val, w_sorted[i]);
         if (min_max) {
             // ph[(ph > 1e-9) * ph < min] = min ; ph[ph > max] = max   (tsp/aco.py:117-118)
             const float gate = __fmul_rn(val > 1e-9f ? 1.0f : 0.0f, val);
@@ -107,6 +145,7 @@ __global__ void __launch_bounds__(256) tsp_update_kernel(float* __restrict__ ph,
             if (val > hi) val = hi;
         }
         row[v] = val;
+        if (prod) prod[((size_t)b * n + u) * n + v] = __fmul_rn(val, heu[((size_t)b * n + u) * n + v]);
     }
 }
 
@@ -130,19 +169,40 @@ extern "C" int deepaco_tsp_cost(const float* distances, const int64_t* paths, co
     return DEEPACO_OK;
 }
 
+static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants,
+                             int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
+                             const float* scale, const float* heuristic, float* product, cudaStream_t st) {
+    const int W = 4;
+    const size_t per_warp = (((size_t)2 * n_ants * 4 + (size_t)(2 * n + 1) * 4) + 15) & ~(size_t)15;
+    const size_t smem = per_warp * W;
+    DACO_CHECK_ARG(smem <= 200 * 1024, "deepaco_tsp_update: n_ants=%d / n=%d too large for one pass", n_ants, n);
+    DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n + W - 1) / W, n_colonies);
+    tsp_update_kernel<<<grid, W * 32, smem, st>>>(pheromone, neighbours, costs, n, n_ants, decay, elitist, min_max, ph_min,
+                                                  ph_max, scale, heuristic, product);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+namespace deepaco {
+int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants, int n_colonies,
+                      float decay, int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
+                      const float* heuristic, float* product, cudaStream_t st) {
+    return launch_tsp_update(pheromone, neighbours, costs, n, n_ants, n_colonies, decay, elitist, min_max, ph_min, ph_max,
+                             scale, heuristic, product, st);
+}
+int tsp_cost_launch(const float* distances, const uint16_t* tours, int n, int n_ants, int n_colonies, float* costs,
+                    uint32_t* neighbours, cudaStream_t st) {
+    return deepaco_tsp_cost(distances, nullptr, tours, n, n_ants, n_colonies, costs, neighbours, st);
+}
+}  // namespace deepaco
+
 extern "C" int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants,
                                   int n_colonies, float decay, int elitist, int min_max, float ph_min,
                                   const float* ph_max, void* stream) {
     DACO_CHECK_ARG(pheromone && neighbours && costs, "deepaco_tsp_update: NULL argument");
     DACO_CHECK_ARG(n >= 2 && n <= 65535 && n_ants >= 1 && n_colonies >= 1, "deepaco_tsp_update: bad sizes");
     DACO_CHECK_ARG(!min_max || ph_max, "deepaco_tsp_update: min_max needs ph_max");
-    const size_t smem = (size_t)n_ants * 8;
-    DACO_CHECK_ARG(smem <= 200 * 1024, "deepaco_tsp_update: n_ants=%d too large for one pass", n_ants);
-    DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = n <= 64 ? 64 : (n <= 128 ? 128 : 256);
-    dim3 grid(n, n_colonies);
-    tsp_update_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(pheromone, neighbours, costs, n, n_ants, decay, elitist,
-                                                                     min_max, ph_min, ph_max);
-    DACO_CHECK_LAUNCH();
-    return DEEPACO_OK;
+    return launch_tsp_update(pheromone, neighbours, costs, n, n_ants, n_colonies, decay, elitist, min_max, ph_min, ph_max,
+                             nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }

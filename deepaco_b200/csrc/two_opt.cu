@@ -1,0 +1,258 @@
+// K4 -- batched 2-opt and NLS local search (reference tsp_nls/two_opt.py:6-49 and tsp_nls/aco.py:234-258).
+//
+// One CTA per ant tour; the whole local search of that ant (every pass of every 2-opt call, and for NLS
+// all T_nls perturbation rounds) runs inside one launch -- ants never interact.
+//
+// two_opt_once (two_opt.py:6-28): scan all 1 <= i < j <= n-1, change = d[p,nj] + d[ni,nx] - d[p,ni] - d[nj,nx]
+// (fp32, left to right), keep the first strict minimum in (i,j) order, reverse tour[i..j] iff it is
+// < -1e-6.  Here warp w owns a contiguous band of i (balanced by pair count); for each i it stages the two
+// distance rows d[p,:] and d[ni,:] in shared memory with coalesced loads (the row of ni is reused as the
+// row of p for i+1), lanes sweep j, and the (change, i*n+j) minimum is reduced over the CTA with the same
+// tie rule.  The terms d[p,ni] and d[nj,nx] are tour edges, cached per pass.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace deepaco {
+
+// numpy float32 pairwise summation of one contiguous row (numpy/_core/src/umath/loops_utils.h.src
+// @TYPE@_pairwise_sum, PW_BLOCKSIZE = 128) -- tsp_nls/aco.py:171-182 compares tours by np.sum(dist[u, v], axis=1).
+template <typename F>
+__device__ float numpy_pairwise_sum(F f, int lo, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, f(lo + i));
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], f(lo + i + k));
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, f(lo + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(numpy_pairwise_sum(f, lo, n2), numpy_pairwise_sum(f, lo + n2, n - n2));
+}
+
+struct TwoOptShared {
+    uint16_t* tour;   // [n]
+    float* edge;      // [n]  edge[k] = d[tour[k-1], tour[k]], edge[0] = d[tour[n-1], tour[0]]
+    float* rows;      // [W][2][n]
+    float* red_c;     // [W]
+    uint32_t* red_k;  // [W]
+    int* band;        // [W+1]
+};
+
+// one 2-opt call: up to max_iterations passes on the tour in shared memory; returns passes done
+__device__ int two_opt_call(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    float* rowA = S.rows + (size_t)warp * 2 * n;
+    float* rowB = rowA + n;
+    int it = 0;
+    while (it < max_iterations) {
+        __syncthreads();
+        for (int k = tid; k < n; k += blockDim.x) {
+            const int a = S.tour[k == 0 ? n - 1 : k - 1], b = S.tour[k];
+            S.edge[k] = __ldg(D + (size_t)a * n + b);
+        }
+        __syncthreads();
+        float best = 0.f;                 // delta starts at 0 (two_opt.py:10)
+        uint32_t bestkey = 0xffffffffu;
+        const int lo = S.band[warp], hi = S.band[warp + 1];
+        float* rp = rowA;                 // d[tour[i-1], :]
+        float* ri = rowB;                 // d[tour[i], :]
+        if (lo < hi) {
+            const float* src = D + (size_t)S.tour[lo - 1] * n;
+            for (int c = lane; c < n; c += 32) rp[c] = __ldg(src + c);
+        }
+        for (int i = lo; i < hi; ++i) {
+            const int ni = S.tour[i];
+            const float* src = D + (size_t)ni * n;
+            for (int c = lane; c < n; c += 32) ri[c] = __ldg(src + c);
+            __syncwarp();
+            const int p = S.tour[i - 1];
+            const float e_i = S.edge[i];
+            for (int j = i + 1 + lane; j < n; j += 32) {
+                const int nj = S.tour[j];
+                const int jn = (j + 1 == n) ? 0 : j + 1;
+                const int nx = S.tour[jn];
+                if (p == nj || nx == ni) continue;
+                const float change = __fsub_rn(__fsub_rn(__fadd_rn(rp[nj], ri[nx]), e_i), S.edge[jn]);
+                if (change < best) {      // strict: first minimum in (i, j) order within this lane's sweep
+                    best = change;
+                    bestkey = (uint32_t)i * (uint32_t)n + (uint32_t)j;
+                }
+            }
+            __syncwarp();
+            float* t = rp; rp = ri; ri = t;
+        }
+        // CTA arg-min with lowest key on ties (== first strict minimum of the sequential scan)
+        for (int off = 16; off > 0; off >>= 1) {
+            const float oc = __shfl_xor_sync(DACO_FULL, best, off);
+            const uint32_t ok = __shfl_xor_sync(DACO_FULL, bestkey, off);
+            if (oc < best || (oc == best && ok < bestkey)) { best = oc; bestkey = ok; }
+        }
+        if (lane == 0) { S.red_c[warp] = best; S.red_k[warp] = bestkey; }
+        __syncthreads();
+        best = S.red_c[0];
+        bestkey = S.red_k[0];
+        for (int w = 1; w < W; ++w) {
+            const float oc = S.red_c[w];
+            const uint32_t ok = S.red_k[w];
+            if (oc < best || (oc == best && ok < bestkey)) { best = oc; bestkey = ok; }
+        }
+        ++it;
+        if (!((double)best < -1e-6)) break;   // two_opt.py:24,36
+        const int i = (int)(bestkey / (uint32_t)n), j = (int)(bestkey % (uint32_t)n);
+        __syncthreads();
+        for (int k = tid; k < (j - i + 1) / 2; k += blockDim.x) {
+            const uint16_t x = S.tour[i + k];
+            S.tour[i + k] = S.tour[j - k];
+            S.tour[j - k] = x;
+        }
+    }
+    __syncthreads();
+    return it;
+}
+
+__device__ float tour_cost_numpy(const float* __restrict__ D, int n, const uint16_t* tour) {
+    auto f = [&](int k) -> float { return __ldg(D + (size_t)tour[k] * n + tour[k == 0 ? n - 1 : k - 1]); };
+    return numpy_pairwise_sum(f, 0, n);
+}
+
+// mode 0: one 2-opt call (ACO.two_opt); mode 1: NLS (ACO.nls)
+__global__ void __launch_bounds__(256) two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dist,
+                                                      uint16_t* __restrict__ tours, int n, int A, int mode, int maxt,
+                                                      int T_nls, int T_p, float* __restrict__ costs_out,
+                                                      int32_t* __restrict__ passes_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, W = blockDim.x >> 5;
+    const int a = blockIdx.x, b = blockIdx.y;
+    TwoOptShared S;
+    S.rows = reinterpret_cast<float*>(smem);
+    S.edge = S.rows + (size_t)W * 2 * n;
+    S.red_c = S.edge + n;
+    S.red_k = reinterpret_cast<uint32_t*>(S.red_c + W);
+    S.band = reinterpret_cast<int*>(S.red_k + W);
+    S.tour = reinterpret_cast<uint16_t*>(S.band + W + 1);
+    uint16_t* best_tour = S.tour + n;   // NLS only
+    __shared__ float s_best_cost, s_new_cost;
+
+    const float* D = dist + (size_t)b * n * n;
+    const float* H = heu_dist ? heu_dist + (size_t)b * n * n : nullptr;
+    uint16_t* T = tours + ((size_t)b * A + a) * n;
+    for (int k = tid; k < n; k += blockDim.x) S.tour[k] = T[k];
+    if (tid == 0) {
+        // bands of i in [1, n-1) with ~equal numbers of (i, j) pairs
+        const long total = (long)(n - 2) * (n - 1) / 2;
+        int i = 1;
+        long acc = 0;
+        S.band[0] = 1;
+        for (int w = 1; w <= W; ++w) {
+            const long target = total * w / W;
+            while (i < n - 1 && acc < target) { acc += n - 1 - i; ++i; }
+            S.band[w] = (w == W) ? n - 1 : i;
+        }
+    }
+    __syncthreads();
+    int passes = two_opt_call(D, n, maxt, S);
+    if (mode == 1) {
+        for (int k = tid; k < n; k += blockDim.x) best_tour[k] = S.tour[k];
+        if (tid == 0) s_best_cost = tour_cost_numpy(D, n, S.tour);
+        __syncthreads();
+        for (int r = 0; r < T_nls; ++r) {
+            passes += two_opt_call(H, n, T_p, S);      // perturbation on the heuristic "distance"
+            passes += two_opt_call(D, n, maxt, S);
+            if (tid == 0) s_new_cost = tour_cost_numpy(D, n, S.tour);
+            __syncthreads();
+            if (s_new_cost < s_best_cost) {            // tsp_nls/aco.py:252-254
+                for (int k = tid; k < n; k += blockDim.x) best_tour[k] = S.tour[k];
+                __syncthreads();
+                if (tid == 0) s_best_cost = s_new_cost;
+            }
+            __syncthreads();
+        }
+        for (int k = tid; k < n; k += blockDim.x) T[k] = best_tour[k];
+        if (costs_out && tid == 0) costs_out[(size_t)b * A + a] = s_best_cost;
+    } else {
+        for (int k = tid; k < n; k += blockDim.x) T[k] = S.tour[k];
+    }
+    if (passes_out && tid == 0) passes_out[(size_t)b * A + a] = passes;
+}
+
+}  // namespace deepaco
+
+using namespace deepaco;
+
+static int launch_two_opt(const float* dist, const float* heu_dist, uint16_t* tours, int n, int A, int B, int mode, int maxt,
+                          int T_nls, int T_p, float* costs_out, int32_t* passes_out, cudaStream_t st) {
+    const DeviceInfo* di = device_info();
+    if (!di) return DEEPACO_ENODEV;
+    DACO_CHECK_ARG(dist && tours, "deepaco_two_opt: NULL argument");
+    DACO_CHECK_ARG(n >= 4 && n <= 65535 && A >= 1 && B >= 1 && B <= 65535, "deepaco_two_opt: bad sizes (n >= 4)");
+    DACO_CHECK_ARG(maxt >= 0 && T_nls >= 0 && T_p >= 0, "deepaco_two_opt: negative iteration count");
+    const int W = 8;
+    const size_t smem = ((size_t)W * 2 * n + n + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)2 * n * 2 + 16;
+    DACO_CHECK_ARG(smem <= (size_t)di->max_smem_optin - 1024, "deepaco_two_opt: n=%d does not fit shared memory", n);
+    DACO_CHECK_CUDA(cudaFuncSetAttribute(two_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(A, B);
+    two_opt_kernel<<<grid, W * 32, smem, st>>>(dist, heu_dist, tours, n, A, mode, maxt, T_nls, T_p, costs_out, passes_out);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+extern "C" int deepaco_two_opt(const float* distances, uint16_t* tours, int n, int n_ants, int n_colonies,
+                               int max_iterations, int32_t* passes_out, void* stream) {
+    return launch_two_opt(distances, nullptr, tours, n, n_ants, n_colonies, 0, max_iterations, 0, 0, nullptr, passes_out,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int deepaco_tsp_nls(const float* distances, const float* heuristic_dist, uint16_t* tours, int n, int n_ants,
+                               int n_colonies, int max_iterations, int T_nls, int T_p, float* costs_out,
+                               int32_t* passes_out, void* stream) {
+    DACO_CHECK_ARG(heuristic_dist != nullptr, "deepaco_tsp_nls: heuristic_dist is NULL");
+    return launch_two_opt(distances, heuristic_dist, tours, n, n_ants, n_colonies, 1, max_iterations, T_nls, T_p, costs_out,
+                          passes_out, (cudaStream_t)stream);
+}
+
+// tour layout conversion helpers for the Python boundary: paths int64 [B][n][A] <-> tours u16 [B][A][n]
+namespace deepaco {
+__global__ void paths_to_tours_kernel(const int64_t* __restrict__ paths, uint16_t* __restrict__ tours, int n, int A, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / ((size_t)n * A), r = i % ((size_t)n * A);
+        const int a = (int)(r / n), k = (int)(r % n);
+        tours[i] = (uint16_t)paths[(b * n + k) * A + a];
+    }
+}
+__global__ void tours_to_paths_kernel(const uint16_t* __restrict__ tours, int64_t* __restrict__ paths, int n, int A, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / ((size_t)n * A), r = i % ((size_t)n * A);
+        const int k = (int)(r / A), a = (int)(r % A);
+        paths[i] = (int64_t)tours[(b * A + a) * n + k];
+    }
+}
+}  // namespace deepaco
+
+extern "C" int deepaco_paths_to_tours(const int64_t* paths, uint16_t* tours, int n, int n_ants, int n_colonies, void* stream) {
+    DACO_CHECK_ARG(paths && tours && n >= 1 && n_ants >= 1 && n_colonies >= 1, "deepaco_paths_to_tours: bad arguments");
+    const size_t total = (size_t)n_colonies * n * n_ants;
+    paths_to_tours_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(paths, tours, n, n_ants, total);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+extern "C" int deepaco_tours_to_paths(const uint16_t* tours, int64_t* paths, int n, int n_ants, int n_colonies, void* stream) {
+    DACO_CHECK_ARG(paths && tours && n >= 1 && n_ants >= 1 && n_colonies >= 1, "deepaco_tours_to_paths: bad arguments");
+    const size_t total = (size_t)n_colonies * n * n_ants;
+    tours_to_paths_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(tours, paths, n, n_ants, total);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}

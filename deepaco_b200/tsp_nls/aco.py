@@ -1,0 +1,107 @@
+"""`ACO` for TSP with neural-guided local search: the class surface of reference tsp_nls/aco.py:10-258.
+
+Differences from `deepaco_b200.tsp.aco.ACO` (as in the reference): every ant starts at node 0, the
+probability row is normalised once before `Categorical` normalises it again (tsp_nls/aco.py:205-207),
+`sample()` also returns the paths, and `run()` applies 2-opt / NLS to the sampled tours before the
+pheromone update.  The local search runs on the GPU (deepaco_two_opt / deepaco_tsp_nls), bit-exact with
+the reference's numba code, so no tour ever crosses to the host.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _engine as E
+from .._lib import generator_state
+from ..tsp.aco import ACO as _TspACO
+
+
+class ACO(_TspACO):
+    _START_NODE = 0          # tsp_nls/aco.py:191
+    _DOUBLE_NORM = True      # tsp_nls/aco.py:206 + Categorical's own normalisation
+
+    def __init__(self, distances, n_ants=20, decay=0.9, alpha=1, beta=1, elitist=False, min_max=False,
+                 pheromone=None, heuristic=None, min=None, two_opt=False, device='cpu', local_search='nls'):
+        super().__init__(distances, n_ants=n_ants, decay=decay, alpha=alpha, beta=beta, elitist=elitist,
+                         min_max=min_max, pheromone=pheromone, heuristic=heuristic, min=min, device=device)
+        assert local_search in [None, "2opt", "nls"]
+        self.local_search_type = '2opt' if two_opt else local_search
+        self._heuristic_dist = None
+
+    # ---- sampling ----------------------------------------------------------------------------
+    def sample(self, inference=False):
+        '''tsp_nls/aco.py:80-90.  inference=True replaces the numba roulette sampler (whose RNG is numba's own,
+        not reproducible from torch) by the same on-device Categorical construction without log-probs.'''
+        if inference:
+            paths = self.gen_path(require_prob=False)
+            return self.gen_path_costs(paths), None, paths
+        paths, log_probs = self.gen_path(require_prob=True)
+        return self.gen_path_costs(paths), log_probs, paths
+
+    def sample_2opt(self, paths):
+        paths = self.local_search(paths)
+        return self.gen_path_costs(paths), paths
+
+    # ---- local search --------------------------------------------------------------------------
+    @property
+    def heuristic_dist(self):
+        '''1 / (heuristic / rowmax + 1e-5)  (tsp_nls/aco.py:230-232), fp32 on the device.'''
+        if self._heuristic_dist is None:
+            h = self.heuristic.detach().to(torch.float32)
+            self._heuristic_dist = (1 / (h / h.max(-1, keepdim=True).values + 1e-5)).contiguous()
+        return self._heuristic_dist
+
+    def _max_passes(self, inference):
+        return 10000 if inference else self.problem_size // 4      # tsp_nls/aco.py:235
+
+    @torch.no_grad()
+    def two_opt(self, paths, inference=False):
+        tours = E.paths_to_tours(paths)
+        E.two_opt_(self.distances, tours, self._max_passes(inference))
+        return E.tours_to_paths(tours)
+
+    @torch.no_grad()
+    def nls(self, paths, inference=False, T_nls=10, T_p=20):
+        tours = E.paths_to_tours(paths)
+        E.tsp_nls_(self.distances, self.heuristic_dist, tours, self._max_passes(inference), T_nls, T_p)
+        return E.tours_to_paths(tours)
+
+    def local_search(self, paths, inference=False):
+        if self.local_search_type == "2opt":
+            return self.two_opt(paths, inference)
+        if self.local_search_type == "nls":
+            return self.nls(paths, inference)
+        return paths
+
+    # ---- run -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, n_iterations, inference=False):
+        '''tsp_nls/aco.py:104-129; returns lowest_cost as a Python float like the reference (:120).'''
+        if self.local_search_type is None:
+            low = super().run(n_iterations)
+            return float(low)
+        for _ in range(n_iterations):
+            ph, heu = self._weights()
+            gen, seed, offset = generator_state(self.device)
+            _, _, tours = E.tsp_sample(ph.detach(), heu.detach(), self.n_ants, start_node=0, double_norm=True, seed=seed,
+                                       offset=offset, want_paths=False, want_tours=True)
+            gen.set_offset(offset + E.tsp_sample_offset_increment(self.problem_size, self.n_ants, 0))
+            if self.local_search_type == "2opt":
+                E.two_opt_(self.distances, tours, self._max_passes(inference))
+            else:
+                E.tsp_nls_(self.distances, self.heuristic_dist, tours, self._max_passes(inference))
+            costs, nbr = E.tsp_cost(self.distances, tours=tours, want_neighbours=True)
+            best = torch.argmin(costs)
+            if float(costs[best]) < float(self._lowest_cost):            # .item() as in the reference (:120)
+                self._shortest_path = tours[best].to(torch.int64)
+                self._lowest_cost = float(costs[best])
+                if self.min_max:
+                    new_max = self.problem_size / self._lowest_cost
+                    if self.max is None:
+                        self._pheromone = self._pheromone * (new_max / self._pheromone.max())
+                    self.max = new_max
+            newph = self._pheromone.detach().to(torch.float32).clone(memory_format=torch.contiguous_format)
+            E.tsp_update_(newph, nbr, costs, decay=self.decay, elitist=self.elitist, min_max=self.min_max,
+                          ph_min=self.min if self.min_max else 0.0, ph_max=self.max if self.min_max else None)
+            self._pheromone = newph
+            self._runner = None
+        return self._lowest_cost

@@ -49,7 +49,7 @@ int deepaco_aten_sum_plan(int row_len, int n_rows, int* block_width_out, int* ve
  * tsp_nls/aco.py:184-220 (start_node = 0, double_norm = 1).
  * Noise: when `noise` is NULL the kernel regenerates, in registers, exactly the Philox words torch's
  * `randint` / `exponential_` kernels would draw from (seed, offset); batched colonies share the seed and
- * take their Philox offset from offsets[b] (device uint64 [B]; NULL = the by-value offset for all) --
+ * take their Philox offset from offsets[b] + offset (offsets: device uint64 [B], NULL = 0) --
  * i.e. colony b sees the stream the reference would have reached had it processed the colonies one
  * after another under one generator.  The caller advances its generator by
  * deepaco_tsp_sample_offset_increment() per colony.
@@ -76,6 +76,65 @@ int deepaco_tsp_cost(const float* distances, const int64_t* paths, const uint16_
 int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants,
                        int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
                        void* stream);
+
+/* ---- ACO.run for TSP (tsp/aco.py:74-92; tsp_nls/aco.py:104-129 with local_search=None) -------------
+ * n_iterations x { sample -> cost -> best tracking -> evaporate+deposit } on `stream`, no host sync.
+ * All buffers are caller-owned device memory:
+ *   pheromone [B][n][n] in/out; heuristic, distances [B][n][n] in;
+ *   product [B][n][n] scratch holding pheromone (.) heuristic (product_valid = 1 if already up to date);
+ *   tours u16 [B][A][n], costs f32 [B][A], neighbours u32 [B][n][A]: scratch, hold the LAST iteration;
+ *   lowest_cost f32 [B] in/out (+inf before the first run); shortest_path i64 [B][n] in/out;
+ *   ph_max f32 [B] in/out (min_max only; 0 = not set yet); scale f32 [B] scratch (min_max only).
+ * Iteration t of colony b consumes the Philox stream at offsets[b] + offset + t * increment, increment =
+ * deepaco_tsp_sample_offset_increment(): exactly the reference's generator consumption. */
+typedef struct {
+    int n, n_ants, n_colonies;
+    int start_node;   /* -1: torch.randint start (tsp/);  0: fixed start (tsp_nls/) */
+    int double_norm;  /* 1 for tsp_nls/ */
+    float decay;
+    int elitist, min_max;
+    float ph_min;
+    uint64_t seed, offset;
+    const uint64_t* offsets;
+    float* pheromone;
+    const float* heuristic;
+    const float* distances;
+    float* product;
+    int product_valid;
+    uint16_t* tours;
+    float* costs;
+    uint32_t* neighbours;
+    float* lowest_cost;
+    int64_t* shortest_path;
+    float* ph_max;
+    float* scale;
+    void* ev_sample_begin; /* optional cudaEvent_t recorded before / after each sampling launch (profiling) */
+    void* ev_sample_end;
+} deepaco_tsp_run_args;
+int deepaco_tsp_run(const deepaco_tsp_run_args* args, int n_iterations, void* stream);
+/* Same with HOST matrices ([B][n][n] fp32 each): H2D of distances, heuristic, pheromone into the device
+ * buffers of `args`, n_iterations, D2H of pheromone, lowest_cost [B], shortest_path [B][n]; synchronises
+ * `stream` before returning.  Bytes moved: 3 * B*n*n*4 in, B*n*n*4 + B*4 + B*n*8 out. */
+int deepaco_tsp_run_host(const deepaco_tsp_run_args* args, int n_iterations, const float* distances_host,
+                         const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
+                         int64_t* shortest_path_host, void* stream);
+
+/* ---- local search (tsp_nls/two_opt.py:6-49, tsp_nls/aco.py:234-258) ---------------------------------
+ * In place on compact tours (u16 [B][A][n]); one CTA per tour, bit-exact with the reference's numba code
+ * (first strict minimum in (i,j) scan order, fp32 left-to-right delta, threshold -1e-6).
+ * deepaco_two_opt  = batched_two_opt_python(dist, tours, max_iterations).
+ * deepaco_tsp_nls  = ACO.nls: 2-opt(dist, max_iterations), then T_nls x { 2-opt(heuristic_dist, T_p),
+ *                    2-opt(dist, max_iterations), keep if numpy-summed cost strictly improves }.
+ * passes_out (optional int32 [B][A]) = total 2-opt passes executed; costs_out (optional f32 [B][A]) = the
+ * numpy-order cost of the kept tour. */
+int deepaco_two_opt(const float* distances, uint16_t* tours, int n, int n_ants, int n_colonies, int max_iterations,
+                    int32_t* passes_out, void* stream);
+int deepaco_tsp_nls(const float* distances, const float* heuristic_dist, uint16_t* tours, int n, int n_ants,
+                    int n_colonies, int max_iterations, int T_nls, int T_p, float* costs_out, int32_t* passes_out,
+                    void* stream);
+/* layout conversion between the reference's paths (int64 [B][n][A]) and compact tours (u16 [B][A][n]) */
+int deepaco_paths_to_tours(const int64_t* paths, uint16_t* tours, int n, int n_ants, int n_colonies, void* stream);
+int deepaco_tours_to_paths(const uint16_t* tours, int64_t* paths, int n, int n_ants, int n_colonies, void* stream);
 
 /* ---- CVRP (cvrp/aco.py:106-205, adaptive = False) ----------------------------------------------
  * Node 0 is the depot; n_nodes = customers + 1; demand fp32 [B][n_nodes] (demand[0] = 0).

@@ -1,0 +1,74 @@
+"""K4 parity: GPU 2-opt / NLS vs golden vectors of the reference's numba code and vs the C oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run_two_opt(dist, tours_np, it):
+    from deepaco_b200 import _engine as E
+    t = torch.from_numpy(tours_np.astype(np.uint16)).to(DEV)
+    E.two_opt_(torch.from_numpy(dist).to(DEV), t, it)
+    return t.cpu().numpy().astype(np.int16)
+
+
+def test_two_opt_matches_reference_golden(golden):
+    g = golden("two_opt_n60")
+    for it in (1, 5, 1000):
+        assert np.array_equal(_run_two_opt(g["dist"], g["tours"], it), g[f"out_it{it}"])
+
+
+def test_two_opt_and_nls_on_gnn_instance_match_reference_golden(golden):
+    from deepaco_b200 import _engine as E
+    g = golden("tsp_nls_n200_a16")
+    tours = g["paths_seed12345"].T
+    n = tours.shape[1]
+    assert np.array_equal(_run_two_opt(g["dist"], tours, n // 4), g["two_opt_train"].T)
+    assert np.array_equal(_run_two_opt(g["dist"], tours, 10000), g["two_opt_inference"].T)
+    assert np.array_equal(_run_two_opt(g["heuristic_dist"], tours, 20), g["two_opt_heudist_20"])
+    t = torch.from_numpy(tours.astype(np.uint16)).to(DEV)
+    E.tsp_nls_(torch.from_numpy(g["dist"]).to(DEV), torch.from_numpy(g["heuristic_dist"]).to(DEV), t, n // 4)
+    assert np.array_equal(t.cpu().numpy().astype(np.int16), g["nls_train"].T)
+
+
+@pytest.mark.parametrize("n,count,it", [(5, 7, 100), (33, 20, 3), (120, 40, 1000), (500, 24, 125), (1000, 4, 30)])
+def test_two_opt_matches_c_oracle_on_random_tours(n, count, it):
+    from oracle import two_opt as T2
+    rng = np.random.default_rng(n)
+    xy = rng.random((n, 2), dtype=np.float32)
+    dist = np.sqrt(((xy[:, None] - xy[None]) ** 2).sum(-1)).astype(np.float32)
+    np.fill_diagonal(dist, 1e9)
+    tours = np.stack([np.concatenate(([0], 1 + rng.permutation(n - 1))) for _ in range(count)]).astype(np.uint16)
+    ref = T2.batched_two_opt(dist, tours, it)
+    assert np.array_equal(_run_two_opt(dist, tours, it), ref.astype(np.int16))
+
+
+def test_nls_matches_c_oracle_and_class_api():
+    from deepaco_b200.tsp_nls.aco import ACO
+    from oracle import two_opt as T2
+    n, A = 100, 16
+    torch.manual_seed(3)
+    xy = torch.rand(n, 2, device=DEV)
+    dist = torch.norm(xy[:, None] - xy, dim=2, p=2)
+    dist[torch.arange(n), torch.arange(n)] = 1e9
+    k = 10
+    _, idx = torch.topk(dist, k, dim=1, largest=False)
+    heu = torch.full_like(dist, 1e-10)
+    heu.scatter_(1, idx, torch.rand(n, k, device=DEV) * 0.9 + 0.05)
+    aco = ACO(dist, n_ants=A, heuristic=heu, device=DEV, local_search='nls')
+    paths = aco.gen_path()
+    assert (paths[0] == 0).all()
+    out = aco.nls(paths)
+    ref = T2.nls(dist.cpu().numpy(), aco.heuristic_dist.cpu().numpy(), paths.T.cpu().numpy(), n // 4)
+    assert np.array_equal(out.T.cpu().numpy(), ref.astype(np.int64))
+    out2 = aco.two_opt(paths, inference=True)
+    ref2 = T2.batched_two_opt(dist.cpu().numpy(), paths.T.cpu().numpy(), 10000)
+    assert np.array_equal(out2.T.cpu().numpy(), ref2.astype(np.int64))
+    # 2-opt never lengthens a tour and keeps it a permutation starting at node 0
+    c0, c1 = aco.gen_path_costs(paths), aco.gen_path_costs(out2)
+    assert (c1 <= c0 + 1e-5).all()
+    assert torch.equal(torch.sort(out2, dim=0).values, torch.arange(n, device=DEV)[:, None].expand(n, A))
+    low = aco.run(2)
+    assert isinstance(low, float) and low <= float(c1.min()) * 1.5

@@ -121,3 +121,32 @@ def test_cvrp_n100_gnn(golden):
     low = col.run(3)
     assert np.array_equal(np.asarray(low), g["run3_lowest_seed4321"])
     assert np.array_equal(col.pheromone.numpy(), g["run3_pheromone_seed4321"])
+
+
+# ---- 2-opt / NLS oracle (plain C restatement) vs the reference's numba implementation ---------------
+def test_two_opt_oracle_matches_reference(golden):
+    from oracle import two_opt as T2
+    g = golden("two_opt_n60")
+    for it in (1, 5, 1000):
+        out = T2.batched_two_opt(g["dist"], g["tours"], it)
+        assert np.array_equal(out.astype(np.int16), g[f"out_it{it}"])
+
+
+def test_two_opt_and_nls_oracle_on_gnn_instance(golden):
+    from oracle import two_opt as T2
+    g = golden("tsp_nls_n200_a16")
+    tours = g["paths_seed12345"].T.astype(np.uint16)
+    n = tours.shape[1]
+    assert np.array_equal(T2.batched_two_opt(g["dist"], tours, n // 4).astype(np.int16), g["two_opt_train"].T)
+    assert np.array_equal(T2.batched_two_opt(g["dist"], tours, 10000).astype(np.int16), g["two_opt_inference"].T)
+    assert np.array_equal(T2.batched_two_opt(g["heuristic_dist"], tours, 20).astype(np.int16), g["two_opt_heudist_20"])
+    assert np.array_equal(T2.nls(g["dist"], g["heuristic_dist"], tours, n // 4).astype(np.int16), g["nls_train"].T)
+
+
+def test_numpy_pairwise_sum_restatement():
+    from oracle import two_opt as T2
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 8, 9, 60, 127, 128, 129, 200, 500, 1000, 1031):
+        for _ in range(5):
+            row = rng.random(n, dtype=np.float32) * 3
+            assert T2.numpy_pairwise_sum(row) == np.sum(row.reshape(1, -1), axis=1)[0]
