@@ -137,11 +137,13 @@ class TspRunner:
         self.B, self.n = _colonies(self.distances)
         self.batched = self.distances.dim() == 3
         dev = self.dev = self.distances.device
+        shp = (self.B, self.n, self.n)
         self.heuristic = f32c(require_cuda(heuristic, "heuristic").detach())
         self.pheromone = pheromone.detach().to(torch.float32).clone(memory_format=torch.contiguous_format)
-        shp = (self.B, self.n, self.n)
         if self.heuristic.numel() != self.B * self.n * self.n or self.pheromone.numel() != self.B * self.n * self.n:
             raise _lib.DeepAcoError("distances / heuristic / pheromone shape mismatch")
+        # all state is kept with an explicit leading colony dimension
+        self.distances, self.heuristic, self.pheromone = (t.reshape(shp) for t in (self.distances, self.heuristic, self.pheromone))
         self.n_ants = int(n_ants)
         self.product = torch.empty(shp, dtype=torch.float32, device=dev)
         self.product_valid = False
