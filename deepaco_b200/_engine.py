@@ -159,8 +159,11 @@ class TspRunner:
         self.increment = tsp_sample_offset_increment(self.n, self.n_ants, self.start_node)
 
     def _args(self, seed, offset, offs, events=None):
-        ev0 = events[0].cuda_event if events else None
-        ev1 = events[1].cuda_event if events else None
+        ev0 = ev1 = None
+        if events:
+            for ev in events:      # torch creates the cudaEvent_t lazily on the first record()
+                ev.record(torch.cuda.current_stream(self.dev))
+            ev0, ev1 = events[0].cuda_event, events[1].cuda_event
         return _lib.TspRunArgs(self.n, self.n_ants, self.B, self.start_node, int(self.double_norm), self.decay,
                                int(self.elitist), int(self.min_max), self.ph_min, int(seed), int(offset), ptr(offs),
                                ptr(self.pheromone), ptr(self.heuristic), ptr(self.distances), ptr(self.product),
@@ -218,10 +221,17 @@ def tours_to_paths(tours):
     return paths if batched else paths[0]
 
 
+def _check_tours(tours, n):
+    require_cuda(tours, "tours")
+    if tours.dtype != torch.uint16 or not tours.is_contiguous() or tours.shape[-1] != n:
+        raise _lib.DeepAcoError("tours must be a contiguous uint16 tensor [..., n_ants, n] (in-place local search)")
+
+
 def two_opt_(distances, tours, max_iterations, *, want_passes=False):
     """deepaco_two_opt in place on uint16 tours [A, n] | [B, A, n]."""
     distances = f32c(require_cuda(distances, "distances"))
     B, n = _colonies(distances)
+    _check_tours(tours, n)
     A = tours.shape[-2]
     passes = torch.empty((B, A), dtype=torch.int32, device=tours.device) if want_passes else None
     with torch.cuda.device(tours.device):
@@ -235,6 +245,7 @@ def tsp_nls_(distances, heuristic_dist, tours, max_iterations, T_nls=10, T_p=20,
     distances = f32c(require_cuda(distances, "distances"))
     heuristic_dist = f32c(require_cuda(heuristic_dist, "heuristic_dist"))
     B, n = _colonies(distances)
+    _check_tours(tours, n)
     A = tours.shape[-2]
     passes = torch.empty((B, A), dtype=torch.int32, device=tours.device) if want_passes else None
     with torch.cuda.device(tours.device):

@@ -1,0 +1,27 @@
+"""Instance -> graph helpers with the reference's names (reference tsp/utils.py:4-36).  One-off set-up per instance."""
+import torch
+
+from ..net import Data
+
+
+def gen_distance_matrix(tsp_coordinates):
+    '''[n, 2] coordinates -> [n, n] Euclidean distances with 1e9 on the diagonal (tsp/utils.py:4-14).'''
+    n = len(tsp_coordinates)
+    d = torch.norm(tsp_coordinates[:, None] - tsp_coordinates, dim=2, p=2)
+    d[torch.arange(n), torch.arange(n)] = 1e9
+    return d
+
+
+def gen_pyg_data(tsp_coordinates, k_sparse, start_node=None):
+    '''k-nearest-neighbour graph (tsp/utils.py:16-36; start_node one-hot node feature as tsp_nls/utils.py:37-43).'''
+    n = len(tsp_coordinates)
+    distances = gen_distance_matrix(tsp_coordinates)
+    near_d, near_i = torch.topk(distances, k=k_sparse, dim=1, largest=False)
+    src = torch.arange(n, device=near_i.device).repeat_interleave(k_sparse)
+    edge_index = torch.stack([src, near_i.flatten()])
+    if start_node is None:
+        x = tsp_coordinates
+    else:
+        x = torch.zeros((n, 1), device=tsp_coordinates.device, dtype=tsp_coordinates.dtype)
+        x[start_node, 0] = 1.0
+    return Data(x=x, edge_index=edge_index, edge_attr=near_d.reshape(-1, 1)), distances

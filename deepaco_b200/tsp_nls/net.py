@@ -1,0 +1,7 @@
+"""`Net` for tsp_nls/ (feats = 1: one-hot start node, reference tsp_nls/net.py:9; no par_net_phe)."""
+from ..net import Data, EmbNet, MLP, Net as _Net, ParNet, load_npz_state_dict  # noqa: F401
+
+
+class Net(_Net):
+    FEATS = 1
+    HAS_PHE_HEAD = False

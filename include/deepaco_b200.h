@@ -136,6 +136,17 @@ int deepaco_tsp_nls(const float* distances, const float* heuristic_dist, uint16_
 int deepaco_paths_to_tours(const int64_t* paths, uint16_t* tours, int n, int n_ants, int n_colonies, void* stream);
 int deepaco_tours_to_paths(const uint16_t* tours, int64_t* paths, int n, int n_ants, int n_colonies, void* stream);
 
+/* ---- heuristic network forward, eval mode (Net.forward, tsp/net.py:84-88 -> EmbNet :27-45 -> ParNet :74-75)
+ * Graph per instance in CSR-by-source form: row_ptr int32 [B][n+1]; for the edges sorted by source:
+ * dst_sorted int32 [B][E], attr_sorted f32 [B][E], order int32 [B][E] (original edge id, used to write
+ * heu_out[b][order[e]]).  x: node features f32 [B][n][feats].  weights: packed fp32 (layout in
+ * deepaco_b200/net.py:pack_weights; deepaco_gnn_weight_count(feats) values).  node_ws f32 [B][n][192] and
+ * edge_ws f32 [B][E][32] are scratch.  heu_out f32 [B][E] = Net.forward(pyg) per original edge. */
+int64_t deepaco_gnn_weight_count(int feats);
+int deepaco_gnn_forward(const float* x, const int32_t* row_ptr, const int32_t* dst_sorted, const float* attr_sorted,
+                        const int32_t* order, const float* weights, int n_nodes, int n_edges, int feats,
+                        int n_instances, float* node_ws, float* edge_ws, float* heu_out, void* stream);
+
 /* ---- CVRP (cvrp/aco.py:106-205, adaptive = False) ----------------------------------------------
  * Node 0 is the depot; n_nodes = customers + 1; demand fp32 [B][n_nodes] (demand[0] = 0).
  * deepaco_cvrp_sample replaces ACO.gen_path + pick_move + update_visit_mask + update_capacity_mask +

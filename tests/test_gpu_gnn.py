@@ -1,0 +1,73 @@
+"""K3 parity: heuristic network forward (eval mode) vs the unmodified reference's output stored in the goldens
+(computed with the pretrained checkpoints; fp32 tolerance -- different GEMM summation order)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(net_cls, weights):
+    import os
+    from deepaco_b200.net import load_npz_state_dict
+    net = net_cls().to(DEV)
+    path = os.path.join(os.path.dirname(__file__), "golden", weights + ".npz")
+    missing = net.load_state_dict(load_npz_state_dict(path, DEV))
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return net.eval()
+
+
+def test_tsp100_heuristic_matches_reference(golden):
+    from deepaco_b200.tsp.net import Net
+    from deepaco_b200.tsp.utils import gen_pyg_data
+    g = golden("tsp_n100_a32_gnn")
+    net = _load(Net, "weights_tsp100")
+    pyg, dist = gen_pyg_data(torch.from_numpy(g["coords"]).to(DEV), 20)
+    assert np.array_equal(pyg.edge_index.cpu().numpy(), g["edge_index"])
+    with torch.no_grad():
+        vec = net(pyg)
+    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-4, atol=1e-6)
+    heu = net.reshape(pyg, vec) + 1e-10
+    assert torch.allclose(heu.cpu(), torch.from_numpy(g["heuristic"]), rtol=2e-4, atol=1e-6)
+    # the kernel and the tensor-op (train-mode) formulation agree when BatchNorm uses running statistics
+    net.emb_net.train(False)
+    with torch.no_grad():
+        ref = net.par_net_heu(net.emb_net(pyg.x, pyg.edge_index, pyg.edge_attr))
+    assert torch.allclose(vec, ref, rtol=2e-4, atol=1e-6)
+
+
+def test_tsp_nls_and_cvrp_heuristics_match_reference(golden):
+    from deepaco_b200.cvrp.net import Net as CNet
+    from deepaco_b200.cvrp.utils import gen_pyg_data as cvrp_graph
+    from deepaco_b200.tsp_nls.net import Net as NNet
+    from deepaco_b200.tsp_nls.utils import gen_pyg_data
+    g = golden("tsp_nls_n200_a16")
+    net = _load(NNet, "weights_tsp_nls500")
+    pyg, _ = gen_pyg_data(torch.from_numpy(g["coords"]).to(DEV), 20, start_node=0)
+    with torch.no_grad():
+        vec = net(pyg)
+    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-4, atol=1e-6)
+    g = golden("cvrp_n100_a32_gnn")
+    net = _load(CNet, "weights_cvrp100")
+    pyg = cvrp_graph(torch.from_numpy(g["demand"]).to(DEV), torch.from_numpy(g["dist"]).to(DEV), DEV)
+    with torch.no_grad():
+        vec = net(pyg)
+    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-4, atol=1e-6)
+
+
+def test_batched_forward_equals_single():
+    from deepaco_b200.net import gnn_forward
+    from deepaco_b200.tsp.net import Net
+    from deepaco_b200.tsp.utils import gen_pyg_data
+    net = _load(Net, "weights_tsp100")
+    torch.manual_seed(5)
+    coords = torch.rand(6, 100, 2, device=DEV)
+    graphs = [gen_pyg_data(coords[b], 20)[0] for b in range(6)]
+    x = torch.stack([g.x for g in graphs])
+    ei = torch.stack([g.edge_index for g in graphs])
+    ea = torch.stack([g.edge_attr for g in graphs])
+    out = gnn_forward(net._weights(), 2, x, ei, ea)
+    for b in range(6):
+        with torch.no_grad():
+            assert torch.equal(out[b], net(graphs[b]))

@@ -9,7 +9,7 @@ DEV = "cuda"
 
 def _run_two_opt(dist, tours_np, it):
     from deepaco_b200 import _engine as E
-    t = torch.from_numpy(tours_np.astype(np.uint16)).to(DEV)
+    t = torch.from_numpy(np.ascontiguousarray(tours_np).astype(np.uint16)).to(DEV)
     E.two_opt_(torch.from_numpy(dist).to(DEV), t, it)
     return t.cpu().numpy().astype(np.int16)
 
@@ -28,7 +28,7 @@ def test_two_opt_and_nls_on_gnn_instance_match_reference_golden(golden):
     assert np.array_equal(_run_two_opt(g["dist"], tours, n // 4), g["two_opt_train"].T)
     assert np.array_equal(_run_two_opt(g["dist"], tours, 10000), g["two_opt_inference"].T)
     assert np.array_equal(_run_two_opt(g["heuristic_dist"], tours, 20), g["two_opt_heudist_20"])
-    t = torch.from_numpy(tours.astype(np.uint16)).to(DEV)
+    t = torch.from_numpy(np.ascontiguousarray(tours).astype(np.uint16)).to(DEV)
     E.tsp_nls_(torch.from_numpy(g["dist"]).to(DEV), torch.from_numpy(g["heuristic_dist"]).to(DEV), t, n // 4)
     assert np.array_equal(t.cpu().numpy().astype(np.int16), g["nls_train"].T)
 
