@@ -45,7 +45,7 @@ def make_instances(B, seed, device):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons during the timed region (pynvml, 50 ms period)."""
+    """SM clock / throttle reasons during the timed region (pynvml, 10 ms period)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def finish(self):
         self._halt.set()

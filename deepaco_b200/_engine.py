@@ -32,6 +32,23 @@ def _offsets(offsets, B, dev):
     return t
 
 
+KNN_WIDTH = 32
+
+
+def sparse_candidates(heuristic, ratio=1e-6):
+    """Candidate lists for the kNN sampling kernel: uint8 [..., n, 32] = columns of the 32 largest heuristic
+    values per row, or None when the heuristic is not sparse (the 33rd largest value of a typical row is not
+    `ratio` times smaller than the largest) or n is outside (32, 256].  Set-up code, run once per instance."""
+    n = heuristic.shape[-1]
+    if n <= KNN_WIDTH or n > 256:
+        return None
+    vals, idx = torch.topk(heuristic.detach().to(torch.float32), KNN_WIDTH + 1, dim=-1)
+    rel = vals[..., KNN_WIDTH] / vals[..., 0].clamp(min=1e-30)
+    if float(rel.median()) > ratio:
+        return None
+    return idx[..., :KNN_WIDTH].to(torch.uint8).contiguous()
+
+
 def aten_sum_plan(row_len: int, n_rows: int):
     bw, vec, exact = C.c_int(), C.c_int(), C.c_int()
     check(lib().deepaco_aten_sum_plan(row_len, n_rows, C.byref(bw), C.byref(vec), C.byref(exact)), "aten_sum_plan")
@@ -39,7 +56,7 @@ def aten_sum_plan(row_len: int, n_rows: int):
 
 
 def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False, seed=0, offset=0, offsets=None,
-               noise=None, start=None, want_paths=True, want_logp=False, want_tours=False):
+               noise=None, start=None, want_paths=True, want_logp=False, want_tours=False, knn=None):
     """deepaco_tsp_sample.  Returns (paths|None, log_probs|None, tours|None) shaped like the inputs'
     batching: single colony -> paths [n, A]; batched -> [B, n, A]."""
     pheromone = f32c(require_cuda(pheromone, "pheromone"))
@@ -62,7 +79,7 @@ def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False
     with torch.cuda.device(dev):
         check(lib().deepaco_tsp_sample(ptr(pheromone), ptr(heuristic), n, n_ants, B, int(start_node), int(double_norm),
                                        int(seed), int(offset), ptr(_offsets(offsets, B, dev)), ptr(noise), ptr(start), ptr(paths), ptr(logp),
-                                       ptr(tours), stream_ptr(dev)), "deepaco_tsp_sample")
+                                       ptr(tours), ptr(knn), stream_ptr(dev)), "deepaco_tsp_sample")
     if not batched:
         paths = None if paths is None else paths[0]
         logp = None if logp is None else logp[0]
@@ -132,7 +149,7 @@ class TspRunner:
     """
 
     def __init__(self, distances, heuristic, pheromone, n_ants, *, decay=0.9, elitist=False, min_max=False,
-                 ph_min=0.0, start_node=-1, double_norm=False):
+                 ph_min=0.0, start_node=-1, double_norm=False, use_knn=True):
         self.distances = f32c(require_cuda(distances, "distances"))
         self.B, self.n = _colonies(self.distances)
         self.batched = self.distances.dim() == 3
@@ -157,6 +174,7 @@ class TspRunner:
         self.decay, self.elitist, self.min_max, self.ph_min = float(decay), bool(elitist), bool(min_max), float(ph_min)
         self.start_node, self.double_norm = int(start_node), bool(double_norm)
         self.increment = tsp_sample_offset_increment(self.n, self.n_ants, self.start_node)
+        self.knn = sparse_candidates(self.heuristic) if use_knn else None
 
     def _args(self, seed, offset, offs, events=None):
         ev0 = ev1 = None
@@ -168,7 +186,8 @@ class TspRunner:
                                int(self.elitist), int(self.min_max), self.ph_min, int(seed), int(offset), ptr(offs),
                                ptr(self.pheromone), ptr(self.heuristic), ptr(self.distances), ptr(self.product),
                                int(self.product_valid), ptr(self.tours), ptr(self.costs), ptr(self.neighbours),
-                               ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.ph_max), ptr(self.scale), ev0, ev1)
+                               ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.ph_max), ptr(self.scale), ptr(self.knn),
+                               ev0, ev1)
 
     def run(self, n_iterations, seed, offset=0, offsets=None, sample_events=None):
         """Launch n_iterations ACO iterations; colony b consumes offsets[b] + offset + t * self.increment.

@@ -21,7 +21,7 @@ _SIGNATURES = {
     "deepaco_version": (_i32, []),
     "deepaco_torch_draw_geometry": (_i32, [_i64, C.POINTER(C.c_uint32), C.POINTER(_u64)]),
     "deepaco_aten_sum_plan": (_i32, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
-    "deepaco_tsp_sample": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "deepaco_tsp_sample": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "deepaco_tsp_sample_offset_increment": (_u64, [_i32, _i32, _i32]),
     "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
@@ -49,7 +49,7 @@ class TspRunArgs(C.Structure):
                 ("seed", _u64), ("offset", _u64), ("offsets", _vp),
                 ("pheromone", _vp), ("heuristic", _vp), ("distances", _vp), ("product", _vp), ("product_valid", _i32),
                 ("tours", _vp), ("costs", _vp), ("neighbours", _vp), ("lowest_cost", _vp), ("shortest_path", _vp),
-                ("ph_max", _vp), ("scale", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
+                ("ph_max", _vp), ("scale", _vp), ("knn", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
 
 
 _SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])

@@ -31,6 +31,7 @@ struct ListParams {
     const uint64_t* offsets;   // [B] or null
     PhiloxRoundKeys keys;   // round keys of `seed`, host-computed: read straight from the constant bank
     const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
+    const uint8_t* knn;     // [B][n][32] per-row candidate columns for the kNN kernel, or null
     const int64_t* start;   // [B][A] or null
     int64_t* paths;         // [B][rows][A] or null
     float* logp;            // [B][rows-1][A] or null
@@ -302,6 +303,185 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
         uint16_t* out = p.tours + ((size_t)b * p.A + a0) * R;
         for (int i = tid; i < R * wvalid; i += nthreads) out[i] = tour_all[i];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kNN variant for sparse products (DeepACO's learned heuristic: a few edges per row carry almost all the
+// mass, the rest sit at the 1e-10 floor).  Lane l evaluates candidate knn[cur][l] only (one Philox per lane
+// and step).  Let T = max of the row over the columns NOT in knn[cur] (computed per row at staging).  A
+// column outside the list can only win if x_j / q_j > A_top, and q_j >= q_min = 2^-24 for every possible
+// noise word, so when T * 2^24 < A_top no unlisted column can win whatever its noise: the listed arg-max IS the
+// row's arg-max and the step is done.  Otherwise (about a fifth of the steps on the pretrained TSP-100
+// network) the step is evaluated densely over all unvisited nodes; near-ties go to exact_step() as before.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// dense evaluation of one step over all unvisited nodes (vis = visited bitmap words in shared memory)
+static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, const float* Psm, int cur, uint32_t* vis, uint32_t* alive_scratch,
+                                                uint32_t ctr_lo, uint32_t ctr_hi, uint64_t off_step, uint32_t sub_base) {
+    const int lane = threadIdx.x & 31, n = p.n;
+    const float* row = Psm + (size_t)cur * n;
+    float bestA = 0.f, second = 0.f;
+    uint32_t bestj = 0xffffffffu;
+    for (int j = lane; j < n; j += 32) {
+        const bool alive = !((vis[j >> 5] >> (j & 31)) & 1u);
+        const float x = alive ? row[j] : 0.f;
+        const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, p.keys));
+        if (A > bestA) {
+            second = bestA;
+            bestA = A;
+            bestj = j;
+        } else if (A > second) {
+            second = A;
+        }
+    }
+    const uint32_t mybits = __float_as_uint(bestA);
+    const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+    const float thr = __fmul_rn(__uint_as_float(topbits), 1.0f - 3.814697265625e-06f);
+    const bool is_top = mybits == topbits;
+    const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
+    const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
+    if (nears == 0u && __popc(tops) == 1) return __shfl_sync(DACO_FULL, bestj, __ffs(tops) - 1);
+    for (int w = lane; w < 32; w += 32) {
+        const int base = w * 32;
+        uint32_t valid = base >= n ? 0u : (n - base >= 32 ? 0xffffffffu : ((1u << (n - base)) - 1u));
+        alive_scratch[w] = (base < 256 ? ~vis[w & 7] : 0u) & valid;
+    }
+    __syncwarp();
+    float pn;
+    return exact_step(row, alive_scratch, n, p.lbw, p.vec, p.double_norm, nullptr, p.seed, off_step, sub_base, p.g_noise, &pn);
+}
+
+// TSP only, 32 < n <= 256, no log-probs, Philox noise
+static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_constant__ ListParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const int n = p.n;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int W = nthreads >> 5, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int a0 = blockIdx.x * W;
+    const int a = a0 + warp;
+    // shared layout: P [n*n f32] | T [n f32] | knn [n][32] u8 | tours [W][n] u16 | vis [W][8] u32 | scratch [W][32] u32
+    float* Psm = reinterpret_cast<float*>(smem);
+    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
+    float* Tsm = reinterpret_cast<float*>(smem + pbytes);
+    const size_t tbytes = (((size_t)n * 4) + 15) & ~(size_t)15;
+    uint8_t* knn_sm = smem + pbytes + tbytes;
+    const size_t kbytes = (size_t)n * 32;
+    uint16_t* tour_all = reinterpret_cast<uint16_t*>(smem + pbytes + tbytes + kbytes);
+    const size_t trbytes = (((size_t)W * n * 2) + 15) & ~(size_t)15;
+    uint32_t* vis_all = reinterpret_cast<uint32_t*>(smem + pbytes + tbytes + kbytes + trbytes);
+    uint32_t* scratch_all = vis_all + W * 8;
+    uint16_t* tour_sm = tour_all + (size_t)warp * n;
+    uint32_t* vis = vis_all + warp * 8;
+
+    {   // candidate lists of this colony (static per instance)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.knn + (size_t)b * n * 32);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(knn_sm);
+        for (int i = tid; i < n * 8; i += nthreads) dst[i] = __ldg(src + i);
+    }
+    stage_product(Psm, p.ph, p.heu, n, b, &bar);   // ends with __syncthreads()
+    // T[u] = max of row u over the columns outside knn[u]
+    for (int u = warp; u < n; u += W) {
+        const uint32_t jj = knn_sm[u * 32 + lane];
+        float m = 0.f;
+        for (int k = 0; k * 32 < n; ++k) {
+            const uint32_t listed = __reduce_or_sync(DACO_FULL, (jj >> 5) == (uint32_t)k ? (1u << (jj & 31)) : 0u);
+            const int j = lane + 32 * k;
+            if (j < n && !((listed >> lane) & 1u)) m = fmaxf(m, Psm[(size_t)u * n + j]);
+        }
+        const uint32_t tb = __reduce_max_sync(DACO_FULL, __float_as_uint(m));
+        if (lane == 0) Tsm[u] = __uint_as_float(tb);
+    }
+    __syncthreads();
+
+    if (a < p.A) {
+        const uint32_t P_addr = pin_u32(smem_u32(Psm));
+        const uint32_t T_addr = pin_u32(smem_u32(Tsm));
+        const uint32_t knn_addr = pin_u32(smem_u32(knn_sm));
+        const uint32_t tour_addr = pin_u32(smem_u32(tour_sm));
+        const uint32_t vis_addr = pin_u32(smem_u32(vis));
+        const uint64_t seed = p.seed;
+        const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
+        const PhiloxRoundKeys& K = p.keys;
+        const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
+        const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
+        const float kInvQmin = 16777216.0f * 1.0001f;    // 1 / q_min with a safety margin for the approximate scores
+
+        int cur;
+        uint64_t off_noise = offset0;
+        if (p.start_node >= 0) {
+            cur = p.start_node;
+        } else if (p.start) {
+            cur = (int)p.start[(size_t)b * p.A + a];
+        } else {
+            cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
+            off_noise += p.start_increment;
+        }
+        if (lane < 8) vis[lane] = (lane == (cur >> 5)) ? (1u << (cur & 31)) : 0u;
+        if (lane == 0) sts_u16(tour_addr, (uint32_t)cur);
+        __syncwarp();
+
+#pragma unroll 1
+        for (int step = 0; step < n - 1; ++step) {
+            const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
+            const uint32_t ctr_lo = (uint32_t)(off_step >> 2), ctr_hi = (uint32_t)(off_step >> 34);
+            const uint32_t j = lds_u8(knn_addr + (uint32_t)cur * 32u + lane);
+            const uint32_t vw = lds_u32(vis_addr + ((j >> 5) << 2));
+            const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
+            float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
+            x = ((vw >> (j & 31)) & 1u) ? 0.f : x;
+            const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
+            const uint32_t mybits = __float_as_uint(A);
+            const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+            const float top = __uint_as_float(topbits);
+            const bool is_top = mybits == topbits;
+            const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
+            const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, kGap) && !is_top);
+            uint32_t jstar;
+            if (nears == 0u && __popc(tops) == 1 && __fmul_rn(T, kInvQmin) < top) {
+                jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
+            } else {
+                jstar = knn_dense_step(p, Psm, cur, vis, scratch_all + warp * 32, ctr_lo, ctr_hi, off_step, sub_base);
+            }
+            if (lane == 0) {
+                vis[jstar >> 5] |= 1u << (jstar & 31);
+                sts_u16(tour_addr + 2 * (step + 1), jstar);
+            }
+            __syncwarp();
+            cur = (int)jstar;
+        }
+    }
+    __syncthreads();
+
+    const int wvalid = min(W, p.A - a0);
+    if (p.paths) {
+        int64_t* out = p.paths + (size_t)b * n * p.A;
+        for (int i = tid; i < n * W; i += nthreads) {
+            const int s = i / W, w = i - s * W;
+            if (w < wvalid) out[(size_t)s * p.A + a0 + w] = (int64_t)tour_all[(size_t)w * n + s];
+        }
+    }
+    if (p.tours) {
+        uint16_t* out = p.tours + ((size_t)b * p.A + a0) * n;
+        for (int i = tid; i < n * wvalid; i += nthreads) out[i] = tour_all[i];
+    }
+}
+
+inline size_t knn_kernel_smem(int n, int W) {
+    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
+    const size_t tbytes = (((size_t)n * 4) + 15) & ~(size_t)15;
+    return pbytes + tbytes + (size_t)n * 32 + ((((size_t)W * n * 2) + 15) & ~(size_t)15) + (size_t)W * (8 + 32) * 4;
 }
 
 inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp) {

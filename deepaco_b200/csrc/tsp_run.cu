@@ -112,7 +112,7 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
     for (int it = 0; it < n_iterations; ++it) {
         if (a->ev_sample_begin) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_begin, st));
         int rc = deepaco_tsp_sample(a->product, nullptr, n, A, B, a->start_node, a->double_norm, a->seed,
-                                    a->offset + (uint64_t)it * inc, a->offsets, nullptr, nullptr, nullptr, nullptr, a->tours, st);
+                                    a->offset + (uint64_t)it * inc, a->offsets, nullptr, nullptr, nullptr, nullptr, a->tours, a->knn, st);
         if (rc) return rc;
         if (a->ev_sample_end) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_end, st));
         rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, a->neighbours, st);

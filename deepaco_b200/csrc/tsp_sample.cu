@@ -208,7 +208,7 @@ extern "C" uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int s
 extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
                                   int start_node, int double_norm, uint64_t seed, uint64_t offset,
                                   const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
-                                  float* log_probs, uint16_t* tours, void* stream) {
+                                  float* log_probs, uint16_t* tours, const uint8_t* knn, void* stream) {
     const DeviceInfo* di = device_info();
     if (!di) return DEEPACO_ENODEV;
     DACO_CHECK_ARG(pheromone != nullptr, "deepaco_tsp_sample: pheromone is NULL");
@@ -261,6 +261,17 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
+        if (knn && !noise && !log_probs && n > 32 && n <= 256 && !getenv("DEEPACO_TSP_NO_KNN")) {
+            // sparse product: one candidate per lane (kNN kernel)
+            int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : 8;
+            if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) Wk = w; }
+            if (knn_kernel_smem(n, Wk) <= cap) {
+                if (total_ants > (long)di->sm_count * 4)
+                    while (Wk < 16 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;
+                q.knn = knn;
+                return launch_kernel(aco_knn_kernel, q, Wk, knn_kernel_smem(n, Wk), st);
+            }
+        }
         const int epl = (n - 1 + 31) / 32;
         const size_t sm = list_smem(W);
 #define DACO_LIST(E)                                                                                        \

@@ -96,6 +96,13 @@ class ACO:
         paths, log_probs = self.gen_path(require_prob=True)
         return self.gen_path_costs(paths), log_probs
 
+    def _candidates(self):
+        """Per-row candidate columns for the sparse-heuristic kernel (None for dense heuristics); cached."""
+        key = (self.heuristic.data_ptr(), self.heuristic._version)
+        if getattr(self, "_knn_key", None) != key:
+            self._knn, self._knn_key = E.sparse_candidates(self.heuristic), key
+        return self._knn
+
     def _weights(self):
         """(pheromone ** alpha, heuristic ** beta); alpha = beta = 1 (every reference driver) costs nothing."""
         ph = self._pheromone if self.alpha == 1 else self._pheromone ** self.alpha
@@ -108,7 +115,8 @@ class ACO:
         ph, heu = self._weights()
         gen, seed, offset = generator_state(self.device)
         paths, logp, _ = E.tsp_sample(ph.detach(), heu.detach(), self.n_ants, start_node=self._START_NODE,
-                                      double_norm=self._DOUBLE_NORM, seed=seed, offset=offset, want_logp=require_prob)
+                                      double_norm=self._DOUBLE_NORM, seed=seed, offset=offset, want_logp=require_prob,
+                                      knn=None if require_prob else self._candidates())
         gen.set_offset(offset + E.tsp_sample_offset_increment(self.problem_size, self.n_ants, self._START_NODE))
         return (paths, logp) if require_prob else paths
 

@@ -83,7 +83,7 @@ class ACO(_TspACO):
             ph, heu = self._weights()
             gen, seed, offset = generator_state(self.device)
             _, _, tours = E.tsp_sample(ph.detach(), heu.detach(), self.n_ants, start_node=0, double_norm=True, seed=seed,
-                                       offset=offset, want_paths=False, want_tours=True)
+                                       offset=offset, want_paths=False, want_tours=True, knn=self._candidates())
             gen.set_offset(offset + E.tsp_sample_offset_increment(self.problem_size, self.n_ants, 0))
             if self.local_search_type == "2opt":
                 E.two_opt_(self.distances, tours, self._max_passes(inference))

@@ -55,11 +55,14 @@ int deepaco_aten_sum_plan(int row_len, int n_rows, int* block_width_out, int* ve
  * deepaco_tsp_sample_offset_increment() per colony.
  * With `noise` != NULL ([B][n-1][A][n] Exp(1) draws) and `start` ([B][A], or start_node >= 0) the
  * result is a pure function of its inputs (cross-device parity mode).
- * Outputs (each may be NULL): paths int64 [B][n][A]; log_probs fp32 [B][n-1][A]; tours u16 [B][A][n]. */
+ * Outputs (each may be NULL): paths int64 [B][n][A]; log_probs fp32 [B][n-1][A]; tours u16 [B][A][n].
+ * knn (optional, uint8 [B][n][32], 32 < n <= 256): per row, 32 distinct columns holding the row's largest
+ * products (e.g. topk of the heuristic).  Purely a performance hint for sparse products -- the result is
+ * identical with or without it (see csrc/list_kernel.cuh). */
 int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
                        int start_node, int double_norm, uint64_t seed, uint64_t offset,
                        const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
-                       float* log_probs, uint16_t* tours, void* stream);
+                       float* log_probs, uint16_t* tours, const uint8_t* knn, void* stream);
 uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int start_node);
 
 /* ---- tour cost  (ACO.gen_path_costs, tsp/aco.py:120-132) --------------------------------------
@@ -108,6 +111,7 @@ typedef struct {
     int64_t* shortest_path;
     float* ph_max;
     float* scale;
+    const uint8_t* knn;    /* optional candidate lists, see deepaco_tsp_sample */
     void* ev_sample_begin; /* optional cudaEvent_t recorded before / after each sampling launch (profiling) */
     void* ev_sample_end;
 } deepaco_tsp_run_args;

