@@ -201,8 +201,9 @@ class TspRunner:
         return self.lowest_cost
 
     def run_host(self, n_iterations, seed, distances_h, heuristic_h, pheromone_h, lowest_h, shortest_h, offset=0,
-                 offsets=None):
-        """deepaco_tsp_run_host: pinned HOST tensors in/out (pheromone_h is updated in place); synchronous."""
+                 offsets=None, copy_back_pheromone=True):
+        """deepaco_tsp_run_host: pinned HOST tensors in/out (pheromone_h is updated in place when
+        copy_back_pheromone); synchronous."""
         for t, nm in ((distances_h, "distances"), (heuristic_h, "heuristic"), (pheromone_h, "pheromone")):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.B * self.n * self.n:
                 raise _lib.DeepAcoError(f"run_host: `{nm}` must be a contiguous fp32 host tensor [B, n, n]")
@@ -210,7 +211,8 @@ class TspRunner:
         a = self._args(seed, offset, offs)
         with torch.cuda.device(self.dev):
             check(lib().deepaco_tsp_run_host(C.byref(a), int(n_iterations), ptr(distances_h), ptr(heuristic_h),
-                                             ptr(pheromone_h), ptr(lowest_h), ptr(shortest_h), stream_ptr(self.dev)),
+                                             ptr(pheromone_h), ptr(lowest_h), ptr(shortest_h), int(copy_back_pheromone),
+                                             stream_ptr(self.dev)),
                   "deepaco_tsp_run_host")
         self.product_valid = n_iterations > 0
         return lowest_h

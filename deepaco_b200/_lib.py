@@ -53,7 +53,7 @@ class TspRunArgs(C.Structure):
 
 
 _SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])
-_SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp])
+_SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp])
 
 _lib = None
 

@@ -32,6 +32,7 @@ struct ListParams {
     PhiloxRoundKeys keys;   // round keys of `seed`, host-computed: read straight from the constant bank
     const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
     const uint8_t* knn;     // [B][n][32] per-row candidate columns for the kNN kernel, or null
+    int rounds;             // kNN kernel: ant groups processed per CTA (amortises the staging of P)
     const int64_t* start;   // [B][A] or null
     int64_t* paths;         // [B][rows][A] or null
     float* logp;            // [B][rows-1][A] or null
@@ -369,8 +370,6 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int W = nthreads >> 5, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
-    const int a0 = blockIdx.x * W;
-    const int a = a0 + warp;
     // shared layout: P [n*n f32] | T [n f32] | knn [n][32] u8 | tours [W][n] u16 | vis [W][8] u32 | scratch [W][32] u32
     float* Psm = reinterpret_cast<float*>(smem);
     const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
@@ -405,76 +404,83 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
     }
     __syncthreads();
 
-    if (a < p.A) {
-        const uint32_t P_addr = pin_u32(smem_u32(Psm));
-        const uint32_t T_addr = pin_u32(smem_u32(Tsm));
-        const uint32_t knn_addr = pin_u32(smem_u32(knn_sm));
-        const uint32_t tour_addr = pin_u32(smem_u32(tour_sm));
-        const uint32_t vis_addr = pin_u32(smem_u32(vis));
-        const uint64_t seed = p.seed;
-        const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
-        const PhiloxRoundKeys& K = p.keys;
-        const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
-        const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
-        const float kInvQmin = 16777216.0f * 1.0001f;    // 1 / q_min with a safety margin for the approximate scores
+    const int rounds = p.rounds > 0 ? p.rounds : 1;
+    const uint32_t P_addr = pin_u32(smem_u32(Psm));
+    const uint32_t T_addr = pin_u32(smem_u32(Tsm));
+    const uint32_t knn_addr = pin_u32(smem_u32(knn_sm));
+    const uint32_t tour_addr = pin_u32(smem_u32(tour_sm));
+    const uint32_t vis_addr = pin_u32(smem_u32(vis));
+    for (int r = 0; r < rounds; ++r) {
+        const int a0 = (blockIdx.x * rounds + r) * W;
+        const int a = a0 + warp;
+        if (a < p.A) {
+            const uint64_t seed = p.seed;
+            const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
+            const PhiloxRoundKeys& K = p.keys;
+            const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
+            const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
+            const float kInvQmin = 16777216.0f * 1.0001f;    // 1 / q_min with a safety margin for the approximate scores
 
-        int cur;
-        uint64_t off_noise = offset0;
-        if (p.start_node >= 0) {
-            cur = p.start_node;
-        } else if (p.start) {
-            cur = (int)p.start[(size_t)b * p.A + a];
-        } else {
-            cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
-            off_noise += p.start_increment;
-        }
-        if (lane < 8) vis[lane] = (lane == (cur >> 5)) ? (1u << (cur & 31)) : 0u;
-        if (lane == 0) sts_u16(tour_addr, (uint32_t)cur);
-        __syncwarp();
+            int cur;
+            uint64_t off_noise = offset0;
+            if (p.start_node >= 0) {
+                cur = p.start_node;
+            } else if (p.start) {
+                cur = (int)p.start[(size_t)b * p.A + a];
+            } else {
+                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
+                off_noise += p.start_increment;
+            }
+            if (lane < 8) vis[lane] = (lane == (cur >> 5)) ? (1u << (cur & 31)) : 0u;
+            if (lane == 0) sts_u16(tour_addr, (uint32_t)cur);
+            __syncwarp();
 
 #pragma unroll 1
-        for (int step = 0; step < n - 1; ++step) {
-            const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
-            const uint32_t ctr_lo = (uint32_t)(off_step >> 2), ctr_hi = (uint32_t)(off_step >> 34);
-            const uint32_t j = lds_u8(knn_addr + (uint32_t)cur * 32u + lane);
-            const uint32_t vw = lds_u32(vis_addr + ((j >> 5) << 2));
-            const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
-            float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
-            x = ((vw >> (j & 31)) & 1u) ? 0.f : x;
-            const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
-            const uint32_t mybits = __float_as_uint(A);
-            const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
-            const float top = __uint_as_float(topbits);
-            const bool is_top = mybits == topbits;
-            const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
-            const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, kGap) && !is_top);
-            uint32_t jstar;
-            if (nears == 0u && __popc(tops) == 1 && __fmul_rn(T, kInvQmin) < top) {
-                jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
-            } else {
-                jstar = knn_dense_step(p, Psm, cur, vis, scratch_all + warp * 32, ctr_lo, ctr_hi, off_step, sub_base);
+            for (int step = 0; step < n - 1; ++step) {
+                const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
+                const uint32_t ctr_lo = (uint32_t)(off_step >> 2), ctr_hi = (uint32_t)(off_step >> 34);
+                const uint32_t j = lds_u8(knn_addr + (uint32_t)cur * 32u + lane);
+                const uint32_t vw = lds_u32(vis_addr + ((j >> 5) << 2));
+                const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
+                float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
+                x = ((vw >> (j & 31)) & 1u) ? 0.f : x;
+                const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
+                const uint32_t mybits = __float_as_uint(A);
+                const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+                const float top = __uint_as_float(topbits);
+                const bool is_top = mybits == topbits;
+                const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
+                const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, kGap) && !is_top);
+                uint32_t jstar;
+                if (nears == 0u && __popc(tops) == 1 && __fmul_rn(T, kInvQmin) < top) {
+                    jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
+                } else {
+                    jstar = knn_dense_step(p, Psm, cur, vis, scratch_all + warp * 32, ctr_lo, ctr_hi, off_step, sub_base);
+                }
+                if (lane == 0) {
+                    vis[jstar >> 5] |= 1u << (jstar & 31);
+                    sts_u16(tour_addr + 2 * (step + 1), jstar);
+                }
+                __syncwarp();
+                cur = (int)jstar;
             }
-            if (lane == 0) {
-                vis[jstar >> 5] |= 1u << (jstar & 31);
-                sts_u16(tour_addr + 2 * (step + 1), jstar);
+            if (p.tours) {   // warp-local, coalesced: this ant's row of the compact layout
+                uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
+                for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
             }
+        }
+        if (p.paths) {       // reference layout needs the CTA's ants side by side: cooperative write
+            __syncthreads();
+            const int wvalid = min(W, p.A - a0);
+            int64_t* out = p.paths + (size_t)b * n * p.A;
+            for (int i = tid; i < n * W; i += nthreads) {
+                const int s2 = i / W, w = i - s2 * W;
+                if (w < wvalid) out[(size_t)s2 * p.A + a0 + w] = (int64_t)tour_all[(size_t)w * n + s2];
+            }
+            __syncthreads();
+        } else {
             __syncwarp();
-            cur = (int)jstar;
         }
-    }
-    __syncthreads();
-
-    const int wvalid = min(W, p.A - a0);
-    if (p.paths) {
-        int64_t* out = p.paths + (size_t)b * n * p.A;
-        for (int i = tid; i < n * W; i += nthreads) {
-            const int s = i / W, w = i - s * W;
-            if (w < wvalid) out[(size_t)s * p.A + a0 + w] = (int64_t)tour_all[(size_t)w * n + s];
-        }
-    }
-    if (p.tours) {
-        uint16_t* out = p.tours + ((size_t)b * p.A + a0) * n;
-        for (int i = tid; i < n * wvalid; i += nthreads) out[i] = tour_all[i];
     }
 }
 

@@ -131,9 +131,10 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
 // matrices of every colony to the device buffers named in `a`, runs, copies the results back, synchronises.
 extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterations, const float* distances_host,
                                     const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
-                                    int64_t* shortest_path_host, void* stream) {
+                                    int64_t* shortest_path_host, int copy_back_pheromone, void* stream) {
     DACO_CHECK_ARG(a && distances_host && heuristic_host && pheromone_host && lowest_cost_host && shortest_path_host,
                    "deepaco_tsp_run_host: NULL argument");
+    const bool ph_back = (copy_back_pheromone != 0);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t mat = (size_t)a->n_colonies * a->n * a->n * sizeof(float);
     DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->distances), distances_host, mat, cudaMemcpyHostToDevice, st));
@@ -143,7 +144,7 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
     b.product_valid = 0;
     const int rc = deepaco_tsp_run(&b, n_iterations, stream);
     if (rc) return rc;
-    DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host, a->pheromone, mat, cudaMemcpyDeviceToHost, st));
+    if (ph_back) DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host, a->pheromone, mat, cudaMemcpyDeviceToHost, st));
     DACO_CHECK_CUDA(cudaMemcpyAsync(lowest_cost_host, a->lowest_cost, sizeof(float) * a->n_colonies, cudaMemcpyDeviceToHost, st));
     DACO_CHECK_CUDA(cudaMemcpyAsync(shortest_path_host, a->shortest_path, sizeof(int64_t) * a->n_colonies * a->n,
                                     cudaMemcpyDeviceToHost, st));

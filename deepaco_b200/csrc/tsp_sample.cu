@@ -269,7 +269,20 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
                 if (total_ants > (long)di->sm_count * 4)
                     while (Wk < 16 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;
                 q.knn = knn;
-                return launch_kernel(aco_knn_kernel, q, Wk, knn_kernel_smem(n, Wk), st);
+                // several ant groups per CTA once the grid is many waves deep: staging P and the per-row bounds
+                // is paid once per CTA
+                int rounds = 1;
+                const long ctas = (long)n_colonies * ((n_ants + Wk - 1) / Wk);
+                const long slots = (long)di->sm_count * (cap / knn_kernel_smem(n, Wk));
+                if (const char* e = getenv("DEEPACO_TSP_ROUNDS")) rounds = atoi(e) > 0 ? atoi(e) : 1;
+                else while (rounds < 8 && ctas / (rounds * 2) >= 6 * slots && (n_ants + Wk * rounds * 2 - 1) / (Wk * rounds * 2) >= 1 && n_ants % (Wk * rounds * 2) == 0) rounds *= 2;
+                q.rounds = rounds;
+                DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_kernel_smem(n, Wk)));
+                DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                dim3 grid((n_ants + Wk * rounds - 1) / (Wk * rounds), n_colonies);
+                aco_knn_kernel<<<grid, Wk * 32, knn_kernel_smem(n, Wk), st>>>(q);
+                DACO_CHECK_LAUNCH();
+                return DEEPACO_OK;
             }
         }
         const int epl = (n - 1 + 31) / 32;

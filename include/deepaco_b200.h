@@ -117,11 +117,12 @@ typedef struct {
 } deepaco_tsp_run_args;
 int deepaco_tsp_run(const deepaco_tsp_run_args* args, int n_iterations, void* stream);
 /* Same with HOST matrices ([B][n][n] fp32 each): H2D of distances, heuristic, pheromone into the device
- * buffers of `args`, n_iterations, D2H of pheromone, lowest_cost [B], shortest_path [B][n]; synchronises
- * `stream` before returning.  Bytes moved: 3 * B*n*n*4 in, B*n*n*4 + B*4 + B*n*8 out. */
+ * buffers of `args`, n_iterations, D2H of lowest_cost [B], shortest_path [B][n] and, if copy_back_pheromone,
+ * the pheromone; synchronises `stream` before returning.
+ * Bytes moved: 3 * B*n*n*4 in; B*4 + B*n*8 (+ B*n*n*4) out. */
 int deepaco_tsp_run_host(const deepaco_tsp_run_args* args, int n_iterations, const float* distances_host,
                          const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
-                         int64_t* shortest_path_host, void* stream);
+                         int64_t* shortest_path_host, int copy_back_pheromone, void* stream);
 
 /* ---- local search (tsp_nls/two_opt.py:6-49, tsp_nls/aco.py:234-258) ---------------------------------
  * In place on compact tours (u16 [B][A][n]); one CTA per tour, bit-exact with the reference's numba code
