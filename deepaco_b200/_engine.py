@@ -87,6 +87,23 @@ def tsp_sample(pheromone, heuristic, n_ants, *, start_node=-1, double_norm=False
     return paths, logp, tours
 
 
+def tsp_sample_shard(pheromone, heuristic, n_ants_local, ant_base, n_ants_total, *, start_node=-1, double_norm=False,
+                     seed=0, offset=0, offsets=None, knn=None):
+    """deepaco_tsp_sample_shard: compact tours (uint16 [B, n_ants_local, n]) of ants
+    [ant_base, ant_base + n_ants_local) of colonies with n_ants_total ants."""
+    pheromone = f32c(require_cuda(pheromone, "pheromone"))
+    B, n = _colonies(pheromone)
+    dev = pheromone.device
+    heuristic = None if heuristic is None else f32c(require_cuda(heuristic, "heuristic"))
+    tours = torch.empty((B, n_ants_local, n), dtype=torch.uint16, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_sample_shard(ptr(pheromone), ptr(heuristic), n, n_ants_local, B, int(start_node),
+                                             int(double_norm), int(seed), int(offset), ptr(_offsets(offsets, B, dev)),
+                                             None, None, ptr(tours), ptr(knn), int(ant_base), int(n_ants_total),
+                                             stream_ptr(dev)), "deepaco_tsp_sample_shard")
+    return tours
+
+
 def tsp_sample_offset_increment(n, n_ants, start_node=-1) -> int:
     return int(lib().deepaco_tsp_sample_offset_increment(n, n_ants, int(start_node)))
 

@@ -22,6 +22,7 @@ _SIGNATURES = {
     "deepaco_torch_draw_geometry": (_i32, [_i64, C.POINTER(C.c_uint32), C.POINTER(_u64)]),
     "deepaco_aten_sum_plan": (_i32, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "deepaco_tsp_sample": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "deepaco_tsp_sample_shard": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "deepaco_tsp_sample_offset_increment": (_u64, [_i32, _i32, _i32]),
     "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),

@@ -33,6 +33,7 @@ struct ListParams {
     const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
     const uint8_t* knn;     // [B][n][32] per-row candidate columns for the kNN kernel, or null
     int rounds;             // kNN kernel: ant groups processed per CTA (amortises the staging of P)
+    int ant_base;           // index of this launch's ant 0 in the colony (ant sharding across GPUs); Philox uses global indices
     const int64_t* start;   // [B][A] or null
     int64_t* paths;         // [B][rows][A] or null
     float* logp;            // [B][rows-1][A] or null
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
         const uint64_t seed = p.seed;
         const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
         const PhiloxRoundKeys& K = p.keys;
-        const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
+        const uint32_t sub_base = (uint32_t)(a + p.ant_base) * (uint32_t)n;
         const float eps = 1.1920928955078125e-07f;
         const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
 
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
                 cur = (int)p.start[(size_t)b * p.A + a];
             } else {
                 // torch.randint(0, n, (A,)): element a <- curand4().x % n  (random_from_to_kernel, 32-bit branch)
-                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
+                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
                 off_noise += p.start_increment;
             }
         }
@@ -417,7 +418,7 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
             const uint64_t seed = p.seed;
             const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
             const PhiloxRoundKeys& K = p.keys;
-            const uint32_t sub_base = (uint32_t)a * (uint32_t)n;
+            const uint32_t sub_base = (uint32_t)(a + p.ant_base) * (uint32_t)n;
             const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
             const float kInvQmin = 16777216.0f * 1.0001f;    // 1 / q_min with a safety margin for the approximate scores
 
@@ -428,7 +429,7 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
             } else if (p.start) {
                 cur = (int)p.start[(size_t)b * p.A + a];
             } else {
-                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
+                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
                 off_noise += p.start_increment;
             }
             if (lane < 8) vis[lane] = (lane == (cur >> 5)) ? (1u << (cur & 31)) : 0u;

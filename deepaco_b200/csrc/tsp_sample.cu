@@ -43,6 +43,7 @@ struct TspSampleParams {
     int vec;              // ATen vectorised summation order (n >= 128)
     DrawGeom g_noise, g_start;
     uint32_t start_increment, step_increment;
+    int ant_base;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
         } else if (p.start) {
             cur = (int)p.start[(size_t)b * p.A + a];
         } else {
-            cur = (int)(torch_philox_word(seed, offset0, (uint64_t)a, p.g_start) % (uint32_t)n);
+            cur = (int)(torch_philox_word(seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
             off_noise += p.start_increment;
         }
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
                 if (lane_on && j < (uint32_t)n) {
                     const float pn = __fdiv_rn(x[k], S);
                     const float q = nz ? nz[j]
-                                       : exp1_from_word(torch_philox_word(seed, off_step, (uint64_t)a * n + j, p.g_noise));
+                                       : exp1_from_word(torch_philox_word(seed, off_step, (uint64_t)(a + p.ant_base) * n + j, p.g_noise));
                     const float v = __fdiv_rn(pn, q);
                     if (bestj == 0xffffffffu || v > best) {
                         best = v;
@@ -205,16 +206,18 @@ extern "C" uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int s
     return inc;
 }
 
-extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
-                                  int start_node, int double_norm, uint64_t seed, uint64_t offset,
-                                  const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
-                                  float* log_probs, uint16_t* tours, const uint8_t* knn, void* stream) {
+static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                           int start_node, int double_norm, uint64_t seed, uint64_t offset,
+                           const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
+                           float* log_probs, uint16_t* tours, const uint8_t* knn, int ant_base, int n_ants_total, void* stream) {
     const DeviceInfo* di = device_info();
     if (!di) return DEEPACO_ENODEV;
     DACO_CHECK_ARG(pheromone != nullptr, "deepaco_tsp_sample: pheromone is NULL");
     DACO_CHECK_ARG(n >= 2 && n <= DEEPACO_MAX_NODES, "deepaco_tsp_sample: n=%d outside [2, %d]", n, DEEPACO_MAX_NODES);
     DACO_CHECK_ARG(n_ants >= 1 && n_colonies >= 1 && n_colonies <= 65535, "deepaco_tsp_sample: bad n_ants/n_colonies");
     DACO_CHECK_ARG(start_node < n, "deepaco_tsp_sample: start_node %d >= n", start_node);
+    DACO_CHECK_ARG(ant_base >= 0 && n_ants_total >= ant_base + n_ants, "deepaco_tsp_sample: ant shard [%d, %d) outside the colony's %d ants",
+                   ant_base, ant_base + n_ants, n_ants_total);
     cudaStream_t st = (cudaStream_t)stream;
 
     TspSampleParams p{};
@@ -225,15 +228,16 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
     p.noise = noise; p.start = start;
     p.paths = paths; p.logp = log_probs; p.tours = tours;
 
-    const SumPlan sp = aten_sum_plan(n, n_ants);
+    const SumPlan sp = aten_sum_plan(n, n_ants_total);   // the reference sums [n_ants_total, n] tensors
     const bool vec = sp.vectorized && (n % 4 == 0);
     int bw = sp.block_width > 32 ? 32 : sp.block_width;
     int lbw = 0;
     while ((1 << lbw) < bw) ++lbw;
     p.lbw = lbw;
     p.vec = sp.vectorized ? 1 : 0;   // runtime ATen sums handle n % 4 != 0 through the row shift
-    const DrawPlan dn = torch_draw_plan((int64_t)n_ants * n, *di);
-    const DrawPlan ds = torch_draw_plan(n_ants, *di);
+    const DrawPlan dn = torch_draw_plan((int64_t)n_ants_total * n, *di);
+    const DrawPlan ds = torch_draw_plan(n_ants_total, *di);
+    p.ant_base = ant_base;
     p.g_noise = {dn.threads, dn.single};
     p.g_start = {ds.threads, ds.single};
     p.start_increment = (uint32_t)ds.increment;
@@ -250,7 +254,7 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
     auto list_smem = [&](int w) { return list_kernel_smem(n, n, w, false); };
     const size_t cap = (size_t)di->max_smem_optin - 1024;
     const bool force_dense = getenv("DEEPACO_TSP_DENSE") != nullptr;
-    if (!force_dense && dn.single && (uint64_t)n_ants * n < (1ull << 32) && n <= 256 && list_smem(W) <= cap) {
+    if (!force_dense && dn.single && (uint64_t)n_ants_total * n < (1ull << 32) && n <= 256 && list_smem(W) <= cap) {
         // keep >= 32 resident warps per SM when shared memory allows only few CTAs
         if (total_ants > (long)di->sm_count * 4)
             while (W < 16 && (cap / list_smem(W)) * W < 32 && list_smem(W * 2) <= cap) W *= 2;
@@ -258,6 +262,7 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
         q.ph = pheromone; q.heu = heuristic; q.n = n; q.A = n_ants; q.B = n_colonies; q.rows = n;
         q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.offsets = offsets;
         q.keys.init(seed);
+        q.ant_base = ant_base;
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
@@ -341,4 +346,23 @@ extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic
         DACO_LAUNCH(32, false, false);
     }
 #undef DACO_LAUNCH
+}
+
+extern "C" int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                                  int start_node, int double_norm, uint64_t seed, uint64_t offset,
+                                  const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
+                                  float* log_probs, uint16_t* tours, const uint8_t* knn, void* stream) {
+    return tsp_sample_impl(pheromone, heuristic, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, noise,
+                           start, paths, log_probs, tours, knn, 0, n_ants, stream);
+}
+
+// Ant-sharded variant: this launch constructs ants [ant_base, ant_base + n_ants) of colonies that have n_ants_total
+// ants.  Noise words and summation plans are those of the full colony, so an ant's tour does not depend on how the
+// colony is split across GPUs.  Output buffers are indexed by the LOCAL ant number.
+extern "C" int deepaco_tsp_sample_shard(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                                        int start_node, int double_norm, uint64_t seed, uint64_t offset,
+                                        const uint64_t* offsets, int64_t* paths, float* log_probs, uint16_t* tours,
+                                        const uint8_t* knn, int ant_base, int n_ants_total, void* stream) {
+    return tsp_sample_impl(pheromone, heuristic, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr,
+                           nullptr, paths, log_probs, tours, knn, ant_base, n_ants_total, stream);
 }

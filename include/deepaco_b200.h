@@ -64,6 +64,14 @@ int deepaco_tsp_sample(const float* pheromone, const float* heuristic, int n, in
                        const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
                        float* log_probs, uint16_t* tours, const uint8_t* knn, void* stream);
 uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int start_node);
+/* Ant-sharded construction (multi-GPU): ants [ant_base, ant_base + n_ants) of colonies with n_ants_total ants.
+ * Philox subsequences and ATen summation plans are those of the full colony: a given ant's tour is the same
+ * whichever GPU builds it.  Outputs are indexed by the local ant number.  The offset increment to advance the
+ * generator by is that of the full colony: deepaco_tsp_sample_offset_increment(n, n_ants_total, start_node). */
+int deepaco_tsp_sample_shard(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                             int start_node, int double_norm, uint64_t seed, uint64_t offset, const uint64_t* offsets,
+                             int64_t* paths, float* log_probs, uint16_t* tours, const uint8_t* knn, int ant_base,
+                             int n_ants_total, void* stream);
 
 /* ---- tour cost  (ACO.gen_path_costs, tsp/aco.py:120-132) --------------------------------------
  * costs[b][a] = sum_k dist[u_k][u_{k-1}] in ATen's summation order.  Input tours either as
