@@ -190,14 +190,17 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(local_rank)
+    from deepaco_b200._lib import lib as _daco_lib
     barrier()
     sampler.start()
+    launches0 = _daco_lib().deepaco_kernel_launches()
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
         runner.run(1, seed, it * inc, offsets, sample_events=evs[k])
         ev[k][1].record()
         it += 1
+    launches = _daco_lib().deepaco_kernel_launches() - launches0
     barrier()
     clocks = sampler.finish()
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -268,7 +271,7 @@ def main():
                      "note": "matrices are L2/SMEM resident: a throughput-normalised figure, not DRAM utilisation"},
         "e2e": {"value": e2e_value, "unit": "ant-tours/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "deepaco_tsp_run_host (C ABI, pinned host buffers)", "ms_per_step": float(e2e_ms) / K},
-        "gpu_launches": 4 * K, "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_cpu_baseline:
         cb, _, _ = cpu_reference_throughput(100, 2)

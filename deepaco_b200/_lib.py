@@ -19,6 +19,7 @@ _SIGNATURES = {
     # name: (restype, [argtypes])
     "deepaco_last_error": (C.c_char_p, []),
     "deepaco_version": (_i32, []),
+    "deepaco_kernel_launches": (C.c_longlong, []),
     "deepaco_torch_draw_geometry": (_i32, [_i64, C.POINTER(C.c_uint32), C.POINTER(_u64)]),
     "deepaco_aten_sum_plan": (_i32, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "deepaco_tsp_sample": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

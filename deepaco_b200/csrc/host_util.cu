@@ -4,11 +4,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 namespace deepaco {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -91,6 +94,8 @@ extern "C" {
 const char* deepaco_last_error(void) { return deepaco::g_err; }
 
 int deepaco_version(void) { return 100; }
+
+long long deepaco_kernel_launches(void) { return deepaco::g_launches.load(); }
 
 int deepaco_torch_draw_geometry(int64_t numel, uint32_t* threads_out, uint64_t* offset_increment_out) {
     const deepaco::DeviceInfo* di = deepaco::device_info();

@@ -35,6 +35,9 @@ struct DrawPlan {
 };
 DrawPlan torch_draw_plan(int64_t numel, const DeviceInfo& di);
 
+void count_launch();   // every kernel launch of the library passes through DACO_CHECK_LAUNCH
+
+// (count_launch is declared before the macros that use it)
 #define DACO_CHECK_ARG(cond, ...)            \
     do {                                     \
         if (!(cond)) {                       \
@@ -52,6 +55,10 @@ DrawPlan torch_draw_plan(int64_t numel, const DeviceInfo& di);
         }                                                                                            \
     } while (0)
 
-#define DACO_CHECK_LAUNCH() DACO_CHECK_CUDA(cudaGetLastError())
+#define DACO_CHECK_LAUNCH()                   \
+    do {                                      \
+        deepaco::count_launch();              \
+        DACO_CHECK_CUDA(cudaGetLastError());  \
+    } while (0)
 
 }  // namespace deepaco

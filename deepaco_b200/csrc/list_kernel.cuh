@@ -33,6 +33,9 @@ struct ListParams {
     const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
     const uint8_t* knn;     // [B][n][32] per-row candidate columns for the kNN kernel, or null
     int rounds;             // kNN kernel: ant groups processed per CTA (amortises the staging of P)
+    const float* dist;      // optional fused epilogue (kNN kernel): distances [B][n][n] ->
+    float* costs;           //   costs [B][A] in ATen summation order and
+    uint32_t* nbr;          //   neighbour table [B][n][A] (pred << 16 | succ), as deepaco_tsp_cost would produce
     int ant_base;           // index of this launch's ant 0 in the colony (ant sharding across GPUs); Philox uses global indices
     const int64_t* start;   // [B][A] or null
     int64_t* paths;         // [B][rows][A] or null
@@ -468,6 +471,19 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
             if (p.tours) {   // warp-local, coalesced: this ant's row of the compact layout
                 uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
                 for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
+            }
+            if (p.costs) {   // fused ACO.gen_path_costs + neighbour table (same arithmetic as tsp_cost_kernel)
+                const float* D = p.dist + (size_t)b * n * n;
+                auto edge = [&](int k) -> float {
+                    return __ldg(D + (size_t)tour_sm[k] * n + tour_sm[k == 0 ? n - 1 : k - 1]);
+                };
+                const float c = aten_row_sum_fn(edge, n, p.lbw, p.vec != 0, lane, p.vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
+                if (lane == 0) p.costs[(size_t)b * p.A + a] = c;
+                uint32_t* N = p.nbr + (size_t)b * n * p.A;
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t u = tour_sm[k], pr = tour_sm[k == 0 ? n - 1 : k - 1], su = tour_sm[k == n - 1 ? 0 : k + 1];
+                    N[(size_t)u * p.A + a] = (pr << 16) | su;
+                }
             }
         }
         if (p.paths) {       // reference layout needs the CTA's ants side by side: cooperative write

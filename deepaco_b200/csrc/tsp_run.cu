@@ -16,6 +16,9 @@ int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float*
                       const float* heuristic, float* product, cudaStream_t st);
 int tsp_cost_launch(const float* distances, const uint16_t* tours, int n, int n_ants, int n_colonies, float* costs,
                     uint32_t* neighbours, cudaStream_t st);
+int tsp_sample_fused(const float* product, int n, int n_ants, int n_colonies, int start_node, int double_norm, uint64_t seed,
+                     uint64_t offset, const uint64_t* offsets, uint16_t* tours, const uint8_t* knn, const float* dist, float* costs,
+                     uint32_t* nbr, int* fused, cudaStream_t st);
 
 __global__ void hadamard2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -111,12 +114,15 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
     }
     for (int it = 0; it < n_iterations; ++it) {
         if (a->ev_sample_begin) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_begin, st));
-        int rc = deepaco_tsp_sample(a->product, nullptr, n, A, B, a->start_node, a->double_norm, a->seed,
-                                    a->offset + (uint64_t)it * inc, a->offsets, nullptr, nullptr, nullptr, nullptr, a->tours, a->knn, st);
+        int fused = 0;
+        int rc = tsp_sample_fused(a->product, n, A, B, a->start_node, a->double_norm, a->seed, a->offset + (uint64_t)it * inc,
+                                  a->offsets, a->tours, a->knn, a->distances, a->costs, a->neighbours, &fused, st);
         if (rc) return rc;
         if (a->ev_sample_end) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_end, st));
-        rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, a->neighbours, st);
-        if (rc) return rc;
+        if (!fused) {
+            rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, a->neighbours, st);
+            if (rc) return rc;
+        }
         tsp_best_kernel<<<B, 256, 0, st>>>(a->costs, a->tours, a->pheromone, n, A, a->min_max, a->lowest_cost, a->shortest_path,
                                            a->ph_max, a->min_max ? a->scale : nullptr);
         DACO_CHECK_LAUNCH();

@@ -209,8 +209,11 @@ extern "C" uint64_t deepaco_tsp_sample_offset_increment(int n, int n_ants, int s
 static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
                            int start_node, int double_norm, uint64_t seed, uint64_t offset,
                            const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
-                           float* log_probs, uint16_t* tours, const uint8_t* knn, int ant_base, int n_ants_total, void* stream) {
+                           float* log_probs, uint16_t* tours, const uint8_t* knn, int ant_base, int n_ants_total, void* stream,
+                           const float* fuse_dist = nullptr, float* fuse_costs = nullptr, uint32_t* fuse_nbr = nullptr,
+                           int* fused_out = nullptr) {
     const DeviceInfo* di = device_info();
+    if (fused_out) *fused_out = 0;
     if (!di) return DEEPACO_ENODEV;
     DACO_CHECK_ARG(pheromone != nullptr, "deepaco_tsp_sample: pheromone is NULL");
     DACO_CHECK_ARG(n >= 2 && n <= DEEPACO_MAX_NODES, "deepaco_tsp_sample: n=%d outside [2, %d]", n, DEEPACO_MAX_NODES);
@@ -274,6 +277,10 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
                 if (total_ants > (long)di->sm_count * 4)
                     while (Wk < 16 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;
                 q.knn = knn;
+                if (fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants) {
+                    q.dist = fuse_dist; q.costs = fuse_costs; q.nbr = fuse_nbr;
+                    if (fused_out) *fused_out = 1;
+                }
                 // several ant groups per CTA once the grid is many waves deep: staging P and the per-row bounds
                 // is paid once per CTA
                 int rounds = 1;
@@ -366,3 +373,13 @@ extern "C" int deepaco_tsp_sample_shard(const float* pheromone, const float* heu
     return tsp_sample_impl(pheromone, heuristic, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr,
                            nullptr, paths, log_probs, tours, knn, ant_base, n_ants_total, stream);
 }
+
+namespace deepaco {
+// internal: sampling with the cost / neighbour-table epilogue fused when the kNN kernel is selected (*fused = 1)
+int tsp_sample_fused(const float* product, int n, int n_ants, int n_colonies, int start_node, int double_norm, uint64_t seed,
+                     uint64_t offset, const uint64_t* offsets, uint16_t* tours, const uint8_t* knn, const float* dist, float* costs,
+                     uint32_t* nbr, int* fused, cudaStream_t st) {
+    return tsp_sample_impl(product, nullptr, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr, nullptr,
+                           nullptr, nullptr, tours, knn, 0, n_ants, st, dist, costs, nbr, fused);
+}
+}  // namespace deepaco

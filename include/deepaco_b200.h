@@ -33,6 +33,8 @@ extern "C" {
 
 const char* deepaco_last_error(void);
 int deepaco_version(void);
+/* number of CUDA kernels this library has launched so far in this process (monotonic counter) */
+long long deepaco_kernel_launches(void);
 
 /* Geometry of torch's Philox draw for a tensor of `numel` elements on the current device
  * (ATen/native/cuda/DistributionTemplates.h:50-62): returns grid*256 threads and the generator
