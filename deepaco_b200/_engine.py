@@ -370,6 +370,90 @@ def cvrp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_
     return pheromone
 
 
+class CvrpRunner:
+    """Device-resident state of `ACO.run` for CVRP colonies (deepaco_cvrp_run); see TspRunner."""
+
+    def __init__(self, distances, demand, heuristic, pheromone, n_ants, *, capacity=50, decay=0.9, elitist=False,
+                 min_max=False, ph_min=0.0):
+        self.distances = f32c(require_cuda(distances, "distances"))
+        self.B, self.N = _colonies(self.distances)
+        dev = self.dev = self.distances.device
+        shp = (self.B, self.N, self.N)
+        self.distances = self.distances.reshape(shp)
+        self.heuristic = f32c(require_cuda(heuristic, "heuristic").detach()).reshape(shp)
+        self.pheromone = pheromone.detach().to(torch.float32).clone(memory_format=torch.contiguous_format).reshape(shp)
+        self.demand = f32c(require_cuda(demand, "demand")).reshape(self.B, self.N)
+        self.n_ants, self.capacity = int(n_ants), float(capacity)
+        R = 2 * self.N
+        self.product = torch.empty(shp, dtype=torch.float32, device=dev)
+        self.product_valid = False
+        self.tours = torch.empty((self.B, self.n_ants, R), dtype=torch.uint16, device=dev)
+        self.costs = torch.empty((self.B, self.n_ants), dtype=torch.float32, device=dev)
+        self.neighbours = torch.empty((self.B, self.N, self.n_ants), dtype=torch.int32, device=dev)
+        self.lens = torch.empty((self.B, self.n_ants), dtype=torch.int32, device=dev)
+        self.tmax = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        self.lowest_cost = torch.full((self.B,), float("inf"), dtype=torch.float32, device=dev)
+        self.shortest_path = torch.zeros((self.B, R), dtype=torch.int64, device=dev)
+        self.shortest_rows = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        self.ph_max = torch.zeros((self.B,), dtype=torch.float32, device=dev)
+        self.scale = torch.ones((self.B,), dtype=torch.float32, device=dev)
+        self.offsets = torch.zeros((self.B,), dtype=torch.int64, device=dev)
+        self.decay, self.elitist, self.min_max, self.ph_min = float(decay), bool(elitist), bool(min_max), float(ph_min)
+
+    def run(self, n_iterations, seed, offsets):
+        """`offsets`: per-colony Philox offsets at entry; self.offsets holds the advanced values afterwards."""
+        self.offsets.copy_(torch.as_tensor(offsets, dtype=torch.int64).reshape(-1).to(self.dev))
+        a = _lib.CvrpRunArgs(self.N, self.n_ants, self.B, self.capacity, self.decay, int(self.elitist), int(self.min_max),
+                             self.ph_min, int(seed), ptr(self.offsets), ptr(self.pheromone), ptr(self.heuristic),
+                             ptr(self.distances), ptr(self.demand), ptr(self.product), int(self.product_valid),
+                             ptr(self.tours), ptr(self.costs), ptr(self.neighbours), ptr(self.lens), ptr(self.tmax),
+                             ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.shortest_rows), ptr(self.ph_max),
+                             ptr(self.scale))
+        with torch.cuda.device(self.dev):
+            check(lib().deepaco_cvrp_run(C.byref(a), int(n_iterations), stream_ptr(self.dev)), "deepaco_cvrp_run")
+        if n_iterations > 0:
+            self.product_valid = True
+        return self.lowest_cost
+
+
+# ---- autograd -----------------------------------------------------------------------------------
+def logp_backward(pheromone_pow, heuristic_pow, paths, grad_logp, *, demand=None, capacity=0.0, want_pheromone_grad=False):
+    """deepaco_logp_backward -> (grad wrt heuristic_pow, grad wrt pheromone_pow | None), single colony."""
+    ph = f32c(require_cuda(pheromone_pow, "pheromone").detach())
+    heu = f32c(require_cuda(heuristic_pow, "heuristic").detach())
+    n = ph.shape[-1]
+    paths = paths.to(torch.int64).contiguous()
+    g = f32c(grad_logp)
+    dem = None if demand is None else f32c(demand)
+    g_heu = torch.zeros_like(heu)
+    g_ph = torch.zeros_like(ph) if want_pheromone_grad else None
+    with torch.cuda.device(ph.device):
+        check(lib().deepaco_logp_backward(ptr(ph), ptr(heu), ptr(paths), ptr(g), n, paths.shape[1], paths.shape[0], ptr(dem),
+                                          float(capacity), ptr(g_heu), ptr(g_ph), stream_ptr(ph.device)), "deepaco_logp_backward")
+    return g_heu, g_ph
+
+
+class SampleLogProbs(torch.autograd.Function):
+    """paths, log_probs = construct(pheromone_pow, heuristic_pow); differentiable in both matrices.
+    `construct` is a closure running the forward kernels; `replay` carries the mask rule for the backward."""
+
+    @staticmethod
+    def forward(ctx, pheromone_pow, heuristic_pow, construct, demand, capacity):
+        paths, logp = construct(pheromone_pow.detach(), heuristic_pow.detach())
+        ctx.save_for_backward(pheromone_pow, heuristic_pow, paths)
+        ctx.demand, ctx.capacity = demand, capacity
+        ctx.mark_non_differentiable(paths)
+        return paths, logp
+
+    @staticmethod
+    def backward(ctx, _gpaths, glogp):
+        ph, heu, paths = ctx.saved_tensors
+        need_ph = ctx.needs_input_grad[0]
+        g_heu, g_ph = logp_backward(ph, heu, paths, glogp, demand=ctx.demand, capacity=ctx.capacity,
+                                    want_pheromone_grad=need_ph)
+        return (g_ph if need_ph else None), (g_heu if ctx.needs_input_grad[1] else None), None, None, None
+
+
 # ---- probes ------------------------------------------------------------------------------------
 def debug_exponential(seed, offset, numel, device):
     out = torch.empty((numel,), dtype=torch.float32, device=device)

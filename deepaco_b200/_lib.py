@@ -37,6 +37,7 @@ _SIGNATURES = {
     "deepaco_cvrp_step_offset_increment": (_u64, [_i32, _i32]),
     "deepaco_cvrp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "deepaco_cvrp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
+    "deepaco_logp_backward": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp]),
     "deepaco_debug_exponential": (_i32, [_u64, _u64, _i64, _vp, _vp]),
     "deepaco_debug_randint": (_i32, [_u64, _u64, _i64, _i64, _vp, _vp]),
     "deepaco_debug_row_sum": (_i32, [_vp, _i32, _i32, _vp, _vp]),
@@ -54,6 +55,16 @@ class TspRunArgs(C.Structure):
                 ("ph_max", _vp), ("scale", _vp), ("knn", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
 
 
+class CvrpRunArgs(C.Structure):
+    """deepaco_cvrp_run_args (include/deepaco_b200.h)."""
+    _fields_ = [("n_nodes", _i32), ("n_ants", _i32), ("n_colonies", _i32), ("capacity", _f32), ("decay", _f32),
+                ("elitist", _i32), ("min_max", _i32), ("ph_min", _f32), ("seed", _u64), ("offsets", _vp),
+                ("pheromone", _vp), ("heuristic", _vp), ("distances", _vp), ("demand", _vp), ("product", _vp),
+                ("product_valid", _i32), ("tours", _vp), ("costs", _vp), ("neighbours", _vp), ("lens", _vp), ("tmax", _vp),
+                ("lowest_cost", _vp), ("shortest_path", _vp), ("shortest_rows", _vp), ("ph_max", _vp), ("scale", _vp)]
+
+
+_SIGNATURES["deepaco_cvrp_run"] = (_i32, [C.POINTER(CvrpRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp])
 

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) cvrp_cost_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) cvrp_update_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
                                                           const float* __restrict__ costs, int N, int A, float decay,
                                                           int elitist, int min_max, float ph_min,
-                                                          const float* __restrict__ ph_max) {
+                                                          const float* __restrict__ ph_max, const float* __restrict__ scale,
+                                                          const float* __restrict__ heu, float* __restrict__ prod) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* nb_s = reinterpret_cast<uint32_t*>(smem);
     float* w_s = reinterpret_cast<float*>(smem) + A;
@@ -106,7 +107,9 @@ __global__ void __launch_bounds__(256) cvrp_update_kernel(float* __restrict__ ph
     const float hi = min_max ? ph_max[b] : 0.f;
     const int a_lo = elitist ? best_ant : 0, a_hi = elitist ? best_ant + 1 : A;
     for (int v = threadIdx.x; v < N; v += blockDim.x) {
-        float val = __fmul_rn(row[v], decay);
+        float val = row[v];
+        if (scale) val = __fmul_rn(val, scale[b]);   // MMAS rescale on the first improvement (cvrp/aco.py:90-92)
+        val = __fmul_rn(val, decay);
         if (u != 0) {
             for (int a = a_lo; a < a_hi; ++a)
                 if ((int)(nb_s[a] & 0xffffu) == v) val = __fadd_rn(val, w_s[a]);          // (u -> succ_a(u))
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(256) cvrp_update_kernel(float* __restrict__ ph
         }
         if (val < 1e-10f) val = 1e-10f;   // cvrp/aco.py:130
         row[v] = val;
+        if (prod) prod[((size_t)b * N + u) * N + v] = __fmul_rn(val, heu[((size_t)b * N + u) * N + v]);
     }
 }
 
@@ -232,7 +236,61 @@ extern "C" int deepaco_cvrp_update(float* pheromone, const uint32_t* neighbours,
     const int threads = n_nodes <= 64 ? 64 : (n_nodes <= 128 ? 128 : 256);
     dim3 grid(n_nodes, n_colonies);
     cvrp_update_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(pheromone, neighbours, costs, n_nodes, n_ants, decay,
-                                                                      elitist, min_max, ph_min, ph_max);
+                                                                      elitist, min_max, ph_min, ph_max, nullptr, nullptr, nullptr);
     DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+// ---- ACO.run for CVRP colonies (cvrp/aco.py:72-104, adaptive = False) without host round trips ---------------
+namespace deepaco {
+int best_launch(const float* costs, const uint16_t* tours, const float* ph, int n, int tour_len, int A, int B, int min_max,
+                float* lowest, int64_t* shortest, float* ph_max, float* scale, const int32_t* tmax, int32_t* shortest_rows,
+                cudaStream_t st);
+
+__global__ void hadamard3_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        o[i] = __fmul_rn(a[i], b[i]);
+}
+// the reference draws one [A, N] exponential_ per construction step until the slowest ant is done: the next
+// iteration's Philox offset is data dependent, so it is advanced on the device
+__global__ void advance_offsets_kernel(uint64_t* offsets, const int32_t* tmax, uint64_t step_increment, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) offsets[b] += (uint64_t)tmax[b] * step_increment;
+}
+}  // namespace deepaco
+
+extern "C" int deepaco_cvrp_run(const deepaco_cvrp_run_args* a, int n_iterations, void* stream) {
+    DACO_CHECK_ARG(a && n_iterations >= 0, "deepaco_cvrp_run: bad arguments");
+    DACO_CHECK_ARG(a->pheromone && a->heuristic && a->distances && a->demand && a->product && a->tours && a->costs &&
+                       a->neighbours && a->lens && a->tmax && a->offsets && a->lowest_cost && a->shortest_path,
+                   "deepaco_cvrp_run: NULL buffer");
+    DACO_CHECK_ARG(!a->min_max || (a->ph_max && a->scale), "deepaco_cvrp_run: min_max needs ph_max and scale buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = a->n_nodes, A = a->n_ants, B = a->n_colonies, R = 2 * N;
+    const uint64_t inc = deepaco_cvrp_step_offset_increment(N, A);
+    const size_t cnt = (size_t)B * N * N;
+    if (n_iterations > 0 && !a->product_valid) {
+        hadamard3_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(a->pheromone, a->heuristic, a->product, cnt);
+        DACO_CHECK_LAUNCH();
+    }
+    for (int it = 0; it < n_iterations; ++it) {
+        int rc = deepaco_cvrp_sample(a->product, nullptr, a->demand, a->capacity, N, A, B, a->seed, 0, a->offsets, nullptr, R,
+                                     nullptr, nullptr, a->tours, a->lens, a->tmax, st);
+        if (rc) return rc;
+        rc = deepaco_cvrp_cost(a->distances, nullptr, a->tours, N, A, B, R, a->tmax, 0, a->costs, a->neighbours, st);
+        if (rc) return rc;
+        rc = best_launch(a->costs, a->tours, a->pheromone, N, R, A, B, a->min_max, a->lowest_cost, a->shortest_path, a->ph_max,
+                         a->min_max ? a->scale : nullptr, a->tmax, a->shortest_rows, st);
+        if (rc) return rc;
+        const size_t smem = (size_t)A * 8;
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(cvrp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int threads = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+        cvrp_update_kernel<<<dim3(N, B), threads, smem, st>>>(a->pheromone, a->neighbours, a->costs, N, A, a->decay, a->elitist,
+                                                              a->min_max, a->ph_min, a->ph_max, a->min_max ? a->scale : nullptr,
+                                                              a->heuristic, a->product);
+        DACO_CHECK_LAUNCH();
+        advance_offsets_kernel<<<(B + 127) / 128, 128, 0, st>>>(a->offsets, a->tmax, inc, B);
+        DACO_CHECK_LAUNCH();
+    }
     return DEEPACO_OK;
 }

@@ -32,7 +32,6 @@ struct ListParams {
     PhiloxRoundKeys keys;   // round keys of `seed`, host-computed: read straight from the constant bank
     const float* noise;     // [B][rows-1][A][n] external Exp(1) draws, or null
     const uint8_t* knn;     // [B][n][32] per-row candidate columns for the kNN kernel, or null
-    int rounds;             // kNN kernel: ant groups processed per CTA (amortises the staging of P)
     const float* dist;      // optional fused epilogue (kNN kernel): distances [B][n][n] ->
     float* costs;           //   costs [B][A] in ATen summation order and
     uint32_t* nbr;          //   neighbour table [B][n][A] (pred << 16 | succ), as deepaco_tsp_cost would produce
@@ -331,14 +330,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 
 // dense evaluation of one step over all unvisited nodes (vis = visited bitmap words in shared memory)
-static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, const float* Psm, int cur, uint32_t* vis, uint32_t* alive_scratch,
+static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, const float* Psm, int cur, const uint8_t* vis, uint32_t* alive_scratch,
                                                 uint32_t ctr_lo, uint32_t ctr_hi, uint64_t off_step, uint32_t sub_base) {
     const int lane = threadIdx.x & 31, n = p.n;
     const float* row = Psm + (size_t)cur * n;
     float bestA = 0.f, second = 0.f;
     uint32_t bestj = 0xffffffffu;
     for (int j = lane; j < n; j += 32) {
-        const bool alive = !((vis[j >> 5] >> (j & 31)) & 1u);
+        const bool alive = vis[j] == 0;
         const float x = alive ? row[j] : 0.f;
         const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, p.keys));
         if (A > bestA) {
@@ -356,37 +355,40 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
     const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
     const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
     if (nears == 0u && __popc(tops) == 1) return __shfl_sync(DACO_FULL, bestj, __ffs(tops) - 1);
-    for (int w = lane; w < 32; w += 32) {
-        const int base = w * 32;
-        uint32_t valid = base >= n ? 0u : (n - base >= 32 ? 0xffffffffu : ((1u << (n - base)) - 1u));
-        alive_scratch[w] = (base < 256 ? ~vis[w & 7] : 0u) & valid;
+    for (int w = 0; w * 32 < n; ++w) {       // alive bitmap for exact_step from the visited byte map
+        const int j = w * 32 + lane;
+        const uint32_t bits = __ballot_sync(DACO_FULL, j < n && vis[j] == 0);
+        if (lane == 0) alive_scratch[w] = bits;
     }
+    for (int w = (n + 31) / 32 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
     __syncwarp();
     float pn;
     return exact_step(row, alive_scratch, n, p.lbw, p.vec, p.double_norm, nullptr, p.seed, off_step, sub_base, p.g_noise, &pn);
 }
 
-// TSP only, 32 < n <= 256, no log-probs, Philox noise
-static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_constant__ ListParams p) {
+// TSP only, 32 < n <= 256, no log-probs, Philox noise, compact tours out.
+// Shared layout (fixed offsets keep the address arithmetic of the step loop in two registers):
+//   per warp w (kKnnWarpBytes each, kKnnMaxWarps slots): visited bytes [256] | scratch u32 [32] | tour u16 [256]
+//   then: knn u8 [n][32] | bound f32 [n] (16-byte padded) | P f32 [n][n]
+constexpr int kKnnWarpBytes = 256 + 128 + 512;
+
+template <bool FUSE_COST, int MAXW>
+static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_kernel(const __grid_constant__ ListParams p) {
+    constexpr int kKnnFixed = kKnnWarpBytes * MAXW;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const int n = p.n;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int W = nthreads >> 5, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
-    // shared layout: P [n*n f32] | T [n f32] | knn [n][32] u8 | tours [W][n] u16 | vis [W][8] u32 | scratch [W][32] u32
-    float* Psm = reinterpret_cast<float*>(smem);
-    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
-    float* Tsm = reinterpret_cast<float*>(smem + pbytes);
-    const size_t tbytes = (((size_t)n * 4) + 15) & ~(size_t)15;
-    uint8_t* knn_sm = smem + pbytes + tbytes;
-    const size_t kbytes = (size_t)n * 32;
-    uint16_t* tour_all = reinterpret_cast<uint16_t*>(smem + pbytes + tbytes + kbytes);
-    const size_t trbytes = (((size_t)W * n * 2) + 15) & ~(size_t)15;
-    uint32_t* vis_all = reinterpret_cast<uint32_t*>(smem + pbytes + tbytes + kbytes + trbytes);
-    uint32_t* scratch_all = vis_all + W * 8;
-    uint16_t* tour_sm = tour_all + (size_t)warp * n;
-    uint32_t* vis = vis_all + warp * 8;
+    uint8_t* wblk = smem + warp * kKnnWarpBytes;
+    uint8_t* vis = wblk;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(wblk + 256);
+    uint16_t* tour_sm = reinterpret_cast<uint16_t*>(wblk + 384);
+    uint8_t* knn_sm = smem + kKnnFixed;
+    const uint32_t tbytes = (((uint32_t)n * 4u) + 15u) & ~15u;
+    float* Tsm = reinterpret_cast<float*>(knn_sm + (size_t)n * 32);
+    float* Psm = reinterpret_cast<float*>(knn_sm + (size_t)n * 32 + tbytes);
 
     {   // candidate lists of this colony (static per instance)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.knn + (size_t)b * n * 32);
@@ -394,7 +396,7 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
         for (int i = tid; i < n * 8; i += nthreads) dst[i] = __ldg(src + i);
     }
     stage_product(Psm, p.ph, p.heu, n, b, &bar);   // ends with __syncthreads()
-    // T[u] = max of row u over the columns outside knn[u]
+    // bound[u] = (max of row u over the columns outside knn[u]) / q_min, with a margin for the approximate scores
     for (int u = warp; u < n; u += W) {
         const uint32_t jj = knn_sm[u * 32 + lane];
         float m = 0.f;
@@ -404,107 +406,83 @@ static __global__ void __launch_bounds__(512, 2) aco_knn_kernel(const __grid_con
             if (j < n && !((listed >> lane) & 1u)) m = fmaxf(m, Psm[(size_t)u * n + j]);
         }
         const uint32_t tb = __reduce_max_sync(DACO_FULL, __float_as_uint(m));
-        if (lane == 0) Tsm[u] = __uint_as_float(tb);
+        if (lane == 0) Tsm[u] = __fmul_rn(__uint_as_float(tb), 16777216.0f * 1.0001f);
     }
     __syncthreads();
 
-    const int rounds = p.rounds > 0 ? p.rounds : 1;
-    const uint32_t P_addr = pin_u32(smem_u32(Psm));
-    const uint32_t T_addr = pin_u32(smem_u32(Tsm));
-    const uint32_t knn_addr = pin_u32(smem_u32(knn_sm));
-    const uint32_t tour_addr = pin_u32(smem_u32(tour_sm));
-    const uint32_t vis_addr = pin_u32(smem_u32(vis));
-    for (int r = 0; r < rounds; ++r) {
-        const int a0 = (blockIdx.x * rounds + r) * W;
-        const int a = a0 + warp;
-        if (a < p.A) {
-            const uint64_t seed = p.seed;
-            const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
-            const PhiloxRoundKeys& K = p.keys;
-            const uint32_t sub_base = (uint32_t)(a + p.ant_base) * (uint32_t)n;
-            const float kGap = 1.0f - 3.814697265625e-06f;   // 1 - 2^-18
-            const float kInvQmin = 16777216.0f * 1.0001f;    // 1 / q_min with a safety margin for the approximate scores
+    const int a = blockIdx.x * W + warp;
+    if (a >= p.A) return;
+    const uint32_t wbase = pin_u32(smem_u32(wblk));                       // vis at +0, tour at +384
+    const uint32_t knn_lane = pin_u32(smem_u32(knn_sm) + (uint32_t)lane);
+    const uint32_t T_addr = knn_lane - (uint32_t)lane + (uint32_t)n * 32u;
+    const uint32_t P_addr = T_addr + tbytes;
+    const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
+    const PhiloxRoundKeys& K = p.keys;
+    const uint32_t sub_base = (uint32_t)(a + p.ant_base) * (uint32_t)n;
 
-            int cur;
-            uint64_t off_noise = offset0;
-            if (p.start_node >= 0) {
-                cur = p.start_node;
-            } else if (p.start) {
-                cur = (int)p.start[(size_t)b * p.A + a];
-            } else {
-                cur = (int)(torch_philox_word(seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
-                off_noise += p.start_increment;
-            }
-            if (lane < 8) vis[lane] = (lane == (cur >> 5)) ? (1u << (cur & 31)) : 0u;
-            if (lane == 0) sts_u16(tour_addr, (uint32_t)cur);
-            __syncwarp();
+    int cur;
+    uint64_t ctr = offset0 >> 2;                                          // Philox counter of the first noise draw
+    if (p.start_node >= 0) {
+        cur = p.start_node;
+    } else {
+        cur = (int)(torch_philox_word(p.seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
+        ctr += p.start_increment >> 2;
+    }
+    const uint32_t ctr_step = p.step_increment >> 2;
+    for (int k = lane; k < 64; k += 32) reinterpret_cast<uint32_t*>(vis)[k] = 0u;
+    __syncwarp();
+    if (lane == 0) {
+        vis[cur] = 1;
+        tour_sm[0] = (uint16_t)cur;
+    }
+    __syncwarp();
 
 #pragma unroll 1
-            for (int step = 0; step < n - 1; ++step) {
-                const uint64_t off_step = off_noise + (uint64_t)p.step_increment * (uint64_t)step;
-                const uint32_t ctr_lo = (uint32_t)(off_step >> 2), ctr_hi = (uint32_t)(off_step >> 34);
-                const uint32_t j = lds_u8(knn_addr + (uint32_t)cur * 32u + lane);
-                const uint32_t vw = lds_u32(vis_addr + ((j >> 5) << 2));
-                const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
-                float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
-                x = ((vw >> (j & 31)) & 1u) ? 0.f : x;
-                const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
-                const uint32_t mybits = __float_as_uint(A);
-                const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
-                const float top = __uint_as_float(topbits);
-                const bool is_top = mybits == topbits;
-                const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
-                const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, kGap) && !is_top);
-                uint32_t jstar;
-                if (nears == 0u && __popc(tops) == 1 && __fmul_rn(T, kInvQmin) < top) {
-                    jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
-                } else {
-                    jstar = knn_dense_step(p, Psm, cur, vis, scratch_all + warp * 32, ctr_lo, ctr_hi, off_step, sub_base);
-                }
-                if (lane == 0) {
-                    vis[jstar >> 5] |= 1u << (jstar & 31);
-                    sts_u16(tour_addr + 2 * (step + 1), jstar);
-                }
-                __syncwarp();
-                cur = (int)jstar;
-            }
-            if (p.tours) {   // warp-local, coalesced: this ant's row of the compact layout
-                uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
-                for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
-            }
-            if (p.costs) {   // fused ACO.gen_path_costs + neighbour table (same arithmetic as tsp_cost_kernel)
-                const float* D = p.dist + (size_t)b * n * n;
-                auto edge = [&](int k) -> float {
-                    return __ldg(D + (size_t)tour_sm[k] * n + tour_sm[k == 0 ? n - 1 : k - 1]);
-                };
-                const float c = aten_row_sum_fn(edge, n, p.lbw, p.vec != 0, lane, p.vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
-                if (lane == 0) p.costs[(size_t)b * p.A + a] = c;
-                uint32_t* N = p.nbr + (size_t)b * n * p.A;
-                for (int k = lane; k < n; k += 32) {
-                    const uint32_t u = tour_sm[k], pr = tour_sm[k == 0 ? n - 1 : k - 1], su = tour_sm[k == n - 1 ? 0 : k + 1];
-                    N[(size_t)u * p.A + a] = (pr << 16) | su;
-                }
-            }
-        }
-        if (p.paths) {       // reference layout needs the CTA's ants side by side: cooperative write
-            __syncthreads();
-            const int wvalid = min(W, p.A - a0);
-            int64_t* out = p.paths + (size_t)b * n * p.A;
-            for (int i = tid; i < n * W; i += nthreads) {
-                const int s2 = i / W, w = i - s2 * W;
-                if (w < wvalid) out[(size_t)s2 * p.A + a0 + w] = (int64_t)tour_all[(size_t)w * n + s2];
-            }
-            __syncthreads();
+    for (int step = 1; step < n; ++step, ctr += ctr_step) {
+        const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
+        const uint32_t dead = lds_u8(wbase + j);
+        const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
+        float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
+        x = dead ? 0.f : x;
+        const float A = __fmul_rn(x, noise_rcp((uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base + j, K));
+        const uint32_t mybits = __float_as_uint(A);
+        const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+        const float top = __uint_as_float(topbits);
+        const bool is_top = mybits == topbits;
+        const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
+        const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f) && !is_top);
+        uint32_t jstar;
+        if (nears == 0u && __popc(tops) == 1 && T < top) {
+            jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
         } else {
-            __syncwarp();
+            jstar = knn_dense_step(p, Psm, cur, vis, scratch, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
+        }
+        if (lane == 0) {
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(1u) : "memory");
+            sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
+        }
+        __syncwarp();
+        cur = (int)jstar;
+    }
+    {   // warp-local, coalesced: this ant's row of the compact layout
+        uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
+        for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
+    }
+    if (FUSE_COST) {   // fused ACO.gen_path_costs + neighbour table (same arithmetic as tsp_cost_kernel)
+        const float* D = p.dist + (size_t)b * n * n;
+        auto edge = [&](int k) -> float { return __ldg(D + (size_t)tour_sm[k] * n + tour_sm[k == 0 ? n - 1 : k - 1]); };
+        const float c = aten_row_sum_fn(edge, n, p.lbw, p.vec != 0, lane, p.vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
+        if (lane == 0) p.costs[(size_t)b * p.A + a] = c;
+        uint32_t* N = p.nbr + (size_t)b * n * p.A;
+        for (int k = lane; k < n; k += 32) {
+            const uint32_t u = tour_sm[k], pr = tour_sm[k == 0 ? n - 1 : k - 1], su = tour_sm[k == n - 1 ? 0 : k + 1];
+            N[(size_t)u * p.A + a] = (pr << 16) | su;
         }
     }
 }
 
 inline size_t knn_kernel_smem(int n, int W) {
-    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
-    const size_t tbytes = (((size_t)n * 4) + 15) & ~(size_t)15;
-    return pbytes + tbytes + (size_t)n * 32 + ((((size_t)W * n * 2) + 15) & ~(size_t)15) + (size_t)W * (8 + 32) * 4;
+    return (size_t)kKnnWarpBytes * (W <= 8 ? 8 : 16) + (size_t)n * 32 + ((((size_t)n * 4) + 15) & ~(size_t)15) + ((((size_t)n * n * 4) + 15) & ~(size_t)15);
 }
 
 inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp) {

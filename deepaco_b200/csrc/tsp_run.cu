@@ -27,9 +27,10 @@ __global__ void hadamard2_kernel(const float* __restrict__ a, const float* __res
 
 // one CTA per colony: iteration best -> running best, MMAS bookkeeping
 __global__ void __launch_bounds__(256) tsp_best_kernel(const float* __restrict__ costs, const uint16_t* __restrict__ tours,
-                                                       const float* __restrict__ ph, int n, int A, int min_max,
+                                                       const float* __restrict__ ph, int n, int tour_len, int A, int min_max,
                                                        float* __restrict__ lowest, int64_t* __restrict__ shortest,
-                                                       float* __restrict__ ph_max, float* __restrict__ scale) {
+                                                       float* __restrict__ ph_max, float* __restrict__ scale,
+                                                       const int32_t* __restrict__ tmax, int32_t* __restrict__ shortest_rows) {
     __shared__ float s_c[32];
     __shared__ int s_i[32];
     __shared__ int s_improved, s_first;
@@ -69,9 +70,12 @@ __global__ void __launch_bounds__(256) tsp_best_kernel(const float* __restrict__
     if (!s_improved) return;
     bc = s_c[0];
     bi = s_i[0];
-    const uint16_t* t = tours + ((size_t)b * A + bi) * n;
-    for (int k = tid; k < n; k += blockDim.x) shortest[(size_t)b * n + k] = (int64_t)t[k];
-    if (tid == 0) lowest[b] = bc;
+    const uint16_t* t = tours + ((size_t)b * A + bi) * tour_len;
+    for (int k = tid; k < tour_len; k += blockDim.x) shortest[(size_t)b * tour_len + k] = (int64_t)t[k];
+    if (tid == 0) {
+        lowest[b] = bc;
+        if (shortest_rows) shortest_rows[b] = tmax[b] + 1;   // CVRP: rows of that iteration's `paths`
+    }
     if (min_max) {
         // max = problem_size / lowest_cost  ==  reciprocal(lowest) * n   (Tensor.__rtruediv__)
         const float new_max = __fmul_rn(__fdiv_rn(1.0f, bc), (float)n);
@@ -91,6 +95,15 @@ __global__ void __launch_bounds__(256) tsp_best_kernel(const float* __restrict__
         }
         if (tid == 0) ph_max[b] = new_max;
     }
+}
+
+int best_launch(const float* costs, const uint16_t* tours, const float* ph, int n, int tour_len, int A, int B, int min_max,
+                float* lowest, int64_t* shortest, float* ph_max, float* scale, const int32_t* tmax, int32_t* shortest_rows,
+                cudaStream_t st) {
+    tsp_best_kernel<<<B, 256, 0, st>>>(costs, tours, ph, n, tour_len, A, min_max, lowest, shortest, ph_max, scale, tmax,
+                                       shortest_rows);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
 }
 
 }  // namespace deepaco
@@ -123,8 +136,8 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
             rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, a->neighbours, st);
             if (rc) return rc;
         }
-        tsp_best_kernel<<<B, 256, 0, st>>>(a->costs, a->tours, a->pheromone, n, A, a->min_max, a->lowest_cost, a->shortest_path,
-                                           a->ph_max, a->min_max ? a->scale : nullptr);
+        tsp_best_kernel<<<B, 256, 0, st>>>(a->costs, a->tours, a->pheromone, n, n, A, a->min_max, a->lowest_cost, a->shortest_path,
+                                           a->ph_max, a->min_max ? a->scale : nullptr, nullptr, nullptr);
         DACO_CHECK_LAUNCH();
         rc = tsp_update_launch(a->pheromone, a->neighbours, a->costs, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min,
                                a->ph_max, a->min_max ? a->scale : nullptr, a->heuristic, a->product, st);

@@ -269,7 +269,7 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
-        if (knn && !noise && !log_probs && n > 32 && n <= 256 && !getenv("DEEPACO_TSP_NO_KNN")) {
+        if (knn && !noise && !log_probs && !paths && !start && tours && n > 32 && n <= 256 && !getenv("DEEPACO_TSP_NO_KNN")) {
             // sparse product: one candidate per lane (kNN kernel)
             int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : 8;
             if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) Wk = w; }
@@ -277,22 +277,23 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
                 if (total_ants > (long)di->sm_count * 4)
                     while (Wk < 16 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;
                 q.knn = knn;
-                if (fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants) {
+                const bool fuse = fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants && getenv("DEEPACO_TSP_FUSE_COST");
+                if (fuse) {
                     q.dist = fuse_dist; q.costs = fuse_costs; q.nbr = fuse_nbr;
                     if (fused_out) *fused_out = 1;
                 }
-                // several ant groups per CTA once the grid is many waves deep: staging P and the per-row bounds
-                // is paid once per CTA
-                int rounds = 1;
-                const long ctas = (long)n_colonies * ((n_ants + Wk - 1) / Wk);
-                const long slots = (long)di->sm_count * (cap / knn_kernel_smem(n, Wk));
-                if (const char* e = getenv("DEEPACO_TSP_ROUNDS")) rounds = atoi(e) > 0 ? atoi(e) : 1;
-                else while (rounds < 8 && ctas / (rounds * 2) >= 6 * slots && (n_ants + Wk * rounds * 2 - 1) / (Wk * rounds * 2) >= 1 && n_ants % (Wk * rounds * 2) == 0) rounds *= 2;
-                q.rounds = rounds;
-                DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_kernel_smem(n, Wk)));
-                DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                dim3 grid((n_ants + Wk * rounds - 1) / (Wk * rounds), n_colonies);
-                aco_knn_kernel<<<grid, Wk * 32, knn_kernel_smem(n, Wk), st>>>(q);
+                dim3 grid((n_ants + Wk - 1) / Wk, n_colonies);
+                const size_t ksm = knn_kernel_smem(n, Wk);
+#define DACO_KNN(F, M)                                                                                                          \
+    do {                                                                                                                        \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));     \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel<F, M>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                                             cudaSharedmemCarveoutMaxShared));                                                  \
+        aco_knn_kernel<F, M><<<grid, Wk * 32, ksm, st>>>(q);                                                                    \
+    } while (0)
+                if (fuse) { if (Wk <= 8) DACO_KNN(true, 8); else DACO_KNN(true, 16); }
+                else { if (Wk <= 8) DACO_KNN(false, 8); else DACO_KNN(false, 16); }
+#undef DACO_KNN
                 DACO_CHECK_LAUNCH();
                 return DEEPACO_OK;
             }

@@ -62,6 +62,7 @@ class ACO:
         self.shortest_path = None
         self.lowest_cost = float('inf')
         self.device = distances.device if str(device) == 'cpu' else torch.device(device)
+        self._runner = None
 
     def sample(self):
         paths, log_probs = self.gen_path(require_prob=True)
@@ -77,14 +78,18 @@ class ACO:
         '''cvrp/aco.py:138-165.  Returns paths [T+1, n_ants] int64 (T data dependent) and log_probs [T, n_ants].'''
         ph, heu = self._weights()
         gen, seed, offset = generator_state(self.device)
-        out = E.cvrp_sample(ph.detach(), heu.detach(), self.demand, self.capacity, self.n_ants, seed=seed,
-                            offset=offset, want_logp=require_prob)
-        T = int(out["tmax"][0].item())          # one host sync per construction (the reference has one per step)
-        gen.set_offset(offset + T * E.cvrp_step_offset_increment(self.problem_size, self.n_ants))
-        paths = out["paths"][0, :T + 1]
-        if require_prob:
-            return paths, out["logp"][0, :T]
-        return paths
+
+        def construct(ph_, heu_):
+            out = E.cvrp_sample(ph_, heu_, self.demand, self.capacity, self.n_ants, seed=seed, offset=offset,
+                                want_logp=require_prob)
+            T = int(out["tmax"][0].item())      # one host sync per construction (the reference has one per step)
+            gen.set_offset(offset + T * E.cvrp_step_offset_increment(self.problem_size, self.n_ants))
+            return out["paths"][0, :T + 1].contiguous(), (out["logp"][0, :T].contiguous() if require_prob else None)
+
+        if require_prob and torch.is_grad_enabled() and (ph.requires_grad or heu.requires_grad):
+            return E.SampleLogProbs.apply(ph, heu, construct, self.demand, float(self.capacity))
+        paths, logp = construct(ph.detach(), heu.detach())
+        return (paths, logp) if require_prob else paths
 
     @torch.no_grad()
     def gen_path_costs(self, paths):
@@ -98,20 +103,47 @@ class ACO:
         E.cvrp_update_(ph, nbr, costs, decay=self.decay, elitist=self.elitist, min_max=self.min_max,
                        ph_min=self.min if self.min_max else 0.0, ph_max=self.max if self.min_max else None)
         self.pheromone = ph
+        self._runner = None
 
     @torch.no_grad()
     def run(self, n_iterations):
+        '''cvrp/aco.py:72-104 (adaptive=False) on the device: no host round trip per construction step or per
+        iteration; the generator offset (data dependent: one draw per step of the slowest ant) is read back once.'''
+        if self.alpha != 1 or self.beta != 1:
+            return self._run_stepwise(n_iterations)
+        if self._runner is None:
+            r = E.CvrpRunner(self.distances, self.demand, self.heuristic, self.pheromone, self.n_ants,
+                             capacity=self.capacity, decay=self.decay, elitist=self.elitist, min_max=self.min_max,
+                             ph_min=self.min if self.min_max else 0.0)
+            if not isinstance(self.lowest_cost, float) or self.lowest_cost != float('inf'):
+                r.lowest_cost.fill_(float(self.lowest_cost))
+            if self.min_max and self.max is not None:
+                r.ph_max.fill_(float(self.max))
+            self._runner = r
+        r = self._runner
+        gen, seed, offset = generator_state(self.device)
+        r.run(n_iterations, seed, [offset])
+        gen.set_offset(int(r.offsets[0].item()))
+        self.pheromone = r.pheromone[0].clone()
+        self.lowest_cost = r.lowest_cost[0].clone()
+        rows = int(r.shortest_rows[0].item())
+        if rows > 0:
+            self.shortest_path = r.shortest_path[0, :rows].clone()
+        if self.min_max:
+            self.max = r.ph_max[0].clone()
+        return self.lowest_cost
+
+    def _run_stepwise(self, n_iterations):
         for _ in range(n_iterations):
             paths = self.gen_path(require_prob=False)
             costs = self.gen_path_costs(paths)
-            best_cost, best_idx = costs.min(dim=0)
-            if best_cost < self.lowest_cost:
-                self.shortest_path = paths[:, best_idx]
-                self.lowest_cost = best_cost
+            best = torch.argmin(costs)
+            if costs[best] < self.lowest_cost:
+                self.shortest_path, self.lowest_cost = paths[:, best], costs[best]
                 if self.min_max:
-                    max = self.problem_size / self.lowest_cost
+                    new_max = self.problem_size / self.lowest_cost
                     if self.max is None:
-                        self.pheromone *= max / self.pheromone.max()
-                    self.max = max
+                        self.pheromone = self.pheromone * (new_max / self.pheromone.max())
+                    self.max = new_max
             self.update_pheronome(paths, costs)
         return self.lowest_cost

@@ -114,10 +114,18 @@ class ACO:
         Returns paths [problem_size, n_ants] int64 (and log_probs [problem_size-1, n_ants]).'''
         ph, heu = self._weights()
         gen, seed, offset = generator_state(self.device)
-        paths, logp, _ = E.tsp_sample(ph.detach(), heu.detach(), self.n_ants, start_node=self._START_NODE,
-                                      double_norm=self._DOUBLE_NORM, seed=seed, offset=offset, want_logp=require_prob,
-                                      knn=None if require_prob else self._candidates())
         gen.set_offset(offset + E.tsp_sample_offset_increment(self.problem_size, self.n_ants, self._START_NODE))
+
+        def construct(ph_, heu_):
+            paths_, logp_, _ = E.tsp_sample(ph_, heu_, self.n_ants, start_node=self._START_NODE,
+                                            double_norm=self._DOUBLE_NORM, seed=seed, offset=offset, want_logp=require_prob,
+                                            knn=None if require_prob else self._candidates())
+            return paths_, logp_
+
+        if require_prob and torch.is_grad_enabled() and (ph.requires_grad or heu.requires_grad):
+            # REINFORCE training path: log-probs differentiable w.r.t. heuristic (and pheromone)
+            return E.SampleLogProbs.apply(ph, heu, construct, None, 0.0)
+        paths, logp = construct(ph.detach(), heu.detach())
         return (paths, logp) if require_prob else paths
 
     @torch.no_grad()

@@ -190,6 +190,47 @@ int deepaco_cvrp_update(float* pheromone, const uint32_t* neighbours, const floa
                         int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
                         void* stream);
 
+/* ACO.run for CVRP (cvrp/aco.py:72-104, adaptive = False) on the device, like deepaco_tsp_run.  Path lengths are
+ * data dependent, hence so is the generator consumption: `offsets` (device uint64 [B], REQUIRED, in/out) holds each
+ * colony's current Philox offset and is advanced by tmax * step_increment after every iteration; read it back to
+ * resynchronise a host-side generator.  tours u16 [B][A][2N], lens i32 [B][A], tmax i32 [B], shortest_path i64
+ * [B][2N] (zero padded; its length is the tmax of the iteration that produced it + 1). */
+typedef struct {
+    int n_nodes, n_ants, n_colonies;
+    float capacity;
+    float decay;
+    int elitist, min_max;
+    float ph_min;
+    uint64_t seed;
+    uint64_t* offsets;
+    float* pheromone;
+    const float* heuristic;
+    const float* distances;
+    const float* demand;
+    float* product;
+    int product_valid;
+    uint16_t* tours;
+    float* costs;
+    uint32_t* neighbours;
+    int32_t* lens;
+    int32_t* tmax;
+    float* lowest_cost;
+    int64_t* shortest_path;
+    int32_t* shortest_rows; /* optional i32 [B]: rows (tmax + 1) of the iteration that produced shortest_path */
+    float* ph_max;
+    float* scale;
+} deepaco_cvrp_run_args;
+int deepaco_cvrp_run(const deepaco_cvrp_run_args* args, int n_iterations, void* stream);
+
+/* ---- backward of the log-probabilities (ACO.sample -> REINFORCE loss; tsp/aco.py:165-177, cvrp/aco.py:167-174)
+ * Analytic gradient of sum_{t,a} grad_log_probs[t][a] * log_probs[t][a] with respect to the (powered) heuristic
+ * and optionally the (powered) pheromone, by replaying the paths (int64 [path_rows][n_ants]).  demand = NULL:
+ * TSP masks; demand != NULL: CVRP visit + capacity masks.  Gradients are ACCUMULATED (fp32 atomics) into
+ * grad_heuristic / grad_pheromone ([n][n], caller zeroes; grad_pheromone may be NULL). */
+int deepaco_logp_backward(const float* pheromone_pow, const float* heuristic_pow, const int64_t* paths,
+                          const float* grad_log_probs, int n, int n_ants, int path_rows, const float* demand,
+                          float capacity, float* grad_heuristic, float* grad_pheromone, void* stream);
+
 /* ---- debug / probe entry points (used by tests to validate the torch-parity assumptions) ------ */
 int deepaco_debug_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out, void* stream);
 int deepaco_debug_randint(uint64_t seed, uint64_t offset, int64_t numel, int64_t high, int64_t* out, void* stream);
