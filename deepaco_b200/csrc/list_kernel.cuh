@@ -437,32 +437,45 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     }
     __syncwarp();
 
+    // Fast steps run in an inner loop that contains no call, so its registers are not constrained by the calling
+    // convention; a step that needs the dense / exact treatment leaves it, is handled, and the fast loop resumes.
+    int step = 1;
 #pragma unroll 1
-    for (int step = 1; step < n; ++step, ctr += ctr_step) {
-        const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
-        const uint32_t dead = lds_u8(wbase + j);
-        const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
-        float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
-        x = dead ? 0.f : x;
-        const float A = __fmul_rn(x, noise_rcp((uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base + j, K));
-        const uint32_t mybits = __float_as_uint(A);
-        const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
-        const float top = __uint_as_float(topbits);
-        const bool is_top = mybits == topbits;
-        const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
-        const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f) && !is_top);
-        uint32_t jstar;
-        if (nears == 0u && __popc(tops) == 1 && T < top) {
-            jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
-        } else {
-            jstar = knn_dense_step(p, Psm, cur, vis, scratch, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
+    while (step < n) {
+#pragma unroll 1
+        for (; step < n; ++step, ctr += ctr_step) {
+            const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
+            const uint32_t dead = lds_u8(wbase + j);
+            const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
+            float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
+            x = dead ? 0.f : x;
+            const float A = __fmul_rn(x, noise_rcp((uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base + j, K));
+            const uint32_t mybits = __float_as_uint(A);
+            const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+            const float top = __uint_as_float(topbits);
+            const bool is_top = mybits == topbits;
+            const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
+            const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f) && !is_top);
+            if (!(nears == 0u && __popc(tops) == 1 && T < top)) break;
+            const uint32_t jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
+            if (lane == 0) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(1u) : "memory");
+                sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
+            }
+            __syncwarp();
+            cur = (int)jstar;
         }
-        if (lane == 0) {
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(1u) : "memory");
-            sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
+        if (step < n) {
+            const uint32_t jstar = knn_dense_step(p, Psm, cur, vis, scratch, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
+            if (lane == 0) {
+                vis[jstar] = 1;
+                tour_sm[step] = (uint16_t)jstar;
+            }
+            __syncwarp();
+            cur = (int)jstar;
+            ++step;
+            ctr += ctr_step;
         }
-        __syncwarp();
-        cur = (int)jstar;
     }
     {   // warp-local, coalesced: this ant's row of the compact layout
         uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
