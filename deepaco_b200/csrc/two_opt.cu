@@ -45,7 +45,7 @@ __device__ float numpy_pairwise_sum(F f, int lo, int n) {
 struct TwoOptShared {
     uint16_t* tour;   // [n]
     float* edge;      // [n]  edge[k] = d[tour[k-1], tour[k]], edge[0] = d[tour[n-1], tour[0]]
-    float* rows;      // [W][2][n]
+    float* rows;      // [W][3][n]  triple-buffered distance rows (cp.async prefetch of the next row)
     float* red_c;     // [W]
     uint32_t* red_k;  // [W]
     int* band;        // [W+1]
@@ -54,8 +54,20 @@ struct TwoOptShared {
 // one 2-opt call: up to max_iterations passes on the tour in shared memory; returns passes done
 __device__ int two_opt_call(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    float* rowA = S.rows + (size_t)warp * 2 * n;
-    float* rowB = rowA + n;
+    float* rowbuf = S.rows + (size_t)warp * 3 * n;
+    const bool vec16 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+    // asynchronous global -> shared copy of one distance row (LDGSTS); completion via cp.async groups
+    auto prefetch_row = [&](float* dst, int node) {
+        const float* src = D + (size_t)node * n;
+        if (vec16) {
+            for (int c = lane * 4; c < n; c += 128)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+        } else {
+            for (int c = lane; c < n; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     int it = 0;
     while (it < max_iterations) {
         __syncthreads();
@@ -67,17 +79,18 @@ __device__ int two_opt_call(const float* __restrict__ D, int n, int max_iteratio
         float best = 0.f;                 // delta starts at 0 (two_opt.py:10)
         uint32_t bestkey = 0xffffffffu;
         const int lo = S.band[warp], hi = S.band[warp + 1];
-        float* rp = rowA;                 // d[tour[i-1], :]
-        float* ri = rowB;                 // d[tour[i], :]
         if (lo < hi) {
-            const float* src = D + (size_t)S.tour[lo - 1] * n;
-            for (int c = lane; c < n; c += 32) rp[c] = __ldg(src + c);
+            prefetch_row(rowbuf, S.tour[lo - 1]);          // d[tour[i-1], :] of the first i
+            prefetch_row(rowbuf + n, S.tour[lo]);          // d[tour[i], :]
         }
         for (int i = lo; i < hi; ++i) {
-            const int ni = S.tour[i];
-            const float* src = D + (size_t)ni * n;
-            for (int c = lane; c < n; c += 32) ri[c] = __ldg(src + c);
+            const int slot = (i - lo) % 3;
+            const float* rp = rowbuf + (size_t)slot * n;               // d[tour[i-1], :]
+            const float* ri = rowbuf + (size_t)((slot + 1) % 3) * n;   // d[tour[i], :]
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
+            if (i + 1 < hi) prefetch_row(rowbuf + (size_t)((slot + 2) % 3) * n, S.tour[i + 1]);   // overlaps the sweep below
+            const int ni = S.tour[i];
             const int p = S.tour[i - 1];
             const float e_i = S.edge[i];
             for (int j = i + 1 + lane; j < n; j += 32) {
@@ -92,7 +105,6 @@ __device__ int two_opt_call(const float* __restrict__ D, int n, int max_iteratio
                 }
             }
             __syncwarp();
-            float* t = rp; rp = ri; ri = t;
         }
         // CTA arg-min with lowest key on ties (== first strict minimum of the sequential scan)
         for (int off = 16; off > 0; off >>= 1) {
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(256) two_opt_kernel(const float* __restrict__ 
     const int a = blockIdx.x, b = blockIdx.y;
     TwoOptShared S;
     S.rows = reinterpret_cast<float*>(smem);
-    S.edge = S.rows + (size_t)W * 2 * n;
+    S.edge = S.rows + (size_t)W * 3 * n;
     S.red_c = S.edge + n;
     S.red_k = reinterpret_cast<uint32_t*>(S.red_c + W);
     S.band = reinterpret_cast<int*>(S.red_k + W);
@@ -200,7 +212,7 @@ static int launch_two_opt(const float* dist, const float* heu_dist, uint16_t* to
     DACO_CHECK_ARG(n >= 4 && n <= 65535 && A >= 1 && B >= 1 && B <= 65535, "deepaco_two_opt: bad sizes (n >= 4)");
     DACO_CHECK_ARG(maxt >= 0 && T_nls >= 0 && T_p >= 0, "deepaco_two_opt: negative iteration count");
     const int W = 8;
-    const size_t smem = ((size_t)W * 2 * n + n + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)2 * n * 2 + 16;
+    const size_t smem = ((size_t)W * 3 * n + n + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)2 * n * 2 + 16;
     DACO_CHECK_ARG(smem <= (size_t)di->max_smem_optin - 1024, "deepaco_two_opt: n=%d does not fit shared memory", n);
     DACO_CHECK_CUDA(cudaFuncSetAttribute(two_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(A, B);
