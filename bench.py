@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.004)
 
     def finish(self):
         self._halt.set()
@@ -135,7 +135,7 @@ def cpu_reference_throughput(steps, warmup, seed=1234, budget_s=25.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--colonies", type=int, default=256, help="colonies per GPU")
     ap.add_argument("--impl", default="deepaco_b200", choices=["deepaco_b200", "reference"])
@@ -264,7 +264,7 @@ def main():
         "config": {"workload": workload, "colonies_per_gpu": B, "tours_per_step": tours_per_step, "heuristic": heu_how,
                    "l2": "flushed (256 MiB memset) between steps, outside the per-step CUDA-event pairs",
                    "parallelism": f"{world} x independent colony batches (no data-path collective)"},
-        "roofline": {"bound": "hbm", "kernel": "aco_list_kernel (K1 tour construction)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "K1 tour construction (aco_knn_kernel; aco_list_kernel for dense heuristics)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_TOUR * B * N_ANTS, "kernel_ms": samp_mean,
                      "kernel_share_of_step": samp_mean / (total_ms / K),

@@ -148,25 +148,65 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
 
 // Host-buffer entry point (what a CPU-side caller of the reference's ACO.run would bind): copies the three
 // matrices of every colony to the device buffers named in `a`, runs, copies the results back, synchronises.
+// Colonies are independent, so the batch is cut into up to four chunks that alternate between the caller's stream
+// and an internal one: the H2D / D2H copies of one chunk overlap the kernels of the other.
+static cudaStream_t g_aux_stream = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+
 extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterations, const float* distances_host,
                                     const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
                                     int64_t* shortest_path_host, int copy_back_pheromone, void* stream) {
     DACO_CHECK_ARG(a && distances_host && heuristic_host && pheromone_host && lowest_cost_host && shortest_path_host,
                    "deepaco_tsp_run_host: NULL argument");
-    const bool ph_back = (copy_back_pheromone != 0);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t mat = (size_t)a->n_colonies * a->n * a->n * sizeof(float);
-    DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->distances), distances_host, mat, cudaMemcpyHostToDevice, st));
-    DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->heuristic), heuristic_host, mat, cudaMemcpyHostToDevice, st));
-    DACO_CHECK_CUDA(cudaMemcpyAsync(a->pheromone, pheromone_host, mat, cudaMemcpyHostToDevice, st));
-    deepaco_tsp_run_args b = *a;
-    b.product_valid = 0;
-    const int rc = deepaco_tsp_run(&b, n_iterations, stream);
-    if (rc) return rc;
-    if (ph_back) DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host, a->pheromone, mat, cudaMemcpyDeviceToHost, st));
-    DACO_CHECK_CUDA(cudaMemcpyAsync(lowest_cost_host, a->lowest_cost, sizeof(float) * a->n_colonies, cudaMemcpyDeviceToHost, st));
-    DACO_CHECK_CUDA(cudaMemcpyAsync(shortest_path_host, a->shortest_path, sizeof(int64_t) * a->n_colonies * a->n,
-                                    cudaMemcpyDeviceToHost, st));
+    if (!g_aux_stream) {
+        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking));
+        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    }
+    const int B = a->n_colonies, n = a->n, A = a->n_ants;
+    const int chunks = B >= 16 ? 4 : 1;
+    const size_t mat1 = (size_t)n * n;
+    if (chunks > 1) {   // the internal stream starts after everything already queued on the caller's stream
+        DACO_CHECK_CUDA(cudaEventRecord(g_ev_fork, st));
+        DACO_CHECK_CUDA(cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0));
+    }
+    for (int c = 0; c < chunks; ++c) {
+        const int b0 = (int)((long)B * c / chunks), b1 = (int)((long)B * (c + 1) / chunks), nb = b1 - b0;
+        cudaStream_t s = (c & 1) ? g_aux_stream : st;
+        deepaco_tsp_run_args b = *a;
+        b.n_colonies = nb;
+        b.product_valid = 0;
+        b.offsets = a->offsets ? a->offsets + b0 : nullptr;
+        b.pheromone = a->pheromone + b0 * mat1;
+        b.heuristic = a->heuristic + b0 * mat1;
+        b.distances = a->distances + b0 * mat1;
+        b.product = a->product + b0 * mat1;
+        b.tours = a->tours + (size_t)b0 * A * n;
+        b.costs = a->costs + (size_t)b0 * A;
+        b.neighbours = a->neighbours + (size_t)b0 * n * A;
+        b.lowest_cost = a->lowest_cost + b0;
+        b.shortest_path = a->shortest_path + (size_t)b0 * n;
+        b.ph_max = a->ph_max ? a->ph_max + b0 : nullptr;
+        b.scale = a->scale ? a->scale + b0 : nullptr;
+        b.knn = a->knn ? a->knn + (size_t)b0 * n * 32 : nullptr;
+        b.ev_sample_begin = b.ev_sample_end = nullptr;
+        const size_t bytes = (size_t)nb * mat1 * sizeof(float);
+        DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(b.distances), distances_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));
+        DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(b.heuristic), heuristic_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));
+        DACO_CHECK_CUDA(cudaMemcpyAsync(b.pheromone, pheromone_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));
+        const int rc = deepaco_tsp_run(&b, n_iterations, s);
+        if (rc) return rc;
+        if (copy_back_pheromone)
+            DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host + b0 * mat1, b.pheromone, bytes, cudaMemcpyDeviceToHost, s));
+        DACO_CHECK_CUDA(cudaMemcpyAsync(lowest_cost_host + b0, b.lowest_cost, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
+        DACO_CHECK_CUDA(cudaMemcpyAsync(shortest_path_host + (size_t)b0 * n, b.shortest_path, sizeof(int64_t) * nb * n,
+                                        cudaMemcpyDeviceToHost, s));
+    }
+    if (chunks > 1) {
+        DACO_CHECK_CUDA(cudaEventRecord(g_ev_join, g_aux_stream));
+        DACO_CHECK_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
+    }
     DACO_CHECK_CUDA(cudaStreamSynchronize(st));
     return DEEPACO_OK;
 }
