@@ -273,6 +273,23 @@ def main():
                 "api": "deepaco_tsp_run_host (C ABI, pinned host buffers)", "ms_per_step": float(e2e_ms) / K},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    # best-cost gap vs the reference on this GPU: same torch seed, one colony of the workload, oracle = the
+    # reference's op sequence run with device='cuda' (outside every timed region)
+    try:
+        from deepaco_b200.tsp.aco import ACO
+        from oracle import aco_torch as O
+        T_par = 5
+        torch.manual_seed(2024)
+        mine = ACO(dist[0], n_ants=N_ANTS, heuristic=heu[0], device=dev)
+        low = float(mine.run(T_par))
+        torch.manual_seed(2024)
+        ref = O.TspColony(dist[0], N_ANTS, heuristic=heu[0])
+        ref_low = float(ref.run(T_par))
+        line["parity"] = {"iterations": T_par, "best_cost": low, "reference_best_cost": ref_low,
+                          "best_cost_gap": abs(low - ref_low), "pheromone_identical": bool(torch.equal(mine.pheromone, ref.pheromone)),
+                          "best_tour_identical": bool(torch.equal(mine.shortest_path, ref.shortest_path))}
+    except Exception as exc:      # the oracle is test infrastructure; its absence must not break the bench
+        line["parity"] = {"error": str(exc)[:200]}
     if not args.no_cpu_baseline:
         cb, _, _ = cpu_reference_throughput(100, 2)
         line["cpu_baseline"] = cb
