@@ -31,7 +31,9 @@ struct GnnParams {
     const float* weights;   // packed, see deepaco_b200/net.py pack_weights()
     float* node_ws;         // [B][n][6*32] scratch: x | x1 | x3 | agg | x2 | x4
     float* edge_ws;         // [B][E][32]   scratch: w
-    float* out;             // [B][E]       heuristic per ORIGINAL edge id
+    float* out;             // [B][E]       heuristic per ORIGINAL edge id (may be null when dense_out is given)
+    float* dense_out;       // [B][n][n] or null: Net.reshape(pyg, heu) + eps  (zero-padded matrix, tsp/net.py:95-102)
+    float dense_eps;
     int n, E, feats;
 };
 
@@ -176,6 +178,11 @@ __global__ void __launch_bounds__(512) gnn_forward_kernel(const GnnParams p) {
         }
         __syncthreads();
     }
+    if (p.dense_out) {          // background of the dense matrix: 0 + eps off-graph
+        float* M = p.dense_out + (size_t)b * n * n;
+        for (int i = tid; i < n * n; i += nth) M[i] = p.dense_eps;
+        __syncthreads();
+    }
     // ---- head MLP per edge
     const float* H0 = head, *H1 = head + (U * U + U), *H2 = head + 2 * (U * U + U);
     const int32_t* order = p.order + (size_t)b * E;
@@ -193,7 +200,16 @@ __global__ void __launch_bounds__(512) gnn_forward_kernel(const GnnParams p) {
         float acc = H2[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) acc = fmaf(H2[k], silu_f(h[k]), acc);
-        p.out[(size_t)b * E + order[e]] = sigmoid_f(acc);
+        const float hv = sigmoid_f(acc);
+        if (p.out) p.out[(size_t)b * E + order[e]] = hv;
+        if (p.dense_out) {
+            int lo = 0, hi = n;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (rp[mid] <= e) lo = mid; else hi = mid;
+            }
+            p.dense_out[((size_t)b * n + lo) * n + dst[e]] = hv + p.dense_eps;
+        }
     }
 }
 
@@ -205,11 +221,12 @@ extern "C" int64_t deepaco_gnn_weight_count(int feats) { return (int64_t)U * fea
 
 extern "C" int deepaco_gnn_forward(const float* x, const int32_t* row_ptr, const int32_t* dst_sorted, const float* attr_sorted,
                                    const int32_t* order, const float* weights, int n_nodes, int n_edges, int feats,
-                                   int n_instances, float* node_ws, float* edge_ws, float* heu_out, void* stream) {
-    DACO_CHECK_ARG(x && row_ptr && dst_sorted && attr_sorted && order && weights && node_ws && edge_ws && heu_out,
+                                   int n_instances, float* node_ws, float* edge_ws, float* heu_out, float* dense_out,
+                                   float dense_eps, void* stream) {
+    DACO_CHECK_ARG(x && row_ptr && dst_sorted && attr_sorted && order && weights && node_ws && edge_ws && (heu_out || dense_out),
                    "deepaco_gnn_forward: NULL argument");
     DACO_CHECK_ARG(n_nodes >= 1 && n_edges >= 1 && feats >= 1 && feats <= 8 && n_instances >= 1, "deepaco_gnn_forward: bad sizes");
-    GnnParams p{x, row_ptr, dst_sorted, attr_sorted, order, weights, node_ws, edge_ws, heu_out, n_nodes, n_edges, feats};
+    GnnParams p{x, row_ptr, dst_sorted, attr_sorted, order, weights, node_ws, edge_ws, heu_out, dense_out, dense_eps, n_nodes, n_edges, feats};
     const size_t smem = ((size_t)2 * kLayerFloats + 2 * (U * U + U) + U + 1 + (size_t)U * feats + 3 * U) * 4 + 64;
     DACO_CHECK_CUDA(cudaFuncSetAttribute(gnn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = n_edges >= 512 ? 512 : ((n_edges + 127) / 128) * 128;

@@ -15,17 +15,12 @@ def tsp_heuristic(coords, dist, k_sparse):
     B, n = dist.shape[0], dist.shape[1]
     try:
         from .tsp.net import Net, load_npz_state_dict
-        from .tsp.utils import gen_pyg_data
         wpath = os.path.join(_ROOT, "tests", "golden", f"weights_tsp{n}.npz")
         if os.path.exists(wpath):
             net = Net().to(dist.device)
             net.load_state_dict(load_npz_state_dict(wpath, dist.device))
             net.eval()
-            out = torch.empty_like(dist)
-            with torch.no_grad():
-                for b in range(B):
-                    pyg, _ = gen_pyg_data(coords[b], k_sparse)
-                    out[b] = net.reshape(pyg, net(pyg)) + 1e-10
+            out = net.heuristic_matrices(coords, dist, k_sparse, 1e-10)
             return out, f"Net(pretrained tsp{n} weights) on k={k_sparse} graph + 1e-10"
     except ImportError:
         pass

@@ -119,28 +119,55 @@ def csr_by_source(edge_index, n_nodes):
     return row_ptr, order.to(torch.int32)
 
 
-def gnn_forward(weights, feats, x, edge_index, edge_attr):
-    """deepaco_gnn_forward for one graph or a batch ([B, ...] tensors with identical n and E)."""
+def _launch_gnn(weights, feats, xin, row_ptr, dst_s, attr_s, order, want_vec, dense_eps):
+    B, n = xin.shape[0], xin.shape[1]
+    E = dst_s.shape[1]
+    dev = xin.device
+    node_ws = torch.empty((B, n, 6 * UNITS), dtype=torch.float32, device=dev)
+    edge_ws = torch.empty((B, E, UNITS), dtype=torch.float32, device=dev)
+    out = torch.empty((B, E), dtype=torch.float32, device=dev) if want_vec else None
+    dense = torch.empty((B, n, n), dtype=torch.float32, device=dev) if dense_eps is not None else None
+    with torch.cuda.device(dev):
+        check(lib().deepaco_gnn_forward(ptr(xin), ptr(row_ptr), ptr(dst_s), ptr(attr_s), ptr(order), ptr(weights), n, E, feats,
+                                        B, ptr(node_ws), ptr(edge_ws), ptr(out), ptr(dense),
+                                        float(dense_eps if dense_eps is not None else 0.0), stream_ptr(dev)), "deepaco_gnn_forward")
+    return out, dense
+
+
+def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None):
+    """deepaco_gnn_forward for one graph or a batch ([B, ...] tensors with identical n and E).
+    Returns the edge vector; with dense_eps also the dense heuristic matrix Net.reshape(...) + dense_eps."""
     batched = x.dim() == 3
     if not batched:
         x, edge_index, edge_attr = x[None], edge_index[None], edge_attr[None]
     B, n = x.shape[0], x.shape[1]
     E = edge_index.shape[-1]
-    dev = x.device
     _lib.require_cuda(x, "pyg.x")
     rps, orders = zip(*(csr_by_source(edge_index[b], n) for b in range(B)))
     row_ptr, order = torch.stack(rps).contiguous(), torch.stack(orders).contiguous()
     ol = order.long()
     dst_s = torch.gather(edge_index[:, 1], 1, ol).to(torch.int32).contiguous()
     attr_s = torch.gather(edge_attr.reshape(B, E).to(torch.float32), 1, ol).contiguous()
-    xin = x.to(torch.float32).contiguous()
-    node_ws = torch.empty((B, n, 6 * UNITS), dtype=torch.float32, device=dev)
-    edge_ws = torch.empty((B, E, UNITS), dtype=torch.float32, device=dev)
-    out = torch.empty((B, E), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        check(lib().deepaco_gnn_forward(ptr(xin), ptr(row_ptr), ptr(dst_s), ptr(attr_s), ptr(order), ptr(weights), n, E, feats,
-                                        B, ptr(node_ws), ptr(edge_ws), ptr(out), stream_ptr(dev)), "deepaco_gnn_forward")
-    return out if batched else out[0]
+    out, dense = _launch_gnn(weights, feats, x.to(torch.float32).contiguous(), row_ptr, dst_s, attr_s, order, True, dense_eps)
+    if dense_eps is None:
+        return out if batched else out[0]
+    return (out, dense) if batched else (out[0], dense[0])
+
+
+def knn_heuristic_matrices(weights, feats, node_features, distances, k_sparse, eps=1e-10):
+    """Batched instance -> graph -> network -> dense heuristic front end for k-nearest-neighbour TSP graphs
+    (tsp/utils.py:16-36 + tsp/net.py:84-102 + the `+ EPS` of tsp/test.ipynb cell 1) without any per-instance
+    Python: node_features [B, n, feats], distances [B, n, n] -> heuristic [B, n, n]."""
+    B, n = distances.shape[0], distances.shape[1]
+    dev = distances.device
+    near_d, near_i = torch.topk(distances, k=k_sparse, dim=2, largest=False)       # sorted by source, constant degree
+    E = n * k_sparse
+    row_ptr = (torch.arange(n + 1, device=dev, dtype=torch.int32) * k_sparse).expand(B, n + 1).contiguous()
+    order = torch.arange(E, device=dev, dtype=torch.int32).expand(B, E).contiguous()
+    _, dense = _launch_gnn(weights, feats, node_features.to(torch.float32).contiguous(), row_ptr,
+                           near_i.reshape(B, E).to(torch.int32).contiguous(), near_d.reshape(B, E).to(torch.float32).contiguous(),
+                           order, False, eps)
+    return dense
 
 
 class Net(nn.Module):
@@ -167,6 +194,11 @@ class Net(nn.Module):
         if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             return self.par_net_heu(self.emb_net(x, edge_index, edge_attr))
         return gnn_forward(self._weights(), self.FEATS, x, edge_index, edge_attr)
+
+    @torch.no_grad()
+    def heuristic_matrices(self, node_features, distances, k_sparse, eps=1e-10):
+        """[B, n, n] heuristic matrices of a batch of k-NN TSP instances in one launch (eval mode)."""
+        return knn_heuristic_matrices(self._weights(), self.FEATS, node_features, distances, k_sparse, eps)
 
     def freeze_gnn(self):
         for p in self.emb_net.parameters():

@@ -156,11 +156,14 @@ int deepaco_tours_to_paths(const uint16_t* tours, int64_t* paths, int n, int n_a
  * dst_sorted int32 [B][E], attr_sorted f32 [B][E], order int32 [B][E] (original edge id, used to write
  * heu_out[b][order[e]]).  x: node features f32 [B][n][feats].  weights: packed fp32 (layout in
  * deepaco_b200/net.py:pack_weights; deepaco_gnn_weight_count(feats) values).  node_ws f32 [B][n][192] and
- * edge_ws f32 [B][E][32] are scratch.  heu_out f32 [B][E] = Net.forward(pyg) per original edge. */
+ * edge_ws f32 [B][E][32] are scratch.  heu_out f32 [B][E] = Net.forward(pyg) per original edge (may be NULL).
+ * dense_out (optional f32 [B][n][n]) = Net.reshape(pyg, heu) + dense_eps, i.e. the heuristic matrix the drivers
+ * hand to ACO (tsp/test.ipynb cell 1), written by the same launch. */
 int64_t deepaco_gnn_weight_count(int feats);
 int deepaco_gnn_forward(const float* x, const int32_t* row_ptr, const int32_t* dst_sorted, const float* attr_sorted,
                         const int32_t* order, const float* weights, int n_nodes, int n_edges, int feats,
-                        int n_instances, float* node_ws, float* edge_ws, float* heu_out, void* stream);
+                        int n_instances, float* node_ws, float* edge_ws, float* heu_out, float* dense_out,
+                        float dense_eps, void* stream);
 
 /* ---- CVRP (cvrp/aco.py:106-205, adaptive = False) ----------------------------------------------
  * Node 0 is the depot; n_nodes = customers + 1; demand fp32 [B][n_nodes] (demand[0] = 0).

@@ -71,3 +71,20 @@ def test_batched_forward_equals_single():
     for b in range(6):
         with torch.no_grad():
             assert torch.equal(out[b], net(graphs[b]))
+
+
+def test_batched_front_end_equals_per_instance_path():
+    """coords -> kNN graph -> Net -> dense heuristic for a whole batch in one launch == the per-instance
+    gen_pyg_data / Net.forward / Net.reshape / + EPS sequence of the reference drivers."""
+    from deepaco_b200.tsp.net import Net
+    from deepaco_b200.tsp.utils import gen_distance_matrix, gen_pyg_data
+    net = _load(Net, "weights_tsp100")
+    torch.manual_seed(9)
+    coords = torch.rand(5, 100, 2, device=DEV)
+    dist = torch.stack([gen_distance_matrix(c) for c in coords])
+    dense = net.heuristic_matrices(coords, dist, 20)
+    for b in range(5):
+        pyg, _ = gen_pyg_data(coords[b], 20)
+        with torch.no_grad():
+            want = net.reshape(pyg, net(pyg)) + 1e-10
+        assert torch.equal(dense[b], want)
