@@ -214,6 +214,20 @@ def main():
     tours_per_step = B * N_ANTS * world
     value = tours_per_step * K / (total_ms * 1e-3)
 
+    # ---- the same iteration for ONE colony (512 ants): latency-bound view of the workload, reported beside `value`
+    r1 = E.TspRunner(dist[:1], heu[:1], ph0[:1], N_ANTS)
+    for _ in range(W):
+        r1.run(1, seed, it * inc)
+        it += 1
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    r1.run(K, seed, it * inc)
+    s1.record()
+    torch.cuda.synchronize()
+    it += K
+    single_ms = s0.elapsed_time(s1) / K
+
     # ---- end to end through the host-buffer C-ABI entry (pinned matrices in, results out)
     dist_h, heu_h = dist.cpu().pin_memory(), heu.cpu().pin_memory()
     ph_h = torch.ones_like(dist_h).pin_memory()
@@ -271,6 +285,8 @@ def main():
                      "note": "matrices are L2/SMEM resident: a throughput-normalised figure, not DRAM utilisation"},
         "e2e": {"value": e2e_value, "unit": "ant-tours/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "deepaco_tsp_run_host (C ABI, pinned host buffers)", "ms_per_step": float(e2e_ms) / K},
+        "single_colony": {"value": N_ANTS / (single_ms * 1e-3), "unit": "ant-tours/s", "ms_per_iteration": single_ms,
+                          "note": "one colony of 512 ants, K back-to-back iterations in one deepaco_tsp_run call (rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     # best-cost gap vs the reference on this GPU: same torch seed, one colony of the workload, oracle = the
