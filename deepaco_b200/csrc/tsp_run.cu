@@ -150,8 +150,11 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
 // matrices of every colony to the device buffers named in `a`, runs, copies the results back, synchronises.
 // Colonies are independent, so the batch is cut into up to four chunks that alternate between the caller's stream
 // and an internal one: the H2D / D2H copies of one chunk overlap the kernels of the other.
-static cudaStream_t g_aux_stream = nullptr;
-static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+struct AuxStream {   // one per device ordinal, created on first use
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxStream g_aux[64];
 
 extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterations, const float* distances_host,
                                     const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
@@ -159,11 +162,16 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
     DACO_CHECK_ARG(a && distances_host && heuristic_host && pheromone_host && lowest_cost_host && shortest_path_host,
                    "deepaco_tsp_run_host: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (!g_aux_stream) {
-        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking));
-        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    const DeviceInfo* di = device_info();
+    if (!di) return DEEPACO_ENODEV;
+    AuxStream& aux = g_aux[di->device];
+    if (!aux.stream) {
+        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking));
+        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming));
+        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&aux.join, cudaEventDisableTiming));
     }
+    cudaStream_t g_aux_stream = aux.stream;
+    cudaEvent_t g_ev_fork = aux.fork, g_ev_join = aux.join;
     const int B = a->n_colonies, n = a->n, A = a->n_ants;
     const int chunks = B >= 16 ? 4 : 1;
     const size_t mat1 = (size_t)n * n;
