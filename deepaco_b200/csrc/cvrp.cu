@@ -133,6 +133,13 @@ __global__ void __launch_bounds__(256) cvrp_update_kernel(float* __restrict__ ph
 
 }  // namespace deepaco
 
+namespace deepaco {
+__global__ void hadamard3_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        o[i] = __fmul_rn(a[i], b[i]);
+}
+}  // namespace deepaco
+
 using namespace deepaco;
 
 extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristic, const float* demand, float capacity,
@@ -169,10 +176,29 @@ extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristi
         const int w = atoi(e);
         if (w >= 1 && w <= 16) W = w;
     }
-    auto need = [&](int w) { return list_kernel_smem(n_nodes, path_rows, w, true); };
     const size_t cap = (size_t)di->max_smem_optin - 1024;
-    DACO_CHECK_ARG(n_nodes <= 256 && need(W) <= cap, "deepaco_cvrp_sample: n_nodes=%d does not fit the shared-memory kernel (max ~230)", n_nodes);
-    if (total_ants > (long)di->sm_count * 4)
+    const bool global_p = !(n_nodes <= 256 && list_kernel_smem(n_nodes, path_rows, W, true) <= cap);
+    DACO_CHECK_ARG(n_nodes <= 1024, "deepaco_cvrp_sample: n_nodes=%d exceeds the supported maximum of 1024", n_nodes);
+    static float* cvrp_prod_ws = nullptr;
+    static size_t cvrp_prod_ws_bytes = 0;
+    if (global_p) {
+        W = 4;
+        if (heuristic) {   // product once per call into a scratch matrix; rows are then gathered from L2
+            const size_t need_b = (size_t)n_colonies * n_nodes * n_nodes * sizeof(float);
+            if (need_b > cvrp_prod_ws_bytes) {
+                if (cvrp_prod_ws) cudaFree(cvrp_prod_ws);
+                cvrp_prod_ws = nullptr; cvrp_prod_ws_bytes = 0;
+                DACO_CHECK_CUDA(cudaMalloc(&cvrp_prod_ws, need_b));
+                cvrp_prod_ws_bytes = need_b;
+            }
+            const size_t cnt = (size_t)n_colonies * n_nodes * n_nodes;
+            hadamard3_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, cvrp_prod_ws, cnt);
+            DACO_CHECK_LAUNCH();
+            p.ph = cvrp_prod_ws; p.heu = nullptr;
+        }
+    }
+    auto need = [&](int w) { return list_kernel_smem(n_nodes, path_rows, w, true, global_p); };
+    if (!global_p && total_ants > (long)di->sm_count * 4)
         while (W < 16 && (cap / need(W)) * W < 32 && need(W * 2) <= cap) W *= 2;
     DACO_CHECK_CUDA(cudaMemsetAsync(tmax, 0, sizeof(int32_t) * n_colonies, st));
     dim3 grid((n_ants + W - 1) / W, n_colonies);
@@ -186,19 +212,24 @@ extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristi
         DACO_CHECK_LAUNCH();                                                                                       \
         return DEEPACO_OK;                                                                                         \
     } while (0)
-#define DACO_LIST(E)                                                              \
-    do {                                                                          \
-        if (noise) {                                                              \
-            if (log_probs) DACO_LAUNCH1((aco_list_kernel<E, true, true, true>));  \
-            DACO_LAUNCH1((aco_list_kernel<E, true, false, true>));                \
-        }                                                                         \
-        if (log_probs) DACO_LAUNCH1((aco_list_kernel<E, true, true, false>));     \
-        DACO_LAUNCH1((aco_list_kernel<E, true, false, false>));                   \
+#define DACO_LIST(E, G)                                                              \
+    do {                                                                             \
+        if (noise) {                                                                 \
+            if (log_probs) DACO_LAUNCH1((aco_list_kernel<E, true, true, true, G>));  \
+            DACO_LAUNCH1((aco_list_kernel<E, true, false, true, G>));                \
+        }                                                                            \
+        if (log_probs) DACO_LAUNCH1((aco_list_kernel<E, true, true, false, G>));     \
+        DACO_LAUNCH1((aco_list_kernel<E, true, false, false, G>));                   \
     } while (0)
-    if (epl <= 1) DACO_LIST(1);
-    if (epl <= 2) DACO_LIST(2);
-    if (epl <= 4) DACO_LIST(4);
-    DACO_LIST(8);
+    if (global_p) {
+        if (epl <= 8) DACO_LIST(8, true);
+        if (epl <= 16) DACO_LIST(16, true);
+        DACO_LIST(32, true);
+    }
+    if (epl <= 1) DACO_LIST(1, false);
+    if (epl <= 2) DACO_LIST(2, false);
+    if (epl <= 4) DACO_LIST(4, false);
+    DACO_LIST(8, false);
 #undef DACO_LAUNCH1
 #undef DACO_LIST
 }
@@ -247,10 +278,7 @@ int best_launch(const float* costs, const uint16_t* tours, const float* ph, int 
                 float* lowest, int64_t* shortest, float* ph_max, float* scale, const int32_t* tmax, int32_t* shortest_rows,
                 cudaStream_t st);
 
-__global__ void hadamard3_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        o[i] = __fmul_rn(a[i], b[i]);
-}
+
 // the reference draws one [A, N] exponential_ per construction step until the slowest ant is done: the next
 // iteration's Philox offset is data dependent, so it is advanced on the device
 __global__ void advance_offsets_kernel(uint64_t* offsets, const int32_t* tmax, uint64_t step_increment, int B) {

@@ -74,8 +74,10 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
     return v;
 }
 
-template <int EPL, bool CVRP, bool WANT_LOGP, bool EXT_NOISE>
-__global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant__ ListParams p) {
+// GLOBAL_P: the product matrix stays in global memory (L2-resident) instead of shared memory -- colonies with more
+// than ~230 nodes; `p.ph` must then already be the product (p.heu == nullptr).
+template <int EPL, bool CVRP, bool WANT_LOGP, bool EXT_NOISE, bool GLOBAL_P = false>
+__global__ void __launch_bounds__(GLOBAL_P ? 256 : 512, GLOBAL_P ? 1 : 2) aco_list_kernel(const __grid_constant__ ListParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const int n = p.n, R = p.rows;
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
     const int a0 = blockIdx.x * W;
     const int a = a0 + warp;
     // shared layout: P [n*n f32] | demand [n f32] (CVRP) | tours [W][R] u16 | cand [W][n] u16 | alive [W][32] u32
-    float* Psm = reinterpret_cast<float*>(smem);
-    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
+    const size_t pbytes = GLOBAL_P ? 0 : ((((size_t)n * n * 4) + 15) & ~(size_t)15);
+    const float* Psm = GLOBAL_P ? p.ph + (size_t)b * n * n : reinterpret_cast<const float*>(smem);
     const size_t dbytes = CVRP ? ((((size_t)n * 4) + 15) & ~(size_t)15) : 0;
     float* dem = reinterpret_cast<float*>(smem + pbytes);
     uint16_t* tour_all = reinterpret_cast<uint16_t*>(smem + pbytes + dbytes);
@@ -94,14 +96,15 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
     uint32_t* alive_all = reinterpret_cast<uint32_t*>(smem + pbytes + dbytes + (((size_t)W * (R + n) * 2 + 15) & ~(size_t)15));
     uint16_t* tour_sm = tour_all + (size_t)warp * R;
     uint32_t* alive = alive_all + warp * 32;
-    const uint32_t P_addr = pin_u32(smem_u32(Psm));
+    const uint32_t P_addr = GLOBAL_P ? 0u : pin_u32(smem_u32(smem));
     const uint32_t dem_addr = pin_u32(smem_u32(dem));
     const uint32_t cand_addr = pin_u32(smem_u32(cand_all + (size_t)warp * n));
     const uint32_t tour_addr = pin_u32(smem_u32(tour_sm));
 
     if (CVRP)
         for (int i = tid; i < n; i += nthreads) dem[i] = p.demand[(size_t)b * n + i];
-    stage_product(Psm, p.ph, p.heu, n, b, &bar);   // ends with __syncthreads()
+    if (GLOBAL_P) __syncthreads();
+    else stage_product(reinterpret_cast<float*>(smem), p.ph, p.heu, n, b, &bar);   // ends with __syncthreads()
 
     if (a < p.A) {
         const uint64_t seed = p.seed;
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(512, 2) aco_list_kernel(const __grid_constant_
                 bool ok = s < cnt;
                 if (CVRP && ok) ok = (s == 0) ? depot_ok : !(lds_f32(dem_addr + 4 * cj[k]) > remaining);
                 okk[k] = ok;
-                const float x = ok ? lds_f32(row_addr + 4 * cj[k]) : 0.f;
+                const float x = ok ? (GLOBAL_P ? __ldg(Psm + (size_t)cur * n + cj[k]) : lds_f32(row_addr + 4 * cj[k])) : 0.f;
                 const float rr = EXT_NOISE ? (ok ? rcp_approx(nz[cj[k]]) : 0.f) : r[k];
                 const float A = __fmul_rn(x, rr);
                 if (A > bestA) {
@@ -498,8 +501,8 @@ inline size_t knn_kernel_smem(int n, int W) {
     return (size_t)kKnnWarpBytes * (W <= 8 ? 8 : 16) + (size_t)n * 32 + ((((size_t)n * 4) + 15) & ~(size_t)15) + ((((size_t)n * n * 4) + 15) & ~(size_t)15);
 }
 
-inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp) {
-    const size_t pbytes = (((size_t)n * n * 4) + 15) & ~(size_t)15;
+inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp, bool global_p = false) {
+    const size_t pbytes = global_p ? 0 : ((((size_t)n * n * 4) + 15) & ~(size_t)15);
     const size_t dbytes = cvrp ? ((((size_t)n * 4) + 15) & ~(size_t)15) : 0;
     return pbytes + dbytes + (((size_t)W * (rows + n) * 2 + 15) & ~(size_t)15) + (size_t)W * 128;
 }

@@ -316,6 +316,48 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
 #undef DACO_LIST
     }
 
+    // ---- list kernel with the product in global memory (n too large for shared memory)
+    if (!force_dense && dn.single && (uint64_t)n_ants_total * n < (1ull << 32) && n - 1 <= 32 * 32) {
+        const float* prod = pheromone;
+        if (heuristic) {   // product once per call into a scratch matrix, rows then come from L2
+            const size_t need = (size_t)n_colonies * n * n * sizeof(float);
+            if (need > g_prod_ws_bytes) {
+                if (g_prod_ws) cudaFree(g_prod_ws);
+                g_prod_ws = nullptr; g_prod_ws_bytes = 0;
+                DACO_CHECK_CUDA(cudaMalloc(&g_prod_ws, need));
+                g_prod_ws_bytes = need;
+            }
+            const size_t cnt = (size_t)n_colonies * n * n;
+            hadamard_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, g_prod_ws, cnt);
+            DACO_CHECK_LAUNCH();
+            prod = g_prod_ws;
+        }
+        ListParams q{};
+        q.ph = prod; q.heu = nullptr; q.n = n; q.A = n_ants; q.B = n_colonies; q.rows = n;
+        q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.offsets = offsets;
+        q.keys.init(seed);
+        q.ant_base = ant_base;
+        q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
+        q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
+        q.start_increment = p.start_increment; q.step_increment = p.step_increment;
+        const int Wg = 4;
+        const size_t sm = list_kernel_smem(n, n, Wg, false, true);
+        const int epl = (n - 1 + 31) / 32;
+#define DACO_GLIST(E)                                                                                               \
+        do {                                                                                                        \
+            if (noise) {                                                                                            \
+                if (log_probs) return launch_kernel(aco_list_kernel<E, false, true, true, true>, q, Wg, sm, st);    \
+                return launch_kernel(aco_list_kernel<E, false, false, true, true>, q, Wg, sm, st);                  \
+            }                                                                                                       \
+            if (log_probs) return launch_kernel(aco_list_kernel<E, false, true, false, true>, q, Wg, sm, st);       \
+            return launch_kernel(aco_list_kernel<E, false, false, false, true>, q, Wg, sm, st);                     \
+        } while (0)
+        if (epl <= 8) DACO_GLIST(8);
+        if (epl <= 16) DACO_GLIST(16);
+        DACO_GLIST(32);
+#undef DACO_GLIST
+    }
+
     // ---- dense exact kernel
     int epl_needed = vec ? 4 * ((n + 127) / 128) : (n + bw - 1) / bw;
     int epl = vec ? 8 : 1;

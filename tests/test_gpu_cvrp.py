@@ -50,7 +50,7 @@ def _instance(n, seed=123456, gnn_like=False):
 
 
 @pytest.mark.parametrize("n,n_ants,gnn_like", [(20, 16, False), (20, 20, True), (50, 64, True), (100, 512, True),
-                                               (100, 64, False), (31, 33, True), (200, 64, True)])
+                                               (100, 64, False), (31, 33, True), (200, 64, True), (300, 16, True), (500, 8, False)])
 def test_stream_parity_same_device(n, n_ants, gnn_like):
     from deepaco_b200 import _engine as E
     demand, dist, heu = _instance(n, gnn_like=gnn_like)
