@@ -104,6 +104,22 @@ def tsp_sample_shard(pheromone, heuristic, n_ants_local, ant_base, n_ants_total,
     return tours
 
 
+def tsp_sample_shard_p2p(pheromone, heuristic, n_ants_local, ant_base, n_ants_total, peer_ptrs, *, start_node=-1,
+                         double_norm=False, seed=0, offset=0, offsets=None, knn=None):
+    """deepaco_tsp_sample_shard_p2p: tours of ants [ant_base, ant_base + n_ants_local) are written by the kernel
+    into every rank's [B, n_ants_total, n] uint16 buffer (`peer_ptrs` = peer-mapped device addresses)."""
+    pheromone = f32c(require_cuda(pheromone, "pheromone"))
+    B, n = _colonies(pheromone)
+    dev = pheromone.device
+    heuristic = None if heuristic is None else f32c(require_cuda(heuristic, "heuristic"))
+    arr = (C.c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_sample_shard_p2p(ptr(pheromone), ptr(heuristic), n, n_ants_local, B, int(start_node),
+                                                 int(double_norm), int(seed), int(offset), ptr(_offsets(offsets, B, dev)),
+                                                 ptr(knn), int(ant_base), int(n_ants_total), C.cast(arr, C.c_void_p),
+                                                 len(peer_ptrs), stream_ptr(dev)), "deepaco_tsp_sample_shard_p2p")
+
+
 def tsp_sample_offset_increment(n, n_ants, start_node=-1) -> int:
     return int(lib().deepaco_tsp_sample_offset_increment(n, n_ants, int(start_node)))
 

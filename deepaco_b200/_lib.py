@@ -24,6 +24,7 @@ _SIGNATURES = {
     "deepaco_aten_sum_plan": (_i32, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "deepaco_tsp_sample": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "deepaco_tsp_sample_shard": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "deepaco_tsp_sample_shard_p2p": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "deepaco_tsp_sample_offset_increment": (_u64, [_i32, _i32, _i32]),
     "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),

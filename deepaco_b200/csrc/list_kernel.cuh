@@ -35,6 +35,9 @@ struct ListParams {
     const float* dist;      // optional fused epilogue (kNN kernel): distances [B][n][n] ->
     float* costs;           //   costs [B][A] in ATen summation order and
     uint32_t* nbr;          //   neighbour table [B][n][A] (pred << 16 | succ), as deepaco_tsp_cost would produce
+    uint16_t* peer_tours[8]; // fused exchange (ant sharding over NVLink): every finished tour is stored straight into the
+    int n_peers;             //   [B][A_total][n] tour buffer of each of the n_peers GPUs (peer-mapped pointers, incl. our own)
+    int A_total;
     int ant_base;           // index of this launch's ant 0 in the colony (ant sharding across GPUs); Philox uses global indices
     const int64_t* start;   // [B][A] or null
     int64_t* paths;         // [B][rows][A] or null
@@ -480,8 +483,12 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
             ctr += ctr_step;
         }
     }
-    {   // warp-local, coalesced: this ant's row of the compact layout
+    if (p.tours) {   // warp-local, coalesced: this ant's row of the compact layout
         uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
+        for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
+    }
+    for (int r = 0; r < p.n_peers; ++r) {   // fused exchange: the finished tour goes straight to every GPU's buffer
+        uint16_t* out = p.peer_tours[r] + ((size_t)b * p.A_total + p.ant_base + a) * n;   // while other ants still build
         for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
     }
     if (FUSE_COST) {   // fused ACO.gen_path_costs + neighbour table (same arithmetic as tsp_cost_kernel)

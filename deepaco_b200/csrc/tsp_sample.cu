@@ -211,7 +211,7 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
                            const uint64_t* offsets, const float* noise, const int64_t* start, int64_t* paths,
                            float* log_probs, uint16_t* tours, const uint8_t* knn, int ant_base, int n_ants_total, void* stream,
                            const float* fuse_dist = nullptr, float* fuse_costs = nullptr, uint32_t* fuse_nbr = nullptr,
-                           int* fused_out = nullptr) {
+                           int* fused_out = nullptr, const uint64_t* peer_tours = nullptr, int n_peers = 0) {
     const DeviceInfo* di = device_info();
     if (fused_out) *fused_out = 0;
     if (!di) return DEEPACO_ENODEV;
@@ -266,10 +266,13 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.offsets = offsets;
         q.keys.init(seed);
         q.ant_base = ant_base;
+        q.A_total = n_ants_total;
+        q.n_peers = n_peers;
+        for (int r = 0; r < n_peers && r < 8; ++r) q.peer_tours[r] = reinterpret_cast<uint16_t*>(peer_tours[r]);
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
-        if (knn && !noise && !log_probs && !paths && !start && tours && n > 32 && n <= 256 && !getenv("DEEPACO_TSP_NO_KNN")) {
+        if (knn && !noise && !log_probs && !paths && !start && (tours || n_peers) && n > 32 && n <= 256 && !getenv("DEEPACO_TSP_NO_KNN")) {
             // sparse product: one candidate per lane (kNN kernel)
             int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : 8;
             if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) Wk = w; }
@@ -337,6 +340,9 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         q.start_node = start_node; q.double_norm = double_norm; q.seed = seed; q.offset = offset; q.offsets = offsets;
         q.keys.init(seed);
         q.ant_base = ant_base;
+        q.A_total = n_ants_total;
+        q.n_peers = n_peers;
+        for (int r = 0; r < n_peers && r < 8; ++r) q.peer_tours[r] = reinterpret_cast<uint16_t*>(peer_tours[r]);
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
@@ -426,3 +432,18 @@ int tsp_sample_fused(const float* product, int n, int n_ants, int n_colonies, in
                            nullptr, nullptr, tours, knn, 0, n_ants, st, dist, costs, nbr, fused);
 }
 }  // namespace deepaco
+
+// Ant-sharded construction with the exchange fused into the kernel: each finished tour is written by the building
+// warp into the [B][n_ants_total][n] uint16 tour buffer of EVERY rank (`peer_tours_host[r]` = peer-mapped device
+// pointer of rank r's buffer, r < n_peers <= 8, our own included), so the transfer over NVLink overlaps the
+// construction of the remaining ants.  The caller then needs only a barrier, no collective.
+extern "C" int deepaco_tsp_sample_shard_p2p(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                                            int start_node, int double_norm, uint64_t seed, uint64_t offset,
+                                            const uint64_t* offsets, const uint8_t* knn, int ant_base, int n_ants_total,
+                                            const uint64_t* peer_tours_host, int n_peers, void* stream) {
+    DACO_CHECK_ARG(peer_tours_host && n_peers >= 1 && n_peers <= 8, "deepaco_tsp_sample_shard_p2p: need 1..8 peer buffers");
+    DACO_CHECK_ARG(n <= 256, "deepaco_tsp_sample_shard_p2p: n <= 256 (shared-memory kernels only)");
+    return tsp_sample_impl(pheromone, heuristic, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr,
+                           nullptr, nullptr, nullptr, nullptr, knn, ant_base, n_ants_total, stream, nullptr, nullptr, nullptr,
+                           nullptr, peer_tours_host, n_peers);
+}

@@ -66,6 +66,11 @@ class CudaTspBackend:
         return self.E.tsp_sample_shard(pheromone, self.heuristic, count, a0, n_ants_total, start_node=self.start_node,
                                        double_norm=self.double_norm, seed=seed, offset=offset, knn=self.knn)[0]
 
+    def sample_p2p(self, pheromone, a0, count, n_ants_total, seed, offset, peer_ptrs):
+        self.E.tsp_sample_shard_p2p(pheromone, self.heuristic, count, a0, n_ants_total, peer_ptrs,
+                                    start_node=self.start_node, double_norm=self.double_norm, seed=seed, offset=offset,
+                                    knn=self.knn)
+
     def cost_and_neighbours(self, tours):
         return self.E.tsp_cost(self.distances, tours=tours, want_neighbours=True)
 
@@ -76,10 +81,29 @@ class CudaTspBackend:
         return self.E.tsp_sample_offset_increment(n, n_ants_total, self.start_node)
 
 
-class AntShardedColony:
-    """One TSP colony whose ants are split over the ranks of `group` (see module docstring)."""
+class PeerTourBuffer:
+    """Symmetric-memory tour buffer (`torch.distributed._symmetric_memory`): every rank's [A, n] uint16 buffer is
+    peer-mapped on all ranks (NVLink / NVSwitch), so the sampling kernel of rank r can store its ants' tours into
+    all of them while it is still building the other ants.  `barrier()` (signal pads, no data) then replaces the
+    collective."""
 
-    def __init__(self, backend, pheromone, n_ants, *, decay=0.9, elitist=False, group=None):
+    def __init__(self, n_ants, n, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buf = symm_mem.empty((n_ants, n * 2), dtype=torch.uint8, device=device)     # uint16 tours as bytes
+        self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.tours = self.buf.view(torch.uint16).view(n_ants, n)
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+
+class AntShardedColony:
+    """One TSP colony whose ants are split over the ranks of `group` (see module docstring).
+    exchange='nccl': one all-gather per iteration.  exchange='p2p': the exchange is fused into the sampling kernel
+    (peer stores over NVLink into a symmetric-memory buffer) and only barriers remain."""
+
+    def __init__(self, backend, pheromone, n_ants, *, decay=0.9, elitist=False, group=None, exchange="nccl"):
         self.backend, self.group = backend, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n = pheromone.shape[-1]
@@ -91,6 +115,8 @@ class AntShardedColony:
         self.lowest_cost = torch.tensor(float("inf"), device=pheromone.device)
         self.shortest_path = None
         self.collectives = 0
+        self.exchange = exchange
+        self.peer = PeerTourBuffer(n_ants, self.n, pheromone.device, group) if exchange == "p2p" else None
 
     def _all_gather_tours(self, local):
         mx = max(self.counts)
@@ -105,8 +131,14 @@ class AntShardedColony:
 
     def iterate(self, seed, offset):
         """One ACO iteration (tsp/aco.py:75-90).  Every rank ends with identical state."""
-        local = self.backend.sample(self.pheromone, self.a0, self.count, self.n_ants, seed, offset)
-        tours = self._all_gather_tours(local)
+        if self.peer is not None:
+            self.peer.barrier()      # every rank has finished reading the previous iteration's tours
+            self.backend.sample_p2p(self.pheromone, self.a0, self.count, self.n_ants, seed, offset, self.peer.ptrs)
+            self.peer.barrier()      # every rank's stores have landed everywhere
+            tours = self.peer.tours
+        else:
+            local = self.backend.sample(self.pheromone, self.a0, self.count, self.n_ants, seed, offset)
+            tours = self._all_gather_tours(local)
         costs, nbr = self.backend.cost_and_neighbours(tours)
         best = torch.argmin(costs)
         if costs[best] < self.lowest_cost:

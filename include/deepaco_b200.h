@@ -75,6 +75,14 @@ int deepaco_tsp_sample_shard(const float* pheromone, const float* heuristic, int
                              int64_t* paths, float* log_probs, uint16_t* tours, const uint8_t* knn, int ant_base,
                              int n_ants_total, void* stream);
 
+/* Same, with the multi-GPU exchange fused into the kernel: every finished tour is stored by the building warp into
+ * the uint16 [B][n_ants_total][n] tour buffer of each of the n_peers ranks (peer_tours_host[r] = peer-mapped device
+ * address of rank r's buffer, our own included; n_peers <= 8, n <= 256).  Afterwards only a barrier is needed. */
+int deepaco_tsp_sample_shard_p2p(const float* pheromone, const float* heuristic, int n, int n_ants, int n_colonies,
+                                 int start_node, int double_norm, uint64_t seed, uint64_t offset, const uint64_t* offsets,
+                                 const uint8_t* knn, int ant_base, int n_ants_total, const uint64_t* peer_tours_host,
+                                 int n_peers, void* stream);
+
 /* ---- tour cost  (ACO.gen_path_costs, tsp/aco.py:120-132) --------------------------------------
  * costs[b][a] = sum_k dist[u_k][u_{k-1}] in ATen's summation order.  Input tours either as
  * `paths` (int64 [B][n][A]) or `tours` (u16 [B][A][n]); exactly one non-NULL.  `costs` may be NULL.  Optionally emits

@@ -26,14 +26,24 @@ d[torch.arange(n), torch.arange(n)] = 1e9
 _, idx = torch.topk(d, 20, dim=1, largest=False)
 heu = torch.full_like(d, 1e-10).scatter_(1, idx, (torch.rand((n, 20), generator=g) * 0.9 + 0.05).to(dev))
 
-col = AntShardedColony(CudaTspBackend(d, heu), torch.ones(n, n, device=dev), A)
-col.run(2, seed=11, offset=0)                       # warm-up (NCCL channels, kernels)
-col = AntShardedColony(CudaTspBackend(d, heu), torch.ones(n, n, device=dev), A)
-dist.barrier(); torch.cuda.synchronize()
-t0 = time.perf_counter()
-low = col.run(T, seed=11, offset=0)
-torch.cuda.synchronize(); dist.barrier()
-dt = (time.perf_counter() - t0) / T
+results = {}
+for mode in ("nccl", "p2p"):
+    try:
+        col = AntShardedColony(CudaTspBackend(d, heu), torch.ones(n, n, device=dev), A, exchange=mode)
+        col.run(3, seed=11, offset=0)                       # warm-up (channels, kernels)
+        col = AntShardedColony(CudaTspBackend(d, heu), torch.ones(n, n, device=dev), A, exchange=mode)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        low = col.run(T, seed=11, offset=0)
+        torch.cuda.synchronize(); dist.barrier()
+        results[mode] = (col, low, (time.perf_counter() - t0) / T)
+    except Exception as exc:                                # e.g. no P2P / symmetric memory on this box
+        if rank == 0:
+            print({"exchange": mode, "error": repr(exc)[:300]})
+if rank == 0:
+    for mode, (col, low, dt) in results.items():
+        results[mode] = (col, low, dt)
+col, low, dt = results.get("p2p", results.get("nccl"))
 if rank == 0:
     from deepaco_b200.tsp.aco import ACO
     from oracle import aco_torch as O
@@ -43,6 +53,9 @@ if rank == 0:
     torch.manual_seed(11)
     ref = O.TspColony(d, A, heuristic=heu)
     ref.run(T)
+    for mode, (c2, l2, dt2) in results.items():
+        print({"exchange": mode, "ms_per_iteration": dt2 * 1e3, "collectives_per_iteration": c2.collectives / T,
+               "identical_to_single_gpu": bool(torch.equal(c2.pheromone, single.pheromone))})
     print({"world": world, "collectives_per_iteration": col.collectives / T, "ms_per_iteration": dt * 1e3,
            "identical_to_single_gpu": bool(torch.equal(col.pheromone, single.pheromone)),
            "identical_to_reference_ops": bool(torch.equal(col.pheromone, ref.pheromone)),
