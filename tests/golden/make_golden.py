@@ -248,3 +248,14 @@ if __name__ == "__main__":
     gen_tsp()
     gen_tsp_nls()
     gen_cvrp()
+
+
+def gen_val_fixture():
+    """data/tsp/valDataset-100.pt (100 instances, float32 [100, 100, 2]) as a fixture for the quality check of
+    tools/quality_tsp100.py against the reference's own published validation numbers (tsp/train.ipynb cell 7)."""
+    v = torch.load(os.path.join(REF, "data/tsp/valDataset-100.pt"))
+    save("val_tsp100_coords", coords=v.to(torch.float32))
+
+
+if __name__ == "__main__":
+    gen_val_fixture()
