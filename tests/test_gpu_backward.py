@@ -72,3 +72,52 @@ def test_cvrp_sample_backward_matches_autograd():
     (w * logp.sum(0)).sum().backward()
     assert torch.equal(logp.detach(), logp_ref.detach())
     assert torch.allclose(h.grad, h_ref.grad, rtol=2e-4, atol=1e-6 * float(h_ref.grad.abs().max()))
+
+
+def test_train_instance_parameter_gradients_match_reference_pipeline():
+    """One REINFORCE step as in tsp/train.ipynb cell 1 (`train_instance`): Net in train mode -> heuristic matrix ->
+    ACO.sample() -> loss.backward().  The gradients of every network parameter equal those of the same pipeline with
+    the reference's sampling ops (oracle) in place of the kernels."""
+    import copy
+    from deepaco_b200.tsp.aco import ACO
+    from deepaco_b200.tsp.net import Net
+    from deepaco_b200.tsp.utils import gen_pyg_data
+    n, A, EPS = 40, 16, 1e-10
+    torch.manual_seed(21)
+    net = Net().to(DEV).train()
+    ref_net = copy.deepcopy(net)
+    coords = torch.rand(n, 2, device=DEV)
+    pyg, distances = gen_pyg_data(coords, k_sparse=8)
+
+    def loss_of(model, sampler):
+        heu_vec = model(pyg)
+        heu_mat = model.reshape(pyg, heu_vec) + EPS
+        costs, log_probs = sampler(heu_mat)
+        baseline = costs.mean()
+        return torch.sum((costs - baseline) * log_probs.sum(dim=0)) / A
+
+    def mine(heu_mat):
+        torch.manual_seed(77)
+        return ACO(n_ants=A, heuristic=heu_mat, distances=distances, device=DEV).sample()
+
+    def reference(heu_mat):
+        torch.manual_seed(77)
+        paths, logp = O.tsp_gen_path(torch.ones_like(distances), heu_mat, A, require_prob=True)
+        return O.tsp_path_costs(distances, paths), logp
+
+    l1 = loss_of(net, mine)
+    l1.backward()
+    l2 = loss_of(ref_net, reference)
+    l2.backward()
+    assert torch.allclose(l1, l2, rtol=1e-5)
+    checked = 0
+    for (name, p1), (_, p2) in zip(net.named_parameters(), ref_net.named_parameters()):
+        if p2.grad is None:
+            assert p1.grad is None
+            continue
+        scale = float(p2.grad.abs().max()) + 1e-12
+        assert torch.allclose(p1.grad, p2.grad, rtol=5e-3, atol=2e-4 * scale), name
+        checked += 1
+    assert checked > 50
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
+    opt.step()                                              # the optimiser step of train_instance runs
