@@ -208,6 +208,14 @@ class TspRunner:
         self.start_node, self.double_norm = int(start_node), bool(double_norm)
         self.increment = tsp_sample_offset_increment(self.n, self.n_ants, self.start_node)
         self.knn = sparse_candidates(self.heuristic) if use_knn else None
+        # optional local search between construction and cost (tsp_nls): 0 none, 1 2-opt, 2 NLS
+        self.local_search, self.ls_max_iterations, self.T_nls, self.T_p, self.heuristic_dist = 0, 0, 10, 20, None
+
+    def set_local_search(self, mode, max_iterations, heuristic_dist=None, T_nls=10, T_p=20):
+        self.local_search = {None: 0, "2opt": 1, "nls": 2}[mode]
+        self.ls_max_iterations, self.T_nls, self.T_p = int(max_iterations), int(T_nls), int(T_p)
+        if self.local_search == 2:
+            self.heuristic_dist = f32c(require_cuda(heuristic_dist, "heuristic_dist")).reshape(self.B, self.n, self.n)
 
     def _args(self, seed, offset, offs, events=None):
         ev0 = ev1 = None
@@ -220,6 +228,7 @@ class TspRunner:
                                ptr(self.pheromone), ptr(self.heuristic), ptr(self.distances), ptr(self.product),
                                int(self.product_valid), ptr(self.tours), ptr(self.costs), ptr(self.neighbours),
                                ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.ph_max), ptr(self.scale), ptr(self.knn),
+                               self.local_search, self.ls_max_iterations, self.T_nls, self.T_p, ptr(self.heuristic_dist),
                                ev0, ev1)
 
     def run(self, n_iterations, seed, offset=0, offsets=None, sample_events=None):

@@ -53,7 +53,8 @@ class TspRunArgs(C.Structure):
                 ("seed", _u64), ("offset", _u64), ("offsets", _vp),
                 ("pheromone", _vp), ("heuristic", _vp), ("distances", _vp), ("product", _vp), ("product_valid", _i32),
                 ("tours", _vp), ("costs", _vp), ("neighbours", _vp), ("lowest_cost", _vp), ("shortest_path", _vp),
-                ("ph_max", _vp), ("scale", _vp), ("knn", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
+                ("ph_max", _vp), ("scale", _vp), ("knn", _vp), ("local_search", _i32), ("ls_max_iterations", _i32),
+                ("T_nls", _i32), ("T_p", _i32), ("heuristic_dist", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
 
 
 class CvrpRunArgs(C.Structure):

@@ -116,6 +116,8 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
                        a->lowest_cost && a->shortest_path,
                    "deepaco_tsp_run: NULL buffer");
     DACO_CHECK_ARG(!a->min_max || (a->ph_max && a->scale), "deepaco_tsp_run: min_max needs ph_max and scale buffers");
+    DACO_CHECK_ARG(a->local_search >= 0 && a->local_search <= 2 && (a->local_search != 2 || a->heuristic_dist),
+                   "deepaco_tsp_run: bad local_search / missing heuristic_dist");
     cudaStream_t st = (cudaStream_t)stream;
     const int n = a->n, A = a->n_ants, B = a->n_colonies;
     const uint64_t inc = deepaco_tsp_sample_offset_increment(n, A, a->start_node);
@@ -129,9 +131,18 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
         if (a->ev_sample_begin) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_begin, st));
         int fused = 0;
         int rc = tsp_sample_fused(a->product, n, A, B, a->start_node, a->double_norm, a->seed, a->offset + (uint64_t)it * inc,
-                                  a->offsets, a->tours, a->knn, a->distances, a->costs, a->neighbours, &fused, st);
+                                  a->offsets, a->tours, a->knn, a->local_search ? nullptr : a->distances, a->costs, a->neighbours,
+                                  &fused, st);
         if (rc) return rc;
         if (a->ev_sample_end) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_end, st));
+        if (a->local_search == 1) {
+            rc = deepaco_two_opt(a->distances, a->tours, n, A, B, a->ls_max_iterations, nullptr, st);
+            if (rc) return rc;
+        } else if (a->local_search == 2) {
+            rc = deepaco_tsp_nls(a->distances, a->heuristic_dist, a->tours, n, A, B, a->ls_max_iterations, a->T_nls, a->T_p, nullptr,
+                                 nullptr, st);
+            if (rc) return rc;
+        }
         if (!fused) {
             rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, a->neighbours, st);
             if (rc) return rc;
@@ -198,6 +209,7 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
         b.ph_max = a->ph_max ? a->ph_max + b0 : nullptr;
         b.scale = a->scale ? a->scale + b0 : nullptr;
         b.knn = a->knn ? a->knn + (size_t)b0 * n * 32 : nullptr;
+        b.heuristic_dist = a->heuristic_dist ? a->heuristic_dist + b0 * mat1 : nullptr;
         b.ev_sample_begin = b.ev_sample_end = nullptr;
         const size_t bytes = (size_t)nb * mat1 * sizeof(float);
         DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(b.distances), distances_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));

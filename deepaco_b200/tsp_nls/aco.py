@@ -75,33 +75,22 @@ class ACO(_TspACO):
     # ---- run -----------------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, n_iterations, inference=False):
-        '''tsp_nls/aco.py:104-129; returns lowest_cost as a Python float like the reference (:120).'''
-        if self.local_search_type is None:
-            low = super().run(n_iterations)
-            return float(low)
-        for _ in range(n_iterations):
-            ph, heu = self._weights()
-            gen, seed, offset = generator_state(self.device)
-            _, _, tours = E.tsp_sample(ph.detach(), heu.detach(), self.n_ants, start_node=0, double_norm=True, seed=seed,
-                                       offset=offset, want_paths=False, want_tours=True, knn=self._candidates())
-            gen.set_offset(offset + E.tsp_sample_offset_increment(self.problem_size, self.n_ants, 0))
-            if self.local_search_type == "2opt":
-                E.two_opt_(self.distances, tours, self._max_passes(inference))
-            else:
-                E.tsp_nls_(self.distances, self.heuristic_dist, tours, self._max_passes(inference))
-            costs, nbr = E.tsp_cost(self.distances, tours=tours, want_neighbours=True)
-            best = torch.argmin(costs)
-            if float(costs[best]) < float(self._lowest_cost):            # .item() as in the reference (:120)
-                self._shortest_path = tours[best].to(torch.int64)
-                self._lowest_cost = float(costs[best])
-                if self.min_max:
-                    new_max = self.problem_size / self._lowest_cost
-                    if self.max is None:
-                        self._pheromone = self._pheromone * (new_max / self._pheromone.max())
-                    self.max = new_max
-            newph = self._pheromone.detach().to(torch.float32).clone(memory_format=torch.contiguous_format)
-            E.tsp_update_(newph, nbr, costs, decay=self.decay, elitist=self.elitist, min_max=self.min_max,
-                          ph_min=self.min if self.min_max else 0.0, ph_max=self.max if self.min_max else None)
-            self._pheromone = newph
-            self._runner = None
+        '''tsp_nls/aco.py:104-129 on the device: construction, local search (2-opt / NLS), cost, best tracking and
+        pheromone update of every iteration are enqueued without a host round trip (the reference crosses to the CPU
+        for the numba local search each iteration).  Returns lowest_cost as a Python float like the reference (:120).'''
+        if self.alpha != 1 or self.beta != 1:
+            raise NotImplementedError("tsp_nls ACO.run with alpha / beta != 1: use gen_path / local_search / update_pheronome")
+        if self._runner is None:
+            self._runner = self._make_runner()
+        r = self._runner
+        r.set_local_search(self.local_search_type, self._max_passes(inference),
+                           self.heuristic_dist if self.local_search_type == "nls" else None)
+        gen, seed, offset = generator_state(self.device)
+        r.run(n_iterations, seed, offset)
+        gen.set_offset(offset + n_iterations * r.increment)
+        self._pheromone = r.pheromone[0].clone()
+        self._shortest_path = r.shortest_path[0].clone()
+        self._lowest_cost = float(r.lowest_cost[0].item())
+        if self.min_max:
+            self.max = r.ph_max[0].clone()
         return self._lowest_cost

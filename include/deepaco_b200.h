@@ -130,6 +130,10 @@ typedef struct {
     float* ph_max;
     float* scale;
     const uint8_t* knn;    /* optional candidate lists, see deepaco_tsp_sample */
+    int local_search;      /* tsp_nls/aco.py:97-102 between construction and cost: 0 none, 1 2-opt, 2 NLS */
+    int ls_max_iterations; /* 2-opt passes per call (n/4 in training, 10000 at inference) */
+    int T_nls, T_p;        /* NLS rounds / perturbation passes (10 / 20 in the reference) */
+    const float* heuristic_dist; /* NLS only: [B][n][n], 1 / (heuristic / rowmax + 1e-5), tsp_nls/aco.py:230-232 */
     void* ev_sample_begin; /* optional cudaEvent_t recorded before / after each sampling launch (profiling) */
     void* ev_sample_end;
 } deepaco_tsp_run_args;
