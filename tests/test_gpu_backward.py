@@ -111,12 +111,14 @@ def test_train_instance_parameter_gradients_match_reference_pipeline():
     l2.backward()
     assert torch.allclose(l1, l2, rtol=1e-5)
     checked = 0
+    # biases feeding a train-mode BatchNorm have an exactly-zero true gradient (pure rounding noise on both sides):
+    # the absolute tolerance is therefore set from the largest gradient of the whole network
+    gmax = max(float(p.grad.abs().max()) for p in ref_net.parameters() if p.grad is not None)
     for (name, p1), (_, p2) in zip(net.named_parameters(), ref_net.named_parameters()):
         if p2.grad is None:
             assert p1.grad is None
             continue
-        scale = float(p2.grad.abs().max()) + 1e-12
-        assert torch.allclose(p1.grad, p2.grad, rtol=5e-3, atol=2e-4 * scale), name
+        assert torch.allclose(p1.grad, p2.grad, rtol=5e-3, atol=2e-5 * gmax), name
         checked += 1
     assert checked > 50
     opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
