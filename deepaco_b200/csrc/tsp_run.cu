@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "host_util.h"
 
+#include <stdlib.h>
+
 namespace deepaco {
 
 int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants, int n_colonies,
@@ -184,7 +186,8 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
     cudaStream_t g_aux_stream = aux.stream;
     cudaEvent_t g_ev_fork = aux.fork, g_ev_join = aux.join;
     const int B = a->n_colonies, n = a->n, A = a->n_ants;
-    const int chunks = B >= 16 ? 4 : 1;
+    int chunks = B >= 64 ? 8 : (B >= 16 ? 4 : 1);
+    if (const char* e = getenv("DEEPACO_HOST_CHUNKS")) { const int c = atoi(e); if (c >= 1 && c <= B) chunks = c; }
     const size_t mat1 = (size_t)n * n;
     if (chunks > 1) {   // the internal stream starts after everything already queued on the caller's stream
         DACO_CHECK_CUDA(cudaEventRecord(g_ev_fork, st));
