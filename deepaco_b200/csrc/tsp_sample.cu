@@ -280,7 +280,9 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
                 if (total_ants > (long)di->sm_count * 4)
                     while (Wk < 16 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;
                 q.knn = knn;
-                const bool fuse = fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants && getenv("DEEPACO_TSP_FUSE_COST");
+                // small jobs are launch-latency bound: fold cost + neighbour table into the construction kernel's epilogue
+                const bool fuse = fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants &&
+                                  (getenv("DEEPACO_TSP_FUSE_COST") || total_ants <= (long)di->sm_count * 16);
                 if (fuse) {
                     q.dist = fuse_dist; q.costs = fuse_costs; q.nbr = fuse_nbr;
                     if (fused_out) *fused_out = 1;
