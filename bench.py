@@ -255,6 +255,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist_pg.barrier()          # rank 0 enters this barrier after its CPU-baseline leg
             dist_pg.destroy_process_group()
         return
 
@@ -311,6 +312,7 @@ def main():
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
+        dist_pg.barrier()
         dist_pg.destroy_process_group()
 
 
