@@ -202,7 +202,6 @@ def main():
         it += 1
     launches = _daco_lib().deepaco_kernel_launches() - launches0
     barrier()
-    clocks = sampler.finish()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     samp_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -246,6 +245,7 @@ def main():
         it += 1
     e1.record()
     barrier()
+    clocks = sampler.finish()          # sampled across both timed regions (device-resident steps and e2e steps)
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist_pg.all_reduce(e2e_ms, op=dist_pg.ReduceOp.MAX)
