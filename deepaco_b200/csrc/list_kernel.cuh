@@ -54,12 +54,12 @@ struct ListParams {
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(GLOBAL_P ? 256 : 512, GLOBAL_P ? 1 : 2) aco_li
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 
