@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "host_util.h"
 
+#include <stdlib.h>
+
 namespace deepaco {
 
 // numpy float32 pairwise summation of one contiguous row (numpy/_core/src/umath/loops_utils.h.src
@@ -141,7 +143,7 @@ __device__ float tour_cost_numpy(const float* __restrict__ D, int n, const uint1
 }
 
 // mode 0: one 2-opt call (ACO.two_opt); mode 1: NLS (ACO.nls)
-__global__ void __launch_bounds__(256) two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dist,
+__global__ void __launch_bounds__(512) two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dist,
                                                       uint16_t* __restrict__ tours, int n, int A, int mode, int maxt,
                                                       int T_nls, int T_p, float* __restrict__ costs_out,
                                                       int32_t* __restrict__ passes_out) {
@@ -211,7 +213,8 @@ static int launch_two_opt(const float* dist, const float* heu_dist, uint16_t* to
     DACO_CHECK_ARG(dist && tours, "deepaco_two_opt: NULL argument");
     DACO_CHECK_ARG(n >= 4 && n <= 65535 && A >= 1 && B >= 1 && B <= 65535, "deepaco_two_opt: bad sizes (n >= 4)");
     DACO_CHECK_ARG(maxt >= 0 && T_nls >= 0 && T_p >= 0, "deepaco_two_opt: negative iteration count");
-    const int W = 8;
+    int W = n >= 256 ? 16 : 8;   // more warps per tour once a pass has enough (i, j) pairs to feed them
+    if (const char* e = getenv("DEEPACO_2OPT_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) W = w; }
     const size_t smem = ((size_t)W * 3 * n + n + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)2 * n * 2 + 16;
     DACO_CHECK_ARG(smem <= (size_t)di->max_smem_optin - 1024, "deepaco_two_opt: n=%d does not fit shared memory", n);
     DACO_CHECK_CUDA(cudaFuncSetAttribute(two_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
