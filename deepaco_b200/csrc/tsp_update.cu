@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "host_util.h"
 
+#include <stdlib.h>
+
 namespace deepaco {
 
 struct TourView {
@@ -47,6 +49,48 @@ __global__ void __launch_bounds__(256) tsp_cost_kernel(const float* __restrict__
             const int pr = tv.at(k == 0 ? n - 1 : k - 1);
             const int su = tv.at(k == n - 1 ? 0 : k + 1);
             N[(size_t)u * A + a] = ((uint32_t)pr << 16) | (uint32_t)su;
+        }
+    }
+}
+
+// Tile version for compact tours: one CTA handles 32 consecutive ants.  Tours are staged in shared memory, each
+// ant's inverse permutation is built there, and the neighbour table is written node-major with the 32 ants of a
+// node side by side (128-byte coalesced stores) instead of one scattered 4-byte store per (ant, node).
+//   smem: tours u16 [32][n] | pos u16 [32][n]
+__global__ void __launch_bounds__(256) tsp_cost_tile_kernel(const float* __restrict__ dist, const uint16_t* __restrict__ tours,
+                                                            int n, int A, int lbw, int vec, float* __restrict__ costs,
+                                                            uint32_t* __restrict__ nbr) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* t_s = reinterpret_cast<uint16_t*>(smem);
+    uint16_t* pos_s = t_s + (size_t)32 * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    const int a0 = blockIdx.x * 32, b = blockIdx.y;
+    const int na = min(32, A - a0);
+    const uint16_t* T = tours + ((size_t)b * A + a0) * n;
+    for (int i = tid; i < na * n; i += blockDim.x) t_s[i] = T[i];
+    __syncthreads();
+    const float* D = dist + (size_t)b * n * n;
+    for (int al = warp; al < na; al += W) {
+        const uint16_t* tour = t_s + (size_t)al * n;
+        if (costs) {
+            auto edge = [&](int k) -> float { return __ldg(D + (size_t)tour[k] * n + tour[k == 0 ? n - 1 : k - 1]); };
+            const int a = a0 + al;
+            const float c = aten_row_sum_fn(edge, n, lbw, vec != 0, lane, vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
+            if (lane == 0) costs[(size_t)b * A + a] = c;
+        }
+        for (int k = lane; k < n; k += 32) pos_s[(size_t)al * n + tour[k]] = (uint16_t)k;
+    }
+    __syncthreads();
+    if (nbr) {
+        uint32_t* N = nbr + (size_t)b * n * A;
+        for (int i = tid; i < 32 * n; i += blockDim.x) {
+            const int u = i >> 5, al = i & 31;
+            if (al < na) {
+                const uint16_t* tour = t_s + (size_t)al * n;
+                const int k = pos_s[(size_t)al * n + u];
+                const uint32_t pr = tour[k == 0 ? n - 1 : k - 1], su = tour[k == n - 1 ? 0 : k + 1];
+                N[(size_t)u * A + a0 + al] = (pr << 16) | su;
+            }
         }
     }
 }
@@ -161,6 +205,15 @@ extern "C" int deepaco_tsp_cost(const float* distances, const int64_t* paths, co
     const SumPlan sp = aten_sum_plan(n, n_ants);
     int bw = sp.block_width > 32 ? 32 : sp.block_width, lbw = 0;
     while ((1 << lbw) < bw) ++lbw;
+    const size_t tile_smem = (size_t)32 * n * 4;
+    if (tours && tile_smem <= 96 * 1024 && !getenv("DEEPACO_COST_SIMPLE")) {
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_cost_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        dim3 grid((n_ants + 31) / 32, n_colonies);
+        tsp_cost_tile_kernel<<<grid, 256, tile_smem, (cudaStream_t)stream>>>(distances, tours, n, n_ants, lbw, sp.vectorized, costs,
+                                                                           neighbours);
+        DACO_CHECK_LAUNCH();
+        return DEEPACO_OK;
+    }
     const int W = 8;
     dim3 grid((n_ants + W - 1) / W, n_colonies);
     tsp_cost_kernel<<<grid, W * 32, 0, (cudaStream_t)stream>>>(distances, paths, tours, n, n_ants, lbw, sp.vectorized,
