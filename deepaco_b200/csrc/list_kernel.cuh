@@ -337,15 +337,26 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 
 // dense evaluation of one step over all unvisited nodes (vis = visited bitmap words in shared memory)
 static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, const float* Psm, int cur, const uint8_t* vis, uint32_t* alive_scratch,
-                                                uint32_t ctr_lo, uint32_t ctr_hi, uint64_t off_step, uint32_t sub_base) {
+                                                uint16_t* ids, uint32_t ctr_lo, uint32_t ctr_hi, uint64_t off_step, uint32_t sub_base) {
     const int lane = threadIdx.x & 31, n = p.n;
     const float* row = Psm + (size_t)cur * n;
+    // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer): the fallback
+    // fires late in a tour, when few columns are left, so the Philox work shrinks from ceil(n/32) rounds to ~1.
+    int cnt = 0;
+    for (int w = 0; w * 32 < n; ++w) {
+        const int j = w * 32 + lane;
+        const bool alive = j < n && vis[j] == 0;
+        const uint32_t bits = __ballot_sync(DACO_FULL, alive);
+        if (alive) ids[cnt + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)j;
+        if (lane == 0) alive_scratch[w] = bits;     // alive bitmap for exact_step
+        cnt += __popc(bits);
+    }
+    __syncwarp();
     float bestA = 0.f, second = 0.f;
     uint32_t bestj = 0xffffffffu;
-    for (int j = lane; j < n; j += 32) {
-        const bool alive = vis[j] == 0;
-        const float x = alive ? row[j] : 0.f;
-        const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi, sub_base + j, p.keys));
+    for (int i = lane; i < cnt; i += 32) {
+        const uint32_t j = ids[i];
+        const float A = __fmul_rn(row[j], noise_rcp(ctr_lo, ctr_hi, sub_base + j, p.keys));
         if (A > bestA) {
             second = bestA;
             bestA = A;
@@ -361,11 +372,6 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
     const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
     const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
     if (nears == 0u && __popc(tops) == 1) return __shfl_sync(DACO_FULL, bestj, __ffs(tops) - 1);
-    for (int w = 0; w * 32 < n; ++w) {       // alive bitmap for exact_step from the visited byte map
-        const int j = w * 32 + lane;
-        const uint32_t bits = __ballot_sync(DACO_FULL, j < n && vis[j] == 0);
-        if (lane == 0) alive_scratch[w] = bits;
-    }
     for (int w = (n + 31) / 32 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
     __syncwarp();
     float pn;
@@ -472,7 +478,7 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
             cur = (int)jstar;
         }
         if (step < n) {
-            const uint32_t jstar = knn_dense_step(p, Psm, cur, vis, scratch, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
+            const uint32_t jstar = knn_dense_step(p, Psm, cur, vis, scratch, tour_sm + step, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
             if (lane == 0) {
                 vis[jstar] = 1;
                 tour_sm[step] = (uint16_t)jstar;
