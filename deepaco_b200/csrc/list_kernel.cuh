@@ -340,23 +340,30 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
                                                 uint16_t* ids, uint32_t ctr_lo, uint32_t ctr_hi, uint64_t off_step, uint32_t sub_base) {
     const int lane = threadIdx.x & 31, n = p.n;
     const float* row = Psm + (size_t)cur * n;
+    PhiloxRoundKeys K;          // re-derived from the seed: cheaper than fetching 20 words through a generic pointer
+    K.init(p.seed);
     // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer): the fallback
     // fires late in a tour, when few columns are left, so the Philox work shrinks from ceil(n/32) rounds to ~1.
+    // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the visited bytes; bytes >= n are preset to 1);
+    // the order of the compacted list is irrelevant -- any tie goes to the exact path.
     int cnt = 0;
-    for (int w = 0; w * 32 < n; ++w) {
-        const int j = w * 32 + lane;
-        const bool alive = j < n && vis[j] == 0;
-        const uint32_t bits = __ballot_sync(DACO_FULL, alive);
-        if (alive) ids[cnt + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)j;
-        if (lane == 0) alive_scratch[w] = bits;     // alive bitmap for exact_step
-        cnt += __popc(bits);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int r = 0; r * 128 < n; ++r) {
+        const uint32_t v4 = reinterpret_cast<const uint32_t*>(vis)[r * 32 + lane];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const bool alive = ((v4 >> (8 * s)) & 0xffu) == 0u;
+            const uint32_t bits = __ballot_sync(DACO_FULL, alive);
+            if (alive) ids[cnt + __popc(bits & lt)] = (uint16_t)(r * 128 + 4 * lane + s);
+            cnt += __popc(bits);
+        }
     }
     __syncwarp();
     float bestA = 0.f, second = 0.f;
     uint32_t bestj = 0xffffffffu;
     for (int i = lane; i < cnt; i += 32) {
         const uint32_t j = ids[i];
-        const float A = __fmul_rn(row[j], noise_rcp(ctr_lo, ctr_hi, sub_base + j, p.keys));
+        const float A = __fmul_rn(row[j], noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
         if (A > bestA) {
             second = bestA;
             bestA = A;
@@ -372,7 +379,11 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
     const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
     const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
     if (nears == 0u && __popc(tops) == 1) return __shfl_sync(DACO_FULL, bestj, __ffs(tops) - 1);
-    for (int w = (n + 31) / 32 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
+    for (int w = 0; w < 8; ++w) {       // alive bitmap for exact_step from the visited byte map (rare)
+        const uint32_t bits = __ballot_sync(DACO_FULL, vis[w * 32 + lane] == 0);
+        if (lane == 0) alive_scratch[w] = bits;
+    }
+    for (int w = 8 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
     __syncwarp();
     float pn;
     return exact_step(row, alive_scratch, n, p.lbw, p.vec, p.double_norm, nullptr, p.seed, off_step, sub_base, p.g_noise, &pn);
@@ -441,7 +452,13 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
         ctr += p.start_increment >> 2;
     }
     const uint32_t ctr_step = p.step_increment >> 2;
-    for (int k = lane; k < 64; k += 32) reinterpret_cast<uint32_t*>(vis)[k] = 0u;
+    for (int k = lane; k < 64; k += 32) {          // visited bytes; the bytes of columns >= n read as visited
+        const int j0 = 4 * k;
+        uint32_t v = 0u;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v |= (j0 + s >= n) ? (1u << (8 * s)) : 0u;
+        reinterpret_cast<uint32_t*>(vis)[k] = v;
+    }
     __syncwarp();
     if (lane == 0) {
         vis[cur] = 1;
