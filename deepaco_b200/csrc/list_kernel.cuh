@@ -392,8 +392,9 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
 // TSP only, 32 < n <= 256, no log-probs, Philox noise, compact tours out.
 // Shared layout (fixed offsets keep the address arithmetic of the step loop in two registers):
 //   per warp w (kKnnWarpBytes each, kKnnMaxWarps slots): visited bytes [256] | scratch u32 [32] | tour u16 [256]
-//   then: knn u8 [n][32] | bound f32 [n] (16-byte padded) | P f32 [n][n]
+//   then: bound f32 [256] | knn u8 [n][32] | P f32 [n][n]
 constexpr int kKnnWarpBytes = 256 + 128 + 512;
+constexpr int kKnnBoundBytes = 1024;
 
 template <bool FUSE_COST, int MAXW>
 static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_kernel(const __grid_constant__ ListParams p) {
@@ -408,10 +409,9 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     uint8_t* vis = wblk;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(wblk + 256);
     uint16_t* tour_sm = reinterpret_cast<uint16_t*>(wblk + 384);
-    uint8_t* knn_sm = smem + kKnnFixed;
-    const uint32_t tbytes = (((uint32_t)n * 4u) + 15u) & ~15u;
-    float* Tsm = reinterpret_cast<float*>(knn_sm + (size_t)n * 32);
-    float* Psm = reinterpret_cast<float*>(knn_sm + (size_t)n * 32 + tbytes);
+    float* Tsm = reinterpret_cast<float*>(smem + kKnnFixed);                 // fixed offsets: immediates in the step loop
+    uint8_t* knn_sm = smem + kKnnFixed + kKnnBoundBytes;
+    float* Psm = reinterpret_cast<float*>(knn_sm + (size_t)n * 32);
 
     {   // candidate lists of this colony (static per instance)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.knn + (size_t)b * n * 32);
@@ -436,9 +436,9 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     const int a = blockIdx.x * W + warp;
     if (a >= p.A) return;
     const uint32_t wbase = pin_u32(smem_u32(wblk));                       // vis at +0, tour at +384
-    const uint32_t knn_lane = pin_u32(smem_u32(knn_sm) + (uint32_t)lane);
-    const uint32_t T_addr = knn_lane - (uint32_t)lane + (uint32_t)n * 32u;
-    const uint32_t P_addr = T_addr + tbytes;
+    const uint32_t knn_lane = smem_u32(knn_sm) + (uint32_t)lane;
+    const uint32_t T_addr = smem_u32(Tsm);
+    const uint32_t P_addr = pin_u32(smem_u32(Psm));
     const uint64_t offset0 = (p.offsets ? p.offsets[b] : 0ull) + p.offset;
     const PhiloxRoundKeys& K = p.keys;
     const uint32_t sub_base = (uint32_t)(a + p.ant_base) * (uint32_t)n;
@@ -449,9 +449,9 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
         cur = p.start_node;
     } else {
         cur = (int)(torch_philox_word(p.seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
-        ctr += p.start_increment >> 2;
+        ctr += 1;
     }
-    const uint32_t ctr_step = p.step_increment >> 2;
+    constexpr uint32_t ctr_step = 1;   // single-launch draw geometry (host-checked): every draw advances the offset by 4
     for (int k = lane; k < 64; k += 32) {          // visited bytes; the bytes of columns >= n read as visited
         const int j0 = 4 * k;
         uint32_t v = 0u;
@@ -482,11 +482,11 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
             const uint32_t mybits = __float_as_uint(A);
             const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
             const float top = __uint_as_float(topbits);
-            const bool is_top = mybits == topbits;
-            const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
-            const uint32_t nears = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f) && !is_top);
-            if (!(nears == 0u && __popc(tops) == 1 && T < top)) break;
-            const uint32_t jstar = __shfl_sync(DACO_FULL, j, __ffs(tops) - 1);
+            // lanes within 2^-18 (relative) of the top score, the top lane included: the step is decided here only
+            // when that is exactly one lane and no unlisted column can beat it
+            const uint32_t close = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f));
+            if (!(__popc(close) == 1 && T < top)) break;
+            const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
             if (lane == 0) {
                 asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(1u) : "memory");
                 sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
@@ -528,7 +528,7 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
 }
 
 inline size_t knn_kernel_smem(int n, int W) {
-    return (size_t)kKnnWarpBytes * (W <= 8 ? 8 : 16) + (size_t)n * 32 + ((((size_t)n * 4) + 15) & ~(size_t)15) + ((((size_t)n * n * 4) + 15) & ~(size_t)15);
+    return (size_t)kKnnWarpBytes * (W <= 8 ? 8 : 16) + kKnnBoundBytes + (size_t)n * 32 + ((((size_t)n * n * 4) + 15) & ~(size_t)15);
 }
 
 inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp, bool global_p = false) {

@@ -272,7 +272,8 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
-        if (knn && !noise && !log_probs && !paths && !start && (tours || n_peers) && n > 32 && n <= 256 && !getenv("DEEPACO_TSP_NO_KNN")) {
+        if (knn && !noise && !log_probs && !paths && !start && (tours || n_peers) && n > 32 && n <= 256 && dn.increment == 4 &&
+            ds.increment == 4 && !getenv("DEEPACO_TSP_NO_KNN")) {
             // sparse product: one candidate per lane (kNN kernel)
             int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : 8;
             if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) Wk = w; }
