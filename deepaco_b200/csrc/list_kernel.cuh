@@ -52,6 +52,11 @@ struct ListParams {
     uint32_t start_increment, step_increment;
 };
 
+__device__ __forceinline__ uint32_t lds_s8(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return (uint32_t)v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -344,7 +349,7 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
     K.init(p.seed);
     // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer): the fallback
     // fires late in a tour, when few columns are left, so the Philox work shrinks from ceil(n/32) rounds to ~1.
-    // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the visited bytes; bytes >= n are preset to 1);
+    // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the alive bytes: 0xff = unvisited; bytes >= n are 0);
     // the order of the compacted list is irrelevant -- any tie goes to the exact path.
     int cnt = 0;
     const uint32_t lt = (1u << lane) - 1u;
@@ -352,7 +357,7 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
         const uint32_t v4 = reinterpret_cast<const uint32_t*>(vis)[r * 32 + lane];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const bool alive = ((v4 >> (8 * s)) & 0xffu) == 0u;
+            const bool alive = ((v4 >> (8 * s)) & 0xffu) != 0u;
             const uint32_t bits = __ballot_sync(DACO_FULL, alive);
             if (alive) ids[cnt + __popc(bits & lt)] = (uint16_t)(r * 128 + 4 * lane + s);
             cnt += __popc(bits);
@@ -380,7 +385,7 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
     const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
     if (nears == 0u && __popc(tops) == 1) return __shfl_sync(DACO_FULL, bestj, __ffs(tops) - 1);
     for (int w = 0; w < 8; ++w) {       // alive bitmap for exact_step from the visited byte map (rare)
-        const uint32_t bits = __ballot_sync(DACO_FULL, vis[w * 32 + lane] == 0);
+        const uint32_t bits = __ballot_sync(DACO_FULL, vis[w * 32 + lane] != 0);
         if (lane == 0) alive_scratch[w] = bits;
     }
     for (int w = 8 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
@@ -452,16 +457,16 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
         ctr += 1;
     }
     constexpr uint32_t ctr_step = 1;   // single-launch draw geometry (host-checked): every draw advances the offset by 4
-    for (int k = lane; k < 64; k += 32) {          // visited bytes; the bytes of columns >= n read as visited
+    for (int k = lane; k < 64; k += 32) {          // alive bytes: 0xff = unvisited, 0 = visited or column >= n
         const int j0 = 4 * k;
         uint32_t v = 0u;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) v |= (j0 + s >= n) ? (1u << (8 * s)) : 0u;
+        for (int s = 0; s < 4; ++s) v |= (j0 + s < n) ? (0xffu << (8 * s)) : 0u;
         reinterpret_cast<uint32_t*>(vis)[k] = v;
     }
     __syncwarp();
     if (lane == 0) {
-        vis[cur] = 1;
+        vis[cur] = 0;
         tour_sm[0] = (uint16_t)cur;
     }
     __syncwarp();
@@ -474,10 +479,9 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
 #pragma unroll 1
         for (; step < n; ++step, ctr += ctr_step) {
             const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
-            const uint32_t dead = lds_u8(wbase + j);
+            const uint32_t alive = lds_s8(wbase + j);     // sign-extended: all ones while column j is unvisited
             const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
-            float x = lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u);
-            x = dead ? 0.f : x;
+            const float x = __uint_as_float(__float_as_uint(lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u)) & alive);
             const float A = __fmul_rn(x, noise_rcp((uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base + j, K));
             const uint32_t mybits = __float_as_uint(A);
             const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
@@ -487,17 +491,16 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
             const uint32_t close = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f));
             if (!(__popc(close) == 1 && T < top)) break;
             const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
-            if (lane == 0) {
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(1u) : "memory");
-                sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
-            }
+            // every lane stores the same two values (same address: one wavefront, no predicate to maintain)
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
+            sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
             __syncwarp();
             cur = (int)jstar;
         }
         if (step < n) {
             const uint32_t jstar = knn_dense_step(p, Psm, cur, vis, scratch, tour_sm + step, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
             if (lane == 0) {
-                vis[jstar] = 1;
+                vis[jstar] = 0;
                 tour_sm[step] = (uint16_t)jstar;
             }
             __syncwarp();
