@@ -340,35 +340,54 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 
-// dense evaluation of one step over all unvisited nodes (vis = visited bitmap words in shared memory)
-static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, const float* Psm, int cur, const uint8_t* vis, uint32_t* alive_scratch,
-                                                uint16_t* ids, uint32_t ctr_lo, uint32_t ctr_hi, uint64_t off_step, uint32_t sub_base) {
-    const int lane = threadIdx.x & 31, n = p.n;
-    const float* row = Psm + (size_t)cur * n;
+// Rare tail of the fallback step: a tie or a near-tie among the approximate scores -> exact arithmetic in ATen order.
+static __device__ __noinline__ uint32_t knn_exact_tail(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t ctr_lo, uint32_t ctr_hi,
+                                                       uint32_t sub_base) {
+    const int lane = threadIdx.x & 31;
+    uint32_t* alive_scratch = reinterpret_cast<uint32_t*>(__cvta_shared_to_generic(wbase + 256u));
+    for (int w = 0; w < 8; ++w) {       // alive bitmap for exact_step from the alive byte map
+        const uint32_t bits = __ballot_sync(DACO_FULL, lds_u8(wbase + (uint32_t)(w * 32 + lane)) != 0u);
+        if (lane == 0) alive_scratch[w] = bits;
+    }
+    for (int w = 8 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
+    __syncwarp();
+    float pn;
+    const uint64_t off_step = (((uint64_t)ctr_hi << 32) | ctr_lo) << 2;
+    return exact_step(reinterpret_cast<const float*>(__cvta_shared_to_generic(row_addr)), alive_scratch, p.n, p.lbw, p.vec, p.double_norm, nullptr,
+                      p.seed, off_step, sub_base, p.g_noise, &pn);
+}
+
+// Fallback step of the kNN kernel: evaluate every unvisited column of row `cur` (row_addr = shared address of that
+// row of P), commit the winner (alive byte, tour slot `step`) and return it.  Everything is passed by value / as
+// 32-bit shared addresses so that the call marshals few registers.
+static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t step, uint32_t n,
+                                                       uint32_t seed_lo, uint32_t seed_hi, uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub_base) {
+    const uint32_t lane = threadIdx.x & 31u;
     PhiloxRoundKeys K;          // re-derived from the seed: cheaper than fetching 20 words through a generic pointer
-    K.init(p.seed);
-    // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer): the fallback
-    // fires late in a tour, when few columns are left, so the Philox work shrinks from ceil(n/32) rounds to ~1.
+    K.init(((uint64_t)seed_hi << 32) | seed_lo);
+    // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer, one slot per
+    // unvisited node by construction): the Philox work shrinks from ceil(n/32) rounds to ceil(alive/32).
     // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the alive bytes: 0xff = unvisited; bytes >= n are 0);
     // the order of the compacted list is irrelevant -- any tie goes to the exact path.
-    int cnt = 0;
+    const uint32_t ids_addr = wbase + 384u + 2u * step;
+    uint32_t cnt = 0;
     const uint32_t lt = (1u << lane) - 1u;
-    for (int r = 0; r * 128 < n; ++r) {
-        const uint32_t v4 = reinterpret_cast<const uint32_t*>(vis)[r * 32 + lane];
+    for (uint32_t r = 0; r * 128u < n; ++r) {
+        const uint32_t v4 = lds_u32(wbase + (r * 32u + lane) * 4u);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (uint32_t s = 0; s < 4; ++s) {
             const bool alive = ((v4 >> (8 * s)) & 0xffu) != 0u;
             const uint32_t bits = __ballot_sync(DACO_FULL, alive);
-            if (alive) ids[cnt + __popc(bits & lt)] = (uint16_t)(r * 128 + 4 * lane + s);
+            if (alive) sts_u16(ids_addr + 2u * (cnt + __popc(bits & lt)), r * 128u + 4u * lane + s);
             cnt += __popc(bits);
         }
     }
     __syncwarp();
     float bestA = 0.f, second = 0.f;
     uint32_t bestj = 0xffffffffu;
-    for (int i = lane; i < cnt; i += 32) {
-        const uint32_t j = ids[i];
-        const float A = __fmul_rn(row[j], noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint32_t j = lds_u16(ids_addr + 2u * i);
+        const float A = __fmul_rn(lds_f32(row_addr + 4u * j), noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
         if (A > bestA) {
             second = bestA;
             bestA = A;
@@ -380,18 +399,17 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, cons
     const uint32_t mybits = __float_as_uint(bestA);
     const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
     const float thr = __fmul_rn(__uint_as_float(topbits), 1.0f - 3.814697265625e-06f);
-    const bool is_top = mybits == topbits;
-    const uint32_t tops = __ballot_sync(DACO_FULL, is_top);
-    const uint32_t nears = __ballot_sync(DACO_FULL, (second >= thr) || (bestA >= thr && !is_top));
-    if (nears == 0u && __popc(tops) == 1) return __shfl_sync(DACO_FULL, bestj, __ffs(tops) - 1);
-    for (int w = 0; w < 8; ++w) {       // alive bitmap for exact_step from the visited byte map (rare)
-        const uint32_t bits = __ballot_sync(DACO_FULL, vis[w * 32 + lane] != 0);
-        if (lane == 0) alive_scratch[w] = bits;
-    }
-    for (int w = 8 + lane; w < 32; w += 32) alive_scratch[w] = 0u;
+    // lanes holding a score within 2^-18 of the top (the top lane included), or a runner-up that close
+    const uint32_t close = __ballot_sync(DACO_FULL, bestA >= thr);
+    const uint32_t nears = __ballot_sync(DACO_FULL, second >= thr);
+    uint32_t jstar;
+    if (nears == 0u && __popc(close) == 1) jstar = __shfl_sync(DACO_FULL, bestj, 31 - __clz(close));
+    else jstar = knn_exact_tail(p, row_addr, wbase, ctr_lo, ctr_hi, sub_base);
     __syncwarp();
-    float pn;
-    return exact_step(row, alive_scratch, n, p.lbw, p.vec, p.double_norm, nullptr, p.seed, off_step, sub_base, p.g_noise, &pn);
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
+    sts_u16(wbase + 384u + 2u * step, jstar);
+    __syncwarp();
+    return jstar;
 }
 
 // TSP only, 32 < n <= 256, no log-probs, Philox noise, compact tours out.
@@ -498,13 +516,8 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
             cur = (int)jstar;
         }
         if (step < n) {
-            const uint32_t jstar = knn_dense_step(p, Psm, cur, vis, scratch, tour_sm + step, (uint32_t)ctr, (uint32_t)(ctr >> 32), ctr << 2, sub_base);
-            if (lane == 0) {
-                vis[jstar] = 0;
-                tour_sm[step] = (uint16_t)jstar;
-            }
-            __syncwarp();
-            cur = (int)jstar;
+            cur = (int)knn_dense_step(p, P_addr + (uint32_t)cur * (uint32_t)n * 4u, wbase, (uint32_t)step, (uint32_t)n, (uint32_t)p.seed,
+                                      (uint32_t)(p.seed >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base);
             ++step;
             ctr += ctr_step;
         }

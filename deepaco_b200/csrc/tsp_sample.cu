@@ -275,7 +275,8 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         if (knn && !noise && !log_probs && !paths && !start && (tours || n_peers) && n > 32 && n <= 256 && dn.increment == 4 &&
             ds.increment == 4 && !getenv("DEEPACO_TSP_NO_KNN")) {
             // sparse product: one candidate per lane (kNN kernel)
-            int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : 8;
+            // 4 warps while the job is tiny, 16 when many CTAs queue per SM (the per-CTA staging is shared by more ants)
+            int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : (total_ants >= (long)di->sm_count * 128 && n_ants % 16 == 0 ? 16 : 8);
             if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) Wk = w; }
             if (knn_kernel_smem(n, Wk) <= cap) {
                 if (total_ants > (long)di->sm_count * 4)
