@@ -358,9 +358,9 @@ static __device__ __noinline__ uint32_t knn_exact_tail(const ListParams& p, uint
 }
 
 // Fallback step of the kNN kernel: evaluate every unvisited column of row `cur` (row_addr = shared address of that
-// row of P), commit the winner (alive byte, tour slot `step`) and return it.  Everything is passed by value / as
+// row of P), commit the winner (alive byte, tour slot at shared address `slot`) and return it.  Everything is passed by value / as
 // 32-bit shared addresses so that the call marshals few registers.
-static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t step, uint32_t n,
+static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t slot, uint32_t n,
                                                        uint32_t seed_lo, uint32_t seed_hi, uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub_base) {
     const uint32_t lane = threadIdx.x & 31u;
     PhiloxRoundKeys K;          // re-derived from the seed: cheaper than fetching 20 words through a generic pointer
@@ -369,7 +369,7 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint
     // unvisited node by construction): the Philox work shrinks from ceil(n/32) rounds to ceil(alive/32).
     // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the alive bytes: 0xff = unvisited; bytes >= n are 0);
     // the order of the compacted list is irrelevant -- any tie goes to the exact path.
-    const uint32_t ids_addr = wbase + 384u + 2u * step;
+    const uint32_t ids_addr = slot;
     uint32_t cnt = 0;
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t r = 0; r * 128u < n; ++r) {
@@ -407,7 +407,7 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint
     else jstar = knn_exact_tail(p, row_addr, wbase, ctr_lo, ctr_hi, sub_base);
     __syncwarp();
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
-    sts_u16(wbase + 384u + 2u * step, jstar);
+    sts_u16(slot, jstar);
     __syncwarp();
     return jstar;
 }
@@ -491,37 +491,47 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
 
     // Fast steps run in an inner loop that contains no call, so its registers are not constrained by the calling
     // convention; a step that needs the dense / exact treatment leaves it, is handled, and the fast loop resumes.
-    int step = 1;
+    // The loop state is the shared address of the tour slot being filled (no step counter, no per-step address sum)
+    // and the low word of the Philox counter.  Its high word is loop-invariant unless the low word wraps during this
+    // tour: such a warp (one in ~2^32/n) takes every step through the fallback, which gets the carried high word.
+    uint32_t slot = wbase + 384u + 2u;
+    const uint32_t slot_end = wbase + 384u + 2u * (uint32_t)n;
+    const uint32_t ctr_lo0 = (uint32_t)ctr, ctr_hi0 = (uint32_t)(ctr >> 32);
+    const bool wraps = ctr_lo0 > 0xffffffffu - (uint32_t)n;
+    uint32_t ctr_lo = ctr_lo0;
 #pragma unroll 1
-    while (step < n) {
+    while (slot < slot_end) {
+        if (!wraps) {
 #pragma unroll 1
-        for (; step < n; ++step, ctr += ctr_step) {
-            const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
-            const uint32_t alive = lds_s8(wbase + j);     // sign-extended: all ones while column j is unvisited
-            const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
-            const float x = __uint_as_float(__float_as_uint(lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u)) & alive);
-            const float A = __fmul_rn(x, noise_rcp((uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base + j, K));
-            const uint32_t mybits = __float_as_uint(A);
-            const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
-            const float top = __uint_as_float(topbits);
-            // lanes within 2^-18 (relative) of the top score, the top lane included: the step is decided here only
-            // when that is exactly one lane and no unlisted column can beat it
-            const uint32_t close = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f));
-            if (!(__popc(close) == 1 && T < top)) break;
-            const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
-            // every lane stores the same two values (same address: one wavefront, no predicate to maintain)
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
-            sts_u16(wbase + 384u + 2u * (uint32_t)step, jstar);
-            __syncwarp();
-            cur = (int)jstar;
+            for (; slot < slot_end; slot += 2u, ++ctr_lo) {
+                const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
+                const uint32_t alive = lds_s8(wbase + j);     // sign-extended: all ones while column j is unvisited
+                const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
+                const float x = __uint_as_float(__float_as_uint(lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u)) & alive);
+                const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi0, sub_base + j, K));
+                const uint32_t mybits = __float_as_uint(A);
+                const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+                const float top = __uint_as_float(topbits);
+                // lanes within 2^-18 (relative) of the top score, the top lane included: the step is decided here
+                // only when that is exactly one lane and no unlisted column can beat it
+                const uint32_t close = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f));
+                if (!(__popc(close) == 1 && T < top)) break;
+                const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
+                // Every lane stores the same two values to the same addresses: one wavefront, no predicate to
+                // maintain, and each lane later reads what it wrote itself, so no warp-level fence between steps.
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
+                sts_u16(slot, jstar);
+                cur = (int)jstar;
+            }
         }
-        if (step < n) {
-            cur = (int)knn_dense_step(p, P_addr + (uint32_t)cur * (uint32_t)n * 4u, wbase, (uint32_t)step, (uint32_t)n, (uint32_t)p.seed,
-                                      (uint32_t)(p.seed >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), sub_base);
-            ++step;
-            ctr += ctr_step;
+        if (slot < slot_end) {
+            cur = (int)knn_dense_step(p, P_addr + (uint32_t)cur * (uint32_t)n * 4u, wbase, slot, (uint32_t)n, (uint32_t)p.seed,
+                                      (uint32_t)(p.seed >> 32), ctr_lo, ctr_hi0 + (ctr_lo < ctr_lo0 ? 1u : 0u), sub_base);
+            slot += 2u;
+            ++ctr_lo;
         }
     }
+    __syncwarp();
     if (p.tours) {   // warp-local, coalesced: this ant's row of the compact layout
         uint16_t* out = p.tours + ((size_t)b * p.A + a) * n;
         for (int k = lane; k < n; k += 32) out[k] = tour_sm[k];
