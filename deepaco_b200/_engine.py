@@ -494,6 +494,14 @@ def debug_randint(seed, offset, numel, high, device):
     return out
 
 
+def debug_exp_guard(device):
+    """deepaco_debug_exp_guard: Philox words whose shortened Exp(1) transform differs from the literal ATen form (0)."""
+    out = torch.zeros(1, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        check(lib().deepaco_debug_exp_guard(ptr(out), stream_ptr(out.device)), "debug_exp_guard")
+    return int(out.item())
+
+
 def debug_row_sum(x):
     x = f32c(require_cuda(x, "x"))
     out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "deepaco_debug_exponential": (_i32, [_u64, _u64, _i64, _vp, _vp]),
     "deepaco_debug_randint": (_i32, [_u64, _u64, _i64, _i64, _vp, _vp]),
     "deepaco_debug_row_sum": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "deepaco_debug_exp_guard": (_i32, [_vp, _vp]),
 }
 
 

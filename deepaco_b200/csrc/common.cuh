@@ -108,13 +108,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // at::log<float> on device is the fast `__logf` (ATen/NumericUtils.h:149-160) = lg2.approx.f32 * ln2.
 // u >= 2^-33 is never denormal, so the .ftz form of the MUFU instruction returns the same bits without
 // the denormal pre-scaling code the non-ftz intrinsic expands to.
-__device__ __forceinline__ float exp1_from_word(uint32_t x) {
+__device__ __forceinline__ float exp1_from_word_guarded(uint32_t x) {      // literal form of the ATen transform
     const float u = fmaf((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f);   // product is exact: fma == mul + add
     float l2;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
     const float lg = (u >= 1.0f - 1.1920928955078125e-07f / 2.0f) ? -(1.1920928955078125e-07f / 2.0f)
                                                                    : __fmul_rn(l2, 0.693147182464599609375f);
     return -lg;
+}
+
+// Same bits with one instruction less: the guard only fires for u == 1 (lg2 = 0 -> max picks 2^-24), and for the
+// largest u below 1 (1 - 2^-24) MUFU.LG2 * ln2 is not below 2^-24 on sm_100 -- checked exhaustively over the top
+// 2^20 Philox words by deepaco_debug_exp_guard (tests/test_gpu_probes.py); everywhere else -log(u) >= 2^-23.
+__device__ __forceinline__ float exp1_from_word(uint32_t x) {
+    const float u = fmaf((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+    return fmaxf(-__fmul_rn(l2, 0.693147182464599609375f), 1.1920928955078125e-07f / 2.0f);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -59,3 +59,23 @@ extern "C" int deepaco_debug_row_sum(const float* x, int n_rows, int row_len, fl
     DACO_CHECK_LAUNCH();
     return DEEPACO_OK;
 }
+
+namespace deepaco {
+__global__ void exp_guard_probe_kernel(unsigned long long* bad, uint32_t base, uint32_t stride) {
+    const uint32_t x = base + (blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    if (__float_as_uint(exp1_from_word(x)) != __float_as_uint(exp1_from_word_guarded(x))) atomicAdd(bad, 1ull);
+}
+}  // namespace deepaco
+
+// Counts the 32-bit Philox words for which the shortened Exp(1) transform (common.cuh exp1_from_word) differs from the
+// literal ATen form: exhaustive over the top 2^20 words (the only region where they can differ) + every 256th word.
+extern "C" int deepaco_debug_exp_guard(uint64_t* mismatches, void* stream) {
+    DACO_CHECK_ARG(mismatches, "deepaco_debug_exp_guard: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DACO_CHECK_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), st));
+    deepaco::exp_guard_probe_kernel<<<(1 << 20) / 256, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(mismatches), 0xFFF00000u, 1u);
+    DACO_CHECK_LAUNCH();
+    deepaco::exp_guard_probe_kernel<<<(1 << 24) / 256, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(mismatches), 0u, 256u);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}

@@ -250,6 +250,9 @@ int deepaco_logp_backward(const float* pheromone_pow, const float* heuristic_pow
 int deepaco_debug_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out, void* stream);
 int deepaco_debug_randint(uint64_t seed, uint64_t offset, int64_t numel, int64_t high, int64_t* out, void* stream);
 int deepaco_debug_row_sum(const float* x, int n_rows, int row_len, float* out, void* stream);
+/* Number of 32-bit Philox words for which the kernels' shortened Exp(1) transform differs from the literal
+ * ATen form (TransformationHelper.h:129-146); must be 0.  mismatches: device uint64. */
+int deepaco_debug_exp_guard(uint64_t* mismatches, void* stream);
 
 #ifdef __cplusplus
 }

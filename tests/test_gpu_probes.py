@@ -54,3 +54,10 @@ def test_row_sum_order(rows, cols):
             assert torch.equal(ref, mine), f"bw={bw} vec={vec}: {(ref - mine).abs().max().item()}"
         else:
             assert torch.allclose(ref, mine, rtol=1e-6)
+
+
+def test_shortened_exponential_transform_is_bit_identical():
+    """common.cuh exp1_from_word drops the explicit u >= 1 - 2^-25 guard in favour of max(., 2^-24); the two forms are
+    compared exhaustively over the top 2^20 Philox words (the only place they can differ) and a stride sample."""
+    from deepaco_b200 import _engine as E
+    assert E.debug_exp_guard("cuda") == 0
