@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) tsp_cost_tile_kernel(const float* __restr
 // successor cell -- the reference's statement order) are bucketed by cell with a stable counting sort in
 // shared memory, so each cell then adds its own few weights in ant order: work per row is O(A + n) instead
 // of O(A * n), and the row is read and written exactly once, coalesced.
-//   smem per warp: w_sorted[2A] f32 | start[n+1] i32 | cursor[n] i32
+//   smem: inv[A] f32 (1 / cost, shared by the CTA's rows) | per warp: w_sorted[2A] f32 | start[n+1] i32 | cursor[n] i32
 __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
                                                          const float* __restrict__ costs, int n, int A, float decay,
                                                          int elitist, int min_max, float ph_min,
@@ -108,13 +108,16 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     const int u = blockIdx.x * W + warp, b = blockIdx.y;
-    if (u >= n) return;
     const size_t per_warp = (size_t)2 * A * 4 + (size_t)(2 * n + 1) * 4;
-    float* w_sorted = reinterpret_cast<float*>(smem + warp * ((per_warp + 15) & ~(size_t)15));
+    float* inv = reinterpret_cast<float*>(smem);
+    float* w_sorted = reinterpret_cast<float*>(smem + (((size_t)A * 4 + 15) & ~(size_t)15) + warp * ((per_warp + 15) & ~(size_t)15));
     int* start = reinterpret_cast<int*>(w_sorted + 2 * A);
     int* cursor = start + n + 1;
     const uint32_t* N = nbr + ((size_t)b * n + u) * A;
     const float* C = costs + (size_t)b * A;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) inv[a] = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+    __syncthreads();
+    if (u >= n) return;
 
     int a_lo = 0, a_hi = A;
     if (elitist) {   // costs.min(dim=0): first index of the minimum
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
             const int a = a_lo + (e >> 1);
             const uint32_t nb = N[a];
             cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
-            w = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+            w = inv[a];
         }
         const uint32_t grp = __match_any_sync(DACO_FULL, cell);
         const int rank = __popc(grp & ((1u << lane) - 1u));
@@ -177,19 +180,24 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
     float* row = ph + ((size_t)b * n + u) * n;
     const float hi = min_max ? ph_max[b] : 0.f;
     const float sc = scale ? scale[b] : 1.0f;
-    for (int v = lane; v < n; v += 32) {
-        float val = row[v];
+    for (int base = 0; base < n; base += 32) {      // warp-uniform loop: every lane takes part in the reductions
+        const int v = base + lane;
+        const bool valid = v < n;
+        float val = valid ? row[v] : 0.f;
         if (scale) val = __fmul_rn(val, sc);   // MMAS rescale on the first improvement (tsp/aco.py:86-87)
         val = __fmul_rn(val, decay);
-        for (int i = start[v]; i < start[v + 1]; ++i) val = __fadd_rn(val, w_sorted[i]);
+        if (valid)      // this cell's deposits in ant order
+            for (int i = start[v]; i < start[v + 1]; ++i) val = __fadd_rn(val, w_sorted[i]);
         if (min_max) {
             // ph[(ph > 1e-9) * ph < min] = min ; ph[ph > max] = max   (tsp/aco.py:117-118)
             const float gate = __fmul_rn(val > 1e-9f ? 1.0f : 0.0f, val);
             if (gate < ph_min) val = ph_min;
             if (val > hi) val = hi;
         }
-        row[v] = val;
-        if (prod) prod[((size_t)b * n + u) * n + v] = __fmul_rn(val, heu[((size_t)b * n + u) * n + v]);
+        if (valid) {
+            row[v] = val;
+            if (prod) prod[((size_t)b * n + u) * n + v] = __fmul_rn(val, heu[((size_t)b * n + u) * n + v]);
+        }
     }
 }
 
@@ -227,7 +235,7 @@ static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const
                              const float* scale, const float* heuristic, float* product, cudaStream_t st) {
     const int W = 4;
     const size_t per_warp = (((size_t)2 * n_ants * 4 + (size_t)(2 * n + 1) * 4) + 15) & ~(size_t)15;
-    const size_t smem = per_warp * W;
+    const size_t smem = per_warp * W + (((size_t)n_ants * 4 + 15) & ~(size_t)15);
     DACO_CHECK_ARG(smem <= 200 * 1024, "deepaco_tsp_update: n_ants=%d / n=%d too large for one pass", n_ants, n);
     DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + W - 1) / W, n_colonies);
