@@ -363,8 +363,8 @@ static __device__ __noinline__ uint32_t knn_exact_tail(const ListParams& p, uint
 static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t slot, uint32_t n,
                                                        uint32_t seed_lo, uint32_t seed_hi, uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub_base) {
     const uint32_t lane = threadIdx.x & 31u;
-    PhiloxRoundKeys K;          // re-derived from the seed: cheaper than fetching 20 words through a generic pointer
-    K.init(((uint64_t)seed_hi << 32) | seed_lo);
+    const PhiloxRoundKeys& K = p.keys;   // the compiler clones this function for its kernel: constant-bank operands
+    (void)seed_lo; (void)seed_hi;
     // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer, one slot per
     // unvisited node by construction): the Philox work shrinks from ceil(n/32) rounds to ceil(alive/32).
     // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the alive bytes: 0xff = unvisited; bytes >= n are 0);
@@ -385,9 +385,13 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint
     __syncwarp();
     float bestA = 0.f, second = 0.f;
     uint32_t bestj = 0xffffffffu;
-    for (uint32_t i = lane; i < cnt; i += 32) {
-        const uint32_t j = lds_u16(ids_addr + 2u * i);
-        const float A = __fmul_rn(lds_f32(row_addr + 4u * j), noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
+#pragma unroll 1
+    for (uint32_t base = 0; base < cnt; base += 32) {     // warp-uniform rounds (no divergent remainder loop)
+        const uint32_t i = base + lane;
+        const bool on = i < cnt;
+        const uint32_t j = on ? lds_u16(ids_addr + 2u * i) : 0u;
+        float A = __fmul_rn(lds_f32(row_addr + 4u * j), noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
+        A = on ? A : 0.f;
         if (A > bestA) {
             second = bestA;
             bestA = A;
@@ -554,7 +558,7 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
 }
 
 inline size_t knn_kernel_smem(int n, int W) {
-    return (size_t)kKnnWarpBytes * (W <= 8 ? 8 : 16) + kKnnBoundBytes + (size_t)n * 32 + ((((size_t)n * n * 4) + 15) & ~(size_t)15);
+    return (size_t)kKnnWarpBytes * (W <= 8 ? 8 : W <= 16 ? 16 : 32) + kKnnBoundBytes + (size_t)n * 32 + ((((size_t)n * n * 4) + 15) & ~(size_t)15);
 }
 
 inline size_t list_kernel_smem(int n, int rows, int W, bool cvrp, bool global_p = false) {

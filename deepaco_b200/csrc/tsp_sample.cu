@@ -277,10 +277,10 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
             // sparse product: one candidate per lane (kNN kernel)
             // 4 warps while the job is tiny, 16 when many CTAs queue per SM (the per-CTA staging is shared by more ants)
             int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : (total_ants >= (long)di->sm_count * 128 && n_ants % 16 == 0 ? 16 : 8);
-            if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) Wk = w; }
+            if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 32) Wk = w; }
             if (knn_kernel_smem(n, Wk) <= cap) {
                 if (total_ants > (long)di->sm_count * 4)
-                    while (Wk < 16 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;
+                    while (Wk < 32 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;   // n ~ 200: one 32-warp CTA per SM
                 q.knn = knn;
                 // small jobs are launch-latency bound: fold cost + neighbour table into the construction kernel's epilogue
                 const bool fuse = fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants &&
@@ -298,8 +298,8 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
                                              cudaSharedmemCarveoutMaxShared));                                                  \
         aco_knn_kernel<F, M><<<grid, Wk * 32, ksm, st>>>(q);                                                                    \
     } while (0)
-                if (fuse) { if (Wk <= 8) DACO_KNN(true, 8); else DACO_KNN(true, 16); }
-                else { if (Wk <= 8) DACO_KNN(false, 8); else DACO_KNN(false, 16); }
+                if (fuse) { if (Wk <= 8) DACO_KNN(true, 8); else if (Wk <= 16) DACO_KNN(true, 16); else DACO_KNN(true, 32); }
+                else { if (Wk <= 8) DACO_KNN(false, 8); else if (Wk <= 16) DACO_KNN(false, 16); else DACO_KNN(false, 32); }
 #undef DACO_KNN
                 DACO_CHECK_LAUNCH();
                 return DEEPACO_OK;
