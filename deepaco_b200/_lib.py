@@ -67,6 +67,17 @@ class CvrpRunArgs(C.Structure):
                 ("lowest_cost", _vp), ("shortest_path", _vp), ("shortest_rows", _vp), ("ph_max", _vp), ("scale", _vp)]
 
 
+class GnnTrainArgs(C.Structure):
+    """deepaco_gnn_train_args (include/deepaco_b200.h)."""
+    _fields_ = [("n_nodes", _i32), ("n_edges", _i32), ("feats", _i32), ("n_instances", _i32), ("ctas_per_instance", _i32),
+                ("bn_eps", _f32), ("x", _vp), ("row_ptr", _vp), ("src_sorted", _vp), ("dst_sorted", _vp), ("attr_sorted", _vp),
+                ("order", _vp), ("col_ptr", _vp), ("in_edges", _vp), ("weights", _vp), ("xs", _vp), ("ws", _vp), ("zv", _vp),
+                ("ze", _vp), ("stats", _vp), ("node_ws", _vp), ("edge_ws", _vp), ("red", _vp), ("heu_out", _vp),
+                ("grad_heu", _vp), ("grad_weights", _vp)]
+
+
+_SIGNATURES["deepaco_gnn_train_forward"] = (_i32, [C.POINTER(GnnTrainArgs), _vp])
+_SIGNATURES["deepaco_gnn_train_backward"] = (_i32, [C.POINTER(GnnTrainArgs), _vp])
 _SIGNATURES["deepaco_cvrp_run"] = (_i32, [C.POINTER(CvrpRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp])

@@ -1,0 +1,44 @@
+// C ABI of the training-mode heuristic network (kernels in gnn_train.cuh): one thread-block cluster per graph.
+#include "gnn_train.cuh"
+#include "gnn_train_args.h"
+#include "host_util.h"
+
+using namespace deepaco;
+using namespace deepaco::gnnt;
+
+template <class Kernel>
+static int launch_clustered(Kernel kernel, const TrainParams& p, int n_instances, int ctas, int threads, size_t smem,
+                            cudaStream_t st) {
+    DACO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_instances * ctas));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DACO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+
+extern "C" int deepaco_gnn_train_forward(const deepaco_gnn_train_args* a, void* stream) {
+    TrainParams p;
+    if (const char* err = gnn_train_params(a, false, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_forward: %s", err);
+    const int threads = a->n_edges >= 2048 * a->ctas_per_instance ? 512 : 256;
+    return launch_clustered(gnn_train_forward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
+                            smem_floats_fwd(threads) * 4, (cudaStream_t)stream);
+}
+
+extern "C" int deepaco_gnn_train_backward(const deepaco_gnn_train_args* a, void* stream) {
+    TrainParams p;
+    if (const char* err = gnn_train_params(a, true, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_backward: %s", err);
+    const int threads = 256;
+    return launch_clustered(gnn_train_backward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
+                            smem_floats_bwd(threads) * 4, (cudaStream_t)stream);
+}

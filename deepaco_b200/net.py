@@ -3,8 +3,10 @@ tsp_nls/net.py and cvrp/net.py differ only in `feats` and the unused `par_net_ph
 pretrained/{tsp,tsp_nls,cvrp}/*.pt load unchanged.
 
 eval mode  -> one launch of the sm_100a kernel deepaco_gnn_forward (csrc/gnn.cu) per batch of graphs.
-train mode -> autograd-capable tensor ops (training of the network is listed under "next" in SURVEY.md 8f and
-              is not yet native).
+train mode -> deepaco_gnn_train_forward / deepaco_gnn_train_backward (csrc/gnn_train.cuh) behind a
+              torch.autograd.Function: batch-statistics BatchNorm, analytic backward, running statistics updated
+              as nn.BatchNorm1d does.  There is no tensor-op / CPU formulation in this package (the torch fp32
+              restatement used by the tests lives in oracle/net_torch.py).
 """
 from __future__ import annotations
 
@@ -44,19 +46,7 @@ class EmbNet(nn.Module):
         self.e_bns = nn.ModuleList([_WrappedBatchNorm(units) for _ in range(depth)])
 
     def forward(self, x, edge_index, edge_attr):
-        """Tensor-op formulation (used in train mode; tsp/net.py:27-45)."""
-        src, dst = edge_index[0], edge_index[1]
-        n = x.shape[0]
-        deg = torch.zeros(n, device=x.device, dtype=x.dtype).index_add_(0, src, torch.ones_like(src, dtype=x.dtype))
-        x = F.silu(self.v_lin0(x))
-        w = F.silu(self.e_lin0(edge_attr))
-        for i in range(self.depth):
-            msg = torch.sigmoid(w) * self.v_lins2[i](x)[dst]
-            agg = torch.zeros_like(x).index_add_(0, src, msg) / deg.clamp(min=1).unsqueeze(-1)
-            x_new = x + F.silu(self.v_bns[i](self.v_lins1[i](x) + agg))
-            w = w + F.silu(self.e_bns[i](self.e_lins0[i](w) + self.v_lins3[i](x)[src] + self.v_lins4[i](x)[dst]))
-            x = x_new
-        return w
+        raise _lib.DeepAcoError("EmbNet has no stand-alone forward in deepaco_b200: call Net.forward (fused kernels)")
 
 
 class MLP(nn.Module):
@@ -87,15 +77,20 @@ class ParNet(MLP):
         return super().forward(t).squeeze(dim=-1)
 
 
-def pack_weights(net: "Net") -> torch.Tensor:
+def pack_weights(net: "Net", for_training: bool = False) -> torch.Tensor:
     """Flat fp32 tensor in the layout csrc/gnn.cu expects:
     v_lin0 W[32][feats] b[32] | e_lin0 W[32] b[32] | 12 x { 4 x (W[32][32] b[32]) node linears 1..4 |
-    e_lins0 W b | v_bn gamma beta mean invstd | e_bn gamma beta mean invstd } | head lin0 W b | lin1 W b | lin2 W[32] b[1]"""
+    e_lins0 W b | v_bn gamma beta mean invstd | e_bn gamma beta mean invstd } | head lin0 W b | lin1 W b | lin2 W[32] b[1]
+    for_training: built with autograd-tracked ops (torch.cat routes the packed gradient back to the parameters);
+    the mean / invstd slots are zeros (training mode uses batch statistics)."""
     e = net.emb_net
     parts = [e.v_lin0.weight, e.v_lin0.bias, e.e_lin0.weight.reshape(-1), e.e_lin0.bias]
+    zeros = torch.zeros(2 * UNITS, dtype=torch.float32, device=e.v_lin0.weight.device) if for_training else None
 
     def bn(m):
         m = m.module
+        if for_training:
+            return [m.weight, m.bias, zeros]
         return [m.weight, m.bias, m.running_mean, torch.rsqrt(m.running_var + m.eps)]
 
     for i in range(e.depth):
@@ -104,9 +99,16 @@ def pack_weights(net: "Net") -> torch.Tensor:
         parts += [e.e_lins0[i].weight, e.e_lins0[i].bias] + bn(e.v_bns[i]) + bn(e.e_bns[i])
     h = net.par_net_heu.lins
     parts += [h[0].weight, h[0].bias, h[1].weight, h[1].bias, h[2].weight.reshape(-1), h[2].bias]
-    flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in parts]).contiguous()
-    assert flat.numel() == lib().deepaco_gnn_weight_count(e.feats)
+    if for_training:
+        flat = torch.cat([t.reshape(-1).to(torch.float32) for t in parts])
+    else:
+        flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in parts]).contiguous()
+    assert flat.numel() == weight_count(e.feats)
     return flat
+
+
+def weight_count(feats):
+    return UNITS * feats + 3 * UNITS + DEPTH * (5 * (UNITS * UNITS + UNITS) + 8 * UNITS) + 2 * (UNITS * UNITS + UNITS) + UNITS + 1
 
 
 def csr_by_source(edge_index, n_nodes):
@@ -170,6 +172,140 @@ def knn_heuristic_matrices(weights, feats, node_features, distances, k_sparse, e
     return dense
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# training mode (deepaco_gnn_train_forward / _backward)
+# ---------------------------------------------------------------------------------------------------------------
+def train_graph(edge_index, edge_attr, n_nodes):
+    """Graph arrays of deepaco_gnn_train_args for edge_index [B, 2, E], edge_attr [B, E(,1)]: edges sorted by source
+    (stable) with their CSR, and the same edges grouped by destination (stable) with their CSC."""
+    B, E = edge_index.shape[0], edge_index.shape[-1]
+    dev = edge_index.device
+    src, dst = edge_index[:, 0], edge_index[:, 1]
+    order = torch.argsort(src, dim=1, stable=True)
+    src_s, dst_s = torch.gather(src, 1, order), torch.gather(dst, 1, order)
+    attr_s = torch.gather(edge_attr.reshape(B, E).to(torch.float32), 1, order)
+    in_edges = torch.argsort(dst_s, dim=1, stable=True)
+
+    def ptrs(keys):
+        counts = torch.zeros((B, n_nodes), dtype=torch.int64, device=dev).scatter_add_(1, keys, torch.ones_like(keys))
+        out = torch.zeros((B, n_nodes + 1), dtype=torch.int32, device=dev)
+        out[:, 1:] = torch.cumsum(counts, 1)
+        return out
+
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    return {"row_ptr": ptrs(src_s), "src": i32(src_s), "dst": i32(dst_s), "attr": attr_s.contiguous(), "order": i32(order),
+            "col_ptr": ptrs(dst_s), "in_edges": i32(in_edges), "n": n_nodes, "E": E, "B": B}
+
+
+def train_buffers(B, n, E, device):
+    """Activations the forward saves for the backward, BatchNorm batch statistics and scratch (sizes: include/deepaco_b200.h)."""
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+    return {"xs": f(B, DEPTH + 1, n, UNITS), "ws": f(B, DEPTH + 1, E, UNITS), "zv": f(B, DEPTH, n, UNITS),
+            "ze": f(B, DEPTH, E, UNITS), "stats": f(B, DEPTH, 6, UNITS), "node_ws": f(B, n, 7 * UNITS),
+            "edge_ws": f(B, E, 2 * UNITS), "red": f(B, 36, 8, 128)}
+
+
+def train_args(x, graph, weights, bufs, feats, ctas, bn_eps, heu_out=None, grad_heu=None, grad_weights=None):
+    """Fill a deepaco_gnn_train_args struct; returns (struct, keep-alive list)."""
+    p = lambda t: None if t is None else t.data_ptr()
+    a = _lib.GnnTrainArgs(graph["n"], graph["E"], feats, graph["B"], ctas, bn_eps, p(x), p(graph["row_ptr"]), p(graph["src"]),
+                          p(graph["dst"]), p(graph["attr"]), p(graph["order"]), p(graph["col_ptr"]), p(graph["in_edges"]),
+                          p(weights), p(bufs["xs"]), p(bufs["ws"]), p(bufs["zv"]), p(bufs["ze"]), p(bufs["stats"]),
+                          p(bufs["node_ws"]), p(bufs["edge_ws"]), p(bufs["red"]), p(heu_out), p(grad_heu), p(grad_weights))
+    return a, [x, graph, weights, bufs, heu_out, grad_heu, grad_weights]
+
+
+def default_train_ctas(n_edges):
+    """Thread-block cluster size per graph (DEEPACO_GNN_CTAS overrides): more CTAs once the per-layer edge work
+    outweighs the extra cluster barriers."""
+    import os
+    env = os.environ.get("DEEPACO_GNN_CTAS")
+    if env:
+        return int(env)
+    return 1 if n_edges < 512 else (4 if n_edges < 4096 else 8)
+
+
+class _GnnTrain(torch.autograd.Function):
+    """heu [B, E], stats [B, 12, 6, 32] = f(packed weights, graph); gradient w.r.t. the packed weights only (graph inputs are data)."""
+
+    @staticmethod
+    def forward(ctx, flat, x, graph, feats, ctas, bn_eps):
+        import ctypes
+        dev = x.device
+        flat = flat.detach().contiguous()
+        bufs = train_buffers(graph["B"], graph["n"], graph["E"], dev)
+        heu = torch.empty((graph["B"], graph["E"]), dtype=torch.float32, device=dev)
+        a, keep = train_args(x, graph, flat, bufs, feats, ctas, bn_eps, heu_out=heu)
+        with torch.cuda.device(dev):
+            check(lib().deepaco_gnn_train_forward(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_train_forward")
+        ctx.state = (flat, x, graph, bufs, feats, ctas, bn_eps)
+        ctx.mark_non_differentiable(bufs["stats"])
+        return heu, bufs["stats"]
+
+    @staticmethod
+    def backward(ctx, g_heu, _g_stats):
+        import ctypes
+        flat, x, graph, bufs, feats, ctas, bn_eps = ctx.state
+        dev = x.device
+        g_heu = g_heu.to(torch.float32).contiguous()
+        grad = torch.zeros((graph["B"], ctas, flat.numel()), dtype=torch.float32, device=dev)
+        a, keep = train_args(x, graph, flat, bufs, feats, ctas, bn_eps, grad_heu=g_heu, grad_weights=grad)
+        with torch.cuda.device(dev):
+            check(lib().deepaco_gnn_train_backward(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_train_backward")
+        return grad.sum(dim=(0, 1)), None, None, None, None, None
+
+
+def gnn_train_forward(net, x, edge_index, edge_attr, ctas=None):
+    """Training-mode Net.forward for one graph or a batch ([B, ...] tensors with identical n and E; every graph is its
+    own forward call as far as BatchNorm is concerned).  Differentiable w.r.t. the parameters of `net`; updates the
+    BatchNorm running statistics like the sequence of per-graph calls would (tsp/net.py:41-44 with PyG BatchNorm)."""
+    batched = x.dim() == 3
+    if not batched:
+        x, edge_index, edge_attr = x[None], edge_index[None], edge_attr[None]
+    _lib.require_cuda(x, "pyg.x")
+    B, n = x.shape[0], x.shape[1]
+    graph = train_graph(edge_index, edge_attr, n)
+    e = net.emb_net
+    eps = float(e.v_bns[0].module.eps)
+    flat = pack_weights(net, for_training=True)
+    heu, stats = _GnnTrain.apply(flat, x.to(torch.float32).contiguous(), graph, e.feats,
+                                 ctas or default_train_ctas(graph["E"]), eps)
+    _update_running_stats(e, stats, n, graph["E"])
+    return heu if batched else heu[0]
+
+
+@torch.no_grad()
+def _update_running_stats(emb, stats, n, E):
+    """running_mean / running_var / num_batches_tracked exactly as nn.BatchNorm1d.forward does in training mode
+    (exponential moving average with the module's momentum, unbiased variance), one update per graph."""
+    mods = [m.module for m in emb.v_bns] + [m.module for m in emb.e_bns]
+    mods_on = [m for m in mods if m.track_running_stats and m.running_mean is not None]
+    if not mods_on:
+        return
+    for b in range(stats.shape[0]):
+        means, uvars, rms, rvs, moms, nbts = [], [], [], [], [], []
+        for l in range(DEPTH):
+            for m, base, cnt in ((emb.v_bns[l].module, 0, n), (emb.e_bns[l].module, 3, E)):
+                if not (m.track_running_stats and m.running_mean is not None):
+                    continue
+                nbts.append(m.num_batches_tracked)
+                mom = m.momentum if m.momentum is not None else 1.0 / float(m.num_batches_tracked + 1)   # cumulative average
+                means.append(stats[b, l, base])
+                uvars.append(stats[b, l, base + 2] * (cnt / max(cnt - 1, 1)))
+                rms.append(m.running_mean)
+                rvs.append(m.running_var)
+                moms.append(mom)
+        torch._foreach_add_(nbts, 1)
+        if len(set(moms)) == 1:
+            mom = moms[0]
+            torch._foreach_mul_(rms + rvs, 1.0 - mom)
+            torch._foreach_add_(rms + rvs, means + uvars, alpha=mom)
+        else:
+            for rm, rv, mu, uv, mom in zip(rms, rvs, means, uvars, moms):
+                rm.mul_(1.0 - mom).add_(mu, alpha=mom)
+                rv.mul_(1.0 - mom).add_(uv, alpha=mom)
+
+
 class Net(nn.Module):
     FEATS = 2          # tsp/net.py:9; subclasses in tsp_nls/ and cvrp/ use 1
     HAS_PHE_HEAD = True
@@ -191,8 +327,8 @@ class Net(nn.Module):
 
     def forward(self, pyg):
         x, edge_index, edge_attr = pyg.x, pyg.edge_index, pyg.edge_attr
-        if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            return self.par_net_heu(self.emb_net(x, edge_index, edge_attr))
+        if self.training:
+            return gnn_train_forward(self, x, edge_index, edge_attr)
         return gnn_forward(self._weights(), self.FEATS, x, edge_index, edge_attr)
 
     @torch.no_grad()

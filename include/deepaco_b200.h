@@ -177,6 +177,49 @@ int deepaco_gnn_forward(const float* x, const int32_t* row_ptr, const int32_t* d
                         int n_instances, float* node_ws, float* edge_ws, float* heu_out, float* dense_out,
                         float dense_eps, void* stream);
 
+/* ---- heuristic network, TRAINING mode: forward with batch-statistics BatchNorm, and its backward
+ * (Net.forward under net.train() as driven by train_instance: tsp/train.ipynb cell 1, tsp_nls/train.py:15-44,
+ * cvrp/train.py; PyG BatchNorm(32) == nn.BatchNorm1d over all nodes / all edges of the one graph, eps = bn_eps).
+ * Replaces the autograd graph torch builds through tsp/net.py:27-45,62-75 by two launches.
+ * Every instance b of the batch is an independent forward call (own batch statistics).
+ * Graph arrays as for deepaco_gnn_forward plus src_sorted int32 [B][E] (source of each sorted edge) and, for the
+ * backward pass, the same edges grouped by destination: col_ptr int32 [B][n+1], in_edges int32 [B][E] (indices into
+ * the source-sorted order).  ctas_per_instance in {1, 2, 4, 8}: thread-block cluster size cooperating on one graph.
+ * Buffers (fp32, device):  xs [B][13][n][32], ws [B][13][E][32], zv [B][12][n][32], ze [B][12][E][32] -- activations
+ * saved by the forward for the backward;  stats [B][12][6][32] -- per layer the batch mean, 1/sqrt(var + eps) and
+ * biased variance of the node BatchNorm, then of the edge BatchNorm (the caller updates running_mean / running_var
+ * from them);  node_ws [B][n][224], edge_ws [B][E][64] (backward only), red [B][36][8][128] -- scratch.
+ * forward:  heu_out [B][E] = Net.forward(pyg) per ORIGINAL edge id.
+ * backward: grad_heu [B][E] = dL/d heu_out;  grad_weights [B][ctas_per_instance][deepaco_gnn_weight_count(feats)],
+ *           zero-initialised by the caller, receives partial parameter gradients in the packed weight layout: the
+ *           gradient of instance b is the sum over its ctas_per_instance slices (running-stat slots stay 0). */
+typedef struct deepaco_gnn_train_args {
+    int32_t n_nodes, n_edges, feats, n_instances, ctas_per_instance;
+    float bn_eps;
+    const float* x;
+    const int32_t* row_ptr;
+    const int32_t* src_sorted;
+    const int32_t* dst_sorted;
+    const float* attr_sorted;
+    const int32_t* order;
+    const int32_t* col_ptr;
+    const int32_t* in_edges;
+    const float* weights;
+    float* xs;
+    float* ws;
+    float* zv;
+    float* ze;
+    float* stats;
+    float* node_ws;
+    float* edge_ws;
+    float* red;
+    float* heu_out;
+    const float* grad_heu;
+    float* grad_weights;
+} deepaco_gnn_train_args;
+int deepaco_gnn_train_forward(const deepaco_gnn_train_args* args, void* stream);
+int deepaco_gnn_train_backward(const deepaco_gnn_train_args* args, void* stream);
+
 /* ---- CVRP (cvrp/aco.py:106-205, adaptive = False) ----------------------------------------------
  * Node 0 is the depot; n_nodes = customers + 1; demand fp32 [B][n_nodes] (demand[0] = 0).
  * deepaco_cvrp_sample replaces ACO.gen_path + pick_move + update_visit_mask + update_capacity_mask +

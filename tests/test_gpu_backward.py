@@ -89,8 +89,8 @@ def test_train_instance_parameter_gradients_match_reference_pipeline():
     coords = torch.rand(n, 2, device=DEV)
     pyg, distances = gen_pyg_data(coords, k_sparse=8)
 
-    def loss_of(model, sampler):
-        heu_vec = model(pyg)
+    def loss_of(model, sampler, forward=lambda m: m(pyg)):
+        heu_vec = forward(model)
         heu_mat = model.reshape(pyg, heu_vec) + EPS
         costs, log_probs = sampler(heu_mat)
         baseline = costs.mean()
@@ -107,9 +107,10 @@ def test_train_instance_parameter_gradients_match_reference_pipeline():
 
     l1 = loss_of(net, mine)
     l1.backward()
-    l2 = loss_of(ref_net, reference)
+    from oracle import net_torch
+    l2 = loss_of(ref_net, reference, forward=lambda m: net_torch.net_forward(m, pyg))   # torch autograd through the restated ops
     l2.backward()
-    assert torch.allclose(l1, l2, rtol=1e-5)
+    assert torch.allclose(l1, l2, rtol=1e-4, atol=1e-5)     # native training-mode network vs torch ops: fp32 rounding only
     checked = 0
     # biases feeding a train-mode BatchNorm have an exactly-zero true gradient (pure rounding noise on both sides):
     # the absolute tolerance is therefore set from the largest gradient of the whole network

@@ -1,0 +1,161 @@
+"""K3t parity: training-mode heuristic network (batch-statistics BatchNorm) forward + backward on the B200
+(csrc/gnn_train.cuh through deepaco_gnn_train_forward / _backward) against
+  * the UNMODIFIED reference's train-mode output, parameter gradients and running statistics (goldens written by
+    tests/golden/make_golden_gnn_train.py), for every cluster size, and
+  * torch autograd through the restated ops (oracle/net_torch.py) on this device at the BASELINE graph sizes.
+Tolerances (fp32, different summation order): heuristic rtol 2e-4; gradients rtol 2e-3 with an absolute floor of
+2e-5 x the largest gradient (biases in front of a train-mode BatchNorm have an exactly-zero true gradient)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _net(kind, weights=None):
+    from deepaco_b200.net import load_npz_state_dict
+    if kind == "tsp":
+        from deepaco_b200.tsp.net import Net
+        weights = weights or "weights_tsp100"
+    elif kind == "tsp_nls":
+        from deepaco_b200.tsp_nls.net import Net
+        weights = weights or "weights_tsp_nls500"
+    else:
+        from deepaco_b200.cvrp.net import Net
+        weights = weights or "weights_cvrp100"
+    net = Net().to(DEV)
+    r = net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "tests", "golden", weights + ".npz"), DEV))
+    assert not r.missing_keys and not r.unexpected_keys
+    return net.train()
+
+
+def _pyg(g):
+    from deepaco_b200.net import Data
+    return Data(x=torch.from_numpy(g["x"]), edge_index=torch.from_numpy(g["edge_index"]),
+                edge_attr=torch.from_numpy(g["edge_attr"])).to(DEV)
+
+
+def _compare_grads(net, ref_grads, tag, rtol=2e-3):
+    gmax = max(float(v.abs().max()) for v in ref_grads.values() if v is not None)
+    checked = 0
+    for name, p in net.named_parameters():
+        want = ref_grads.get(name)
+        if want is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        assert torch.allclose(p.grad, want, rtol=rtol, atol=2e-5 * gmax), (tag, name, float((p.grad - want).abs().max()), gmax)
+        checked += 1
+    assert checked >= 70
+
+
+@pytest.mark.parametrize("kind,fixture", [("tsp", "tsp_n40_gnn_train_grads"), ("cvrp", "cvrp_n14_gnn_train_grads")])
+@pytest.mark.parametrize("ctas", [1, 2, 4, 8])
+def test_train_mode_matches_the_reference_goldens(golden, monkeypatch, kind, fixture, ctas):
+    monkeypatch.setenv("DEEPACO_GNN_CTAS", str(ctas))
+    g = golden(fixture)
+    net = _net(kind)
+    heu = net(_pyg(g))
+    assert heu.requires_grad
+    (heu * torch.from_numpy(g["c"]).to(DEV)).sum().backward()
+    assert torch.allclose(heu.detach().cpu(), torch.from_numpy(g["heu_vec"]), rtol=2e-4, atol=1e-7)
+    ref = {k[6:].replace("__", "."): torch.from_numpy(v).to(DEV) for k, v in g.items() if k.startswith("grad__")}
+    _compare_grads(net, ref, f"golden ctas={ctas}")
+    for name, buf in net.named_buffers():
+        want = g["buf__" + name.replace(".", "__")]
+        if name.endswith("num_batches_tracked"):
+            assert int(buf) == int(want), name
+        else:
+            assert torch.allclose(buf.cpu(), torch.from_numpy(want), rtol=1e-4, atol=1e-6), name
+
+
+def _baseline_graph(kind):
+    torch.manual_seed(11)
+    if kind == "tsp":            # C2: n = 100, k = 20
+        from deepaco_b200.tsp.utils import gen_pyg_data
+        return gen_pyg_data(torch.rand(100, 2, device=DEV), 20)[0]
+    if kind == "tsp_nls":        # C3: n = 500, k = 50
+        from deepaco_b200.tsp_nls.utils import gen_pyg_data
+        return gen_pyg_data(torch.rand(500, 2, device=DEV), 50, start_node=0)[0]
+    from deepaco_b200.cvrp.utils import gen_instance, gen_pyg_data          # C4: 100 customers, dense
+    demand, dist = gen_instance(100, DEV)
+    return gen_pyg_data(demand, dist, DEV)
+
+
+@pytest.mark.parametrize("kind", ["tsp", "tsp_nls", "cvrp"])
+def test_train_mode_matches_torch_autograd_at_baseline_sizes(kind):
+    from oracle import net_torch
+    pyg = _baseline_graph(kind)
+    net = _net(kind)
+    ref_net = copy.deepcopy(net)
+    torch.manual_seed(3)
+    c = torch.rand(pyg.edge_index.shape[1], device=DEV) - 0.3
+    heu = net(pyg)
+    (heu * c).sum().backward()
+    want = net_torch.net_forward(ref_net, pyg)
+    (want * c).sum().backward()
+    assert torch.allclose(heu.detach(), want.detach(), rtol=5e-4, atol=1e-7)
+    _compare_grads(net, {k: p.grad for k, p in ref_net.named_parameters()}, kind, rtol=5e-3)
+    for (name, b1), (_, b2) in zip(net.named_buffers(), ref_net.named_buffers()):
+        assert torch.allclose(b1.float(), b2.float(), rtol=1e-4, atol=1e-6), name
+
+
+def test_train_mode_is_deterministic_and_batches_are_independent_calls():
+    from deepaco_b200.net import gnn_train_forward
+    from deepaco_b200.tsp.utils import gen_pyg_data
+    torch.manual_seed(5)
+    coords = torch.rand(3, 100, 2, device=DEV)
+    graphs = [gen_pyg_data(coords[b], 20)[0] for b in range(3)]
+    net = _net("tsp")
+    state = copy.deepcopy(net.state_dict())
+    singles, grads = [], []
+    for g in graphs:                                        # the reference: one forward call per instance
+        net.zero_grad()
+        h = net(g)
+        h.sum().backward()
+        singles.append(h.detach())
+        grads.append(torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None]))
+    seq_buffers = {k: v.clone() for k, v in net.named_buffers()}
+    net.load_state_dict(state)
+    net.zero_grad()
+    x = torch.stack([g.x for g in graphs])
+    ei = torch.stack([g.edge_index for g in graphs])
+    ea = torch.stack([g.edge_attr for g in graphs])
+    hb = gnn_train_forward(net, x, ei, ea)
+    hb.sum().backward()
+    for b in range(3):
+        assert torch.equal(hb[b].detach(), singles[b])      # same kernel, same reduction order: bit-identical
+    gb = torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None])
+    assert torch.allclose(gb, sum(grads), rtol=1e-4, atol=1e-6 * float(gb.abs().max()))
+    for k, v in net.named_buffers():                        # running statistics == the sequence of per-graph updates
+        assert torch.allclose(v.float(), seq_buffers[k].float(), rtol=1e-5, atol=1e-7), k
+    # run-to-run determinism (no atomics anywhere on this path)
+    net.load_state_dict(state)
+    net.zero_grad()
+    hb2 = gnn_train_forward(net, x, ei, ea)
+    hb2.sum().backward()
+    assert torch.equal(hb2, hb)
+    assert torch.equal(torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None]), gb)
+
+
+def test_train_mode_rejects_cpu_tensors_and_frozen_backbone_gets_no_gradient():
+    from deepaco_b200._lib import DeepAcoError
+    from deepaco_b200.net import Data
+    from deepaco_b200.tsp.utils import gen_pyg_data
+    net = _net("tsp")
+    pyg = gen_pyg_data(torch.rand(30, 2, device=DEV), 6)[0]
+    with pytest.raises(DeepAcoError):
+        net(Data(x=pyg.x.cpu(), edge_index=pyg.edge_index.cpu(), edge_attr=pyg.edge_attr.cpu()))
+    net.freeze_gnn()                                         # tsp/net.py:90-92
+    net(pyg).sum().backward()
+    assert all(p.grad is None for p in net.emb_net.parameters())
+    assert all(p.grad is not None for n_, p in net.par_net_heu.named_parameters() if n_ != "_dummy")
+    with torch.no_grad():                                    # forward only: no autograd graph, statistics still updated
+        before = net.emb_net.v_bns[0].module.num_batches_tracked.item()
+        out = net(pyg)
+        assert not out.requires_grad and net.emb_net.v_bns[0].module.num_batches_tracked.item() == before + 1
