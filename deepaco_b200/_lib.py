@@ -72,7 +72,7 @@ class GnnTrainArgs(C.Structure):
     _fields_ = [("n_nodes", _i32), ("n_edges", _i32), ("feats", _i32), ("n_instances", _i32), ("ctas_per_instance", _i32),
                 ("bn_eps", _f32), ("x", _vp), ("row_ptr", _vp), ("src_sorted", _vp), ("dst_sorted", _vp), ("attr_sorted", _vp),
                 ("order", _vp), ("col_ptr", _vp), ("in_edges", _vp), ("weights", _vp), ("xs", _vp), ("ws", _vp), ("zv", _vp),
-                ("ze", _vp), ("stats", _vp), ("node_ws", _vp), ("edge_ws", _vp), ("red", _vp), ("heu_out", _vp),
+                ("ze", _vp), ("stats", _vp), ("node_ws", _vp), ("edge_ws", _vp), ("red", _vp), ("sync_ws", _vp), ("heu_out", _vp),
                 ("grad_heu", _vp), ("grad_weights", _vp)]
 
 

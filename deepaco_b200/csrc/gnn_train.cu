@@ -1,4 +1,4 @@
-// C ABI of the training-mode heuristic network (kernels in gnn_train.cuh): one thread-block cluster per graph.
+// C ABI of the training-mode heuristic network (kernels in gnn_train.cuh): one group of CTAs per graph.
 #include "gnn_train.cuh"
 #include "gnn_train_args.h"
 #include "host_util.h"
@@ -6,24 +6,43 @@
 using namespace deepaco;
 using namespace deepaco::gnnt;
 
+// groups of <= 8 CTAs: one thread-block cluster per graph.  Larger groups: cooperative launches (co-residency is what
+// makes the arrival-counter barrier safe), as many graphs per launch as fit on the device at once.
 template <class Kernel>
-static int launch_clustered(Kernel kernel, const TrainParams& p, int n_instances, int ctas, int threads, size_t smem,
-                            cudaStream_t st) {
+static int launch_groups(Kernel kernel, TrainParams p, int n_instances, int ctas, int threads, size_t smem, cudaStream_t st) {
     DACO_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_instances * ctas));
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)ctas;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DACO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
-    DACO_CHECK_LAUNCH();
+    if (p.grid_ctas == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_instances * ctas));
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)ctas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DACO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+        DACO_CHECK_LAUNCH();
+        return DEEPACO_OK;
+    }
+    const DeviceInfo* di = device_info();
+    DACO_CHECK_ARG(di != nullptr, "deepaco_gnn_train: no CUDA device");
+    int per_sm = 0;
+    DACO_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    const int resident = per_sm * di->sm_count;
+    DACO_CHECK_ARG(resident >= ctas, "deepaco_gnn_train: %d CTAs per graph cannot be co-resident on this device (%d fit)", ctas, resident);
+    const int per_launch = resident / ctas;
+    DACO_CHECK_CUDA(cudaMemsetAsync(p.sync_ctr, 0, sizeof(unsigned) * (size_t)n_instances, st));
+    for (int b0 = 0; b0 < n_instances; b0 += per_launch) {
+        const int nb = n_instances - b0 < per_launch ? n_instances - b0 : per_launch;
+        p.b0 = b0;
+        void* args[] = {&p};
+        DACO_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)(nb * ctas)), dim3((unsigned)threads), args, smem, st));
+        DACO_CHECK_LAUNCH();
+    }
     return DEEPACO_OK;
 }
 
@@ -31,7 +50,7 @@ extern "C" int deepaco_gnn_train_forward(const deepaco_gnn_train_args* a, void* 
     TrainParams p;
     if (const char* err = gnn_train_params(a, false, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_forward: %s", err);
     const int threads = a->n_edges >= 2048 * a->ctas_per_instance ? 512 : 256;
-    return launch_clustered(gnn_train_forward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
+    return launch_groups(gnn_train_forward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
                             smem_floats_fwd(threads) * 4, (cudaStream_t)stream);
 }
 
@@ -39,6 +58,6 @@ extern "C" int deepaco_gnn_train_backward(const deepaco_gnn_train_args* a, void*
     TrainParams p;
     if (const char* err = gnn_train_params(a, true, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_backward: %s", err);
     const int threads = 256;
-    return launch_clustered(gnn_train_backward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
+    return launch_groups(gnn_train_backward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
                             smem_floats_bwd(threads) * 4, (cudaStream_t)stream);
 }

@@ -3,9 +3,10 @@
 // tsp/train.ipynb cell 1 / tsp_nls/train.py:15-44; PyG BatchNorm == nn.BatchNorm1d over all nodes / all edges of
 // the one graph of a forward call, biased variance, eps 1e-5).
 //
-// One thread-block CLUSTER per instance (1, 2, 4 or 8 CTAs): rows (nodes / edges) are split over the cluster's
-// threads, the per-feature BatchNorm reductions go CTA (shared memory, fixed order) -> cluster (global scratch,
-// fixed rank order) so results do not depend on timing, and barrier.cluster orders the phases.  No atomics:
+// One GROUP of CTAs per instance: a thread-block cluster (2, 4, 8 CTAs; hardware barrier.cluster) or, for large graphs,
+// 16 / 32 / 64 co-resident CTAs of a cooperative launch synchronised through a per-instance arrival counter.
+// Rows (nodes / edges) are split over the group's threads, the per-feature BatchNorm reductions go CTA (shared memory,
+// fixed order) -> group (global scratch, fixed rank order) so results do not depend on timing.  No atomics on data:
 // the gather side of every scatter is walked through the CSR (by source) / CSC (by destination) edge lists.
 // The 32x32 linears are fp32 FMAs with the weights broadcast from shared memory; weight gradients are
 // tile-staged outer products (4x4 register blocks) reduced in a fixed order.
@@ -29,9 +30,9 @@ constexpr int kLayerFloats = 5 * LIN + 8 * U;  // 4 node linears | edge linear |
 constexpr int kDepth = 12;
 constexpr int kHeadFloats = 2 * LIN + U + 1;
 constexpr int TS = 36;                         // tile row stride in floats (16-byte aligned, conflict-free float4 rows)
-constexpr int kRedStride = 128;                // floats per (slot, rank) of the cluster reduction scratch
+constexpr int kRedStride = 128;                // floats per (slot, rank) of the group reduction scratch
 constexpr int kRedSlots = 3 * kDepth;          // forward uses 2 per layer, backward 1 per layer
-constexpr int kMaxCtas = 8;
+constexpr int kMaxCtas = 64;
 constexpr int kStatFloats = 6 * U;             // per layer: mean_v, invstd_v, var_v, mean_e, invstd_e, var_e
 
 #ifndef DEEPACO_CPU_EMU
@@ -47,6 +48,21 @@ __device__ __forceinline__ unsigned cta_count() {
 }
 __device__ __forceinline__ void cluster_barrier() {   // all threads of all CTAs of the cluster; release / acquire
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// arrival-counter barrier over the `ncta` co-resident CTAs of one instance (cooperative launch); *ctr starts at 0 and
+// only grows: the k-th barrier completes when it reaches k * ncta.
+__device__ __forceinline__ void counter_barrier(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
 }
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -70,8 +86,11 @@ struct TrainParams {
     float* ZE;                // [B][12][E][32]  pre-BatchNorm edge activations
     float* stats;             // [B][12][6][32]  batch mean / invstd / biased var, nodes then edges
     float* node_ws;           // [B][n][7*32] scratch: fwd x1|x2|x3|x4 ; bwd x2|GX|GZV|G1|G2|G3|G4
-    float* edge_ws;           // [B][E][2*32] scratch (backward): GW | GZ
-    float* red;               // [B][kRedSlots][kMaxCtas][kRedStride] cluster reduction scratch
+    float* edge_ws;           // [B][E][3*32] scratch (backward): GW | GZ | GM
+    float* red;               // [B][kRedSlots][kMaxCtas][kRedStride] group reduction scratch
+    unsigned* sync_ctr;       // [B] arrival counters (zero before the launch); used when grid_ctas > 0
+    int grid_ctas;            // 0: the group is the thread-block cluster; > 0: CTAs per instance of a cooperative launch
+    int b0;                   // first instance of this launch
     float* out;               // forward:  [B][E] heuristic per ORIGINAL edge id
     const float* g_out;       // backward: [B][E] gradient w.r.t. `out`
     float* grad_w;            // backward: [B][ctas][weight_count] partial parameter gradients (zero-initialised by the caller)
@@ -122,9 +141,24 @@ __device__ __forceinline__ void store_row(float* __restrict__ dst, const float (
 struct Cta {
     int tid, nth;
     unsigned rank, ncta;
-    int gt, gn;          // cluster-wide thread index / thread count
-    __device__ __forceinline__ void sync_all() const {
-        if (ncta == 1) __syncthreads(); else cluster_barrier();
+    int gt, gn;          // group-wide thread index / thread count
+    int b;               // instance
+    unsigned* ctr;       // arrival counter of this instance (cooperative-launch groups), else NULL
+    unsigned epoch;      // barriers passed so far
+    __device__ __forceinline__ void init(const int grid_ctas, unsigned* sync_ctr, int b0) {
+        tid = threadIdx.x; nth = blockDim.x;
+        if (grid_ctas > 0) { ncta = (unsigned)grid_ctas; rank = blockIdx.x % ncta; }
+        else { ncta = cta_count(); rank = cta_rank(); }
+        b = b0 + (int)(blockIdx.x / ncta);
+        ctr = grid_ctas > 0 ? sync_ctr + b : nullptr;
+        epoch = 0;
+        gt = (int)rank * nth + tid; gn = (int)ncta * nth;
+    }
+    // all threads of all CTAs of the group; orders global-memory accesses across it
+    __device__ __forceinline__ void sync_all() {
+        if (ncta == 1) __syncthreads();
+        else if (ctr) counter_barrier(ctr, ++epoch * ncta);
+        else cluster_barrier();
     }
 };
 
@@ -162,11 +196,11 @@ __device__ __forceinline__ void cta_colsum_scalar(const Cta& c, float v, float* 
     }
     __syncthreads();
 }
-// S[K*32] holds this CTA's sums; on return it holds the cluster-wide sums (identical bits in every CTA).
-__device__ __forceinline__ void cluster_sum(const Cta& c, float* S, int K, float* red_slot) {
+// S[K*32] holds this CTA's sums; on return it holds the group-wide sums (identical bits in every CTA).
+__device__ __forceinline__ void cluster_sum(Cta& c, float* S, int K, float* red_slot) {
     if (c.ncta == 1) return;
     if (c.tid < K * U) red_slot[c.rank * kRedStride + c.tid] = S[c.tid];
-    cluster_barrier();
+    c.sync_all();
     if (c.tid < K * U) {
         float t = 0.f;
         for (unsigned r = 0; r < c.ncta; ++r) t += ld_cg(red_slot + r * kRedStride + c.tid);
@@ -263,9 +297,8 @@ inline size_t smem_floats_bwd(int nth) {
 __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParams p) {
     DACO_DYN_SMEM(smem_raw);
     Cta c;
-    c.tid = threadIdx.x; c.nth = blockDim.x; c.rank = cta_rank(); c.ncta = cta_count();
-    c.gt = (int)c.rank * c.nth + c.tid; c.gn = (int)c.ncta * c.nth;
-    const int b = blockIdx.x / (int)c.ncta;
+    c.init(p.grid_ctas, p.sync_ctr, p.b0);
+    const int b = c.b;
     const Smem s = carve(reinterpret_cast<float*>(smem_raw), c.nth);
     const int n = p.n, E = p.E, F = p.feats, tid = c.tid, nth = c.nth;
     const int32_t* rp = p.row_ptr + (size_t)b * (n + 1);
@@ -330,7 +363,20 @@ __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParam
             const int i = t / U, f = t % U;
             const int e0 = rp[i], e1 = rp[i + 1];
             float a = 0.f;
-            for (int e = e0; e < e1; ++e) a += sigmoid_f(ld_cg(Wl + (size_t)e * U + f)) * ld_cg(X2 + (size_t)dsts[e] * U + f);
+            int e = e0;
+            for (; e + 8 <= e1; e += 8) {                      // 8 independent gathers in flight; same summation order
+                int d[8];
+                float wv[8], xv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = dsts[e + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wv[j] = ld_cg(Wl + (size_t)(e + j) * U + f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xv[j] = ld_cg(X2 + (size_t)d[j] * U + f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a += sigmoid_f(wv[j]) * xv[j];
+            }
+            for (; e < e1; ++e) a += sigmoid_f(ld_cg(Wl + (size_t)e * U + f)) * ld_cg(X2 + (size_t)dsts[e] * U + f);
             const int deg = e1 - e0;
             const float z = ld_cg(X1 + t) + a / (float)(deg > 0 ? deg : 1);
             Zv[t] = z;
@@ -425,9 +471,8 @@ __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParam
 __global__ void __launch_bounds__(256) gnn_train_backward_kernel(const TrainParams p) {
     DACO_DYN_SMEM(smem_raw);
     Cta c;
-    c.tid = threadIdx.x; c.nth = blockDim.x; c.rank = cta_rank(); c.ncta = cta_count();
-    c.gt = (int)c.rank * c.nth + c.tid; c.gn = (int)c.ncta * c.nth;
-    const int b = blockIdx.x / (int)c.ncta;
+    c.init(p.grid_ctas, p.sync_ctr, p.b0);
+    const int b = c.b;
     const Smem s = carve(reinterpret_cast<float*>(smem_raw), c.nth);
     const int n = p.n, E = p.E, F = p.feats, tid = c.tid, nth = c.nth;
     const int32_t* rp = p.row_ptr + (size_t)b * (n + 1);
@@ -441,8 +486,8 @@ __global__ void __launch_bounds__(256) gnn_train_backward_kernel(const TrainPara
     const float* ZE = p.ZE + (size_t)b * kDepth * E * U;
     float* NW = p.node_ws + (size_t)b * n * 7 * U;
     float* X2 = NW, *GX = NW + (size_t)n * U, *GZV = NW + (size_t)2 * n * U, *G14 = NW + (size_t)3 * n * U;   // G14: [4][n][32]
-    float* GW = p.edge_ws + (size_t)b * E * 2 * U;
-    float* GZ = GW + (size_t)E * U;
+    float* GW = p.edge_ws + (size_t)b * E * 3 * U;
+    float* GZ = GW + (size_t)E * U, *GM = GW + (size_t)2 * E * U;
     float* red = p.red + (size_t)b * kRedSlots * kMaxCtas * kRedStride;
     float* grad = p.grad_w + ((size_t)b * c.ncta + c.rank) * p.wc;     // this CTA's partial gradient buffer
     const int off_layers = U * F + 3 * U;
@@ -632,20 +677,42 @@ __global__ void __launch_bounds__(256) gnn_train_backward_kernel(const TrainPara
             load_row(X2 + (size_t)j * U, xj);
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const float sg = sigmoid_f(w[k]);
-                g[k] = fmaf(gi[k] * idg * xj[k], sg * (1.0f - sg), g[k]);
+                const float sg = sigmoid_f(w[k]), m = gi[k] * idg;
+                g[k] = fmaf(m * xj[k], sg * (1.0f - sg), g[k]);
+                gi[k] = m * sg;                                            // message gradient towards x2[dst]
             }
             store_row(GW + (size_t)e * U, g);
+            store_row(GM + (size_t)e * U, gi);
         }
+        c.sync_all();                                          // GM complete
         for (int t = c.gt; t < n * U; t += c.gn) {
             const int i = t / U, f = t % U;
             float g3 = 0.f, g4 = 0.f, g2 = 0.f;
-            for (int e = rp[i]; e < rp[i + 1]; ++e) g3 += ld_cg(GZ + (size_t)e * U + f);
-            for (int q = cp[i]; q < cp[i + 1]; ++q) {
-                const int e = ine[q], u = srcs[e];
-                const int deg = rp[u + 1] - rp[u];
-                g4 += ld_cg(GZ + (size_t)e * U + f);
-                g2 += ld_cg(GZV + (size_t)u * U + f) / (float)(deg > 0 ? deg : 1) * sigmoid_f(ld_cg(Wl + (size_t)e * U + f));
+            int e = rp[i];
+            const int e1 = rp[i + 1], q1 = cp[i + 1];
+            for (; e + 8 <= e1; e += 8) {                      // 8 independent loads in flight; same summation order
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = ld_cg(GZ + (size_t)(e + j) * U + f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g3 += v[j];
+            }
+            for (; e < e1; ++e) g3 += ld_cg(GZ + (size_t)e * U + f);
+            int q = cp[i];
+            for (; q + 8 <= q1; q += 8) {
+                int ie[8];
+                float v[8], m[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ie[j] = ine[q + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] = ld_cg(GZ + (size_t)ie[j] * U + f); m[j] = ld_cg(GM + (size_t)ie[j] * U + f); }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { g4 += v[j]; g2 += m[j]; }
+            }
+            for (; q < q1; ++q) {
+                const int ie = ine[q];
+                g4 += ld_cg(GZ + (size_t)ie * U + f);
+                g2 += ld_cg(GM + (size_t)ie * U + f);
             }
             G14[t] = ld_cg(GZV + t);
             G14[(size_t)n * U + t] = g2;

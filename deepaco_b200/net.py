@@ -94,9 +94,18 @@ def pack_weights(net: "Net", for_training: bool = False) -> torch.Tensor:
         return [m.weight, m.bias, m.running_mean, torch.rsqrt(m.running_var + m.eps)]
 
     for i in range(e.depth):
+        layer = []
         for lins in (e.v_lins1, e.v_lins2, e.v_lins3, e.v_lins4):
-            parts += [lins[i].weight, lins[i].bias]
-        parts += [e.e_lins0[i].weight, e.e_lins0[i].bias] + bn(e.v_bns[i]) + bn(e.e_bns[i])
+            layer += [lins[i].weight, lins[i].bias]
+        layer += [e.e_lins0[i].weight, e.e_lins0[i].bias] + bn(e.v_bns[i]) + bn(e.e_bns[i])
+        if for_training and i == e.depth - 1:
+            # the last layer's node update never reaches the output (EmbNet.forward returns w, tsp/net.py:45): autograd
+            # leaves .grad of v_lins1/2[11] and v_bns[11] at None in the reference, so they must not receive zeros here
+            # (an optimiser with weight decay treats None and 0 differently)
+            dead = {id(e.v_lins1[i].weight), id(e.v_lins1[i].bias), id(e.v_lins2[i].weight), id(e.v_lins2[i].bias),
+                    id(e.v_bns[i].module.weight), id(e.v_bns[i].module.bias)}
+            layer = [t.detach() if id(t) in dead else t for t in layer]
+        parts += layer
     h = net.par_net_heu.lins
     parts += [h[0].weight, h[0].bias, h[1].weight, h[1].bias, h[2].weight.reshape(-1), h[2].bias]
     if for_training:
@@ -202,7 +211,8 @@ def train_buffers(B, n, E, device):
     f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
     return {"xs": f(B, DEPTH + 1, n, UNITS), "ws": f(B, DEPTH + 1, E, UNITS), "zv": f(B, DEPTH, n, UNITS),
             "ze": f(B, DEPTH, E, UNITS), "stats": f(B, DEPTH, 6, UNITS), "node_ws": f(B, n, 7 * UNITS),
-            "edge_ws": f(B, E, 2 * UNITS), "red": f(B, 36, 8, 128)}
+            "edge_ws": f(B, E, 3 * UNITS), "red": f(B, 36, 64, 128),
+            "sync_ws": torch.zeros(B, dtype=torch.int32, device=device)}
 
 
 def train_args(x, graph, weights, bufs, feats, ctas, bn_eps, heu_out=None, grad_heu=None, grad_weights=None):
@@ -211,18 +221,18 @@ def train_args(x, graph, weights, bufs, feats, ctas, bn_eps, heu_out=None, grad_
     a = _lib.GnnTrainArgs(graph["n"], graph["E"], feats, graph["B"], ctas, bn_eps, p(x), p(graph["row_ptr"]), p(graph["src"]),
                           p(graph["dst"]), p(graph["attr"]), p(graph["order"]), p(graph["col_ptr"]), p(graph["in_edges"]),
                           p(weights), p(bufs["xs"]), p(bufs["ws"]), p(bufs["zv"]), p(bufs["ze"]), p(bufs["stats"]),
-                          p(bufs["node_ws"]), p(bufs["edge_ws"]), p(bufs["red"]), p(heu_out), p(grad_heu), p(grad_weights))
+                          p(bufs["node_ws"]), p(bufs["edge_ws"]), p(bufs["red"]), p(bufs["sync_ws"]), p(heu_out), p(grad_heu), p(grad_weights))
     return a, [x, graph, weights, bufs, heu_out, grad_heu, grad_weights]
 
 
 def default_train_ctas(n_edges):
-    """Thread-block cluster size per graph (DEEPACO_GNN_CTAS overrides): more CTAs once the per-layer edge work
-    outweighs the extra cluster barriers."""
+    """CTAs cooperating on one graph (DEEPACO_GNN_CTAS overrides): a thread-block cluster up to 8, a cooperative
+    launch of 32 / 64 CTAs once the per-layer edge work outweighs the slower arrival-counter barrier."""
     import os
     env = os.environ.get("DEEPACO_GNN_CTAS")
     if env:
         return int(env)
-    return 1 if n_edges < 512 else (4 if n_edges < 4096 else 8)
+    return 1 if n_edges < 512 else (8 if n_edges < 4096 else (32 if n_edges < 16384 else 64))
 
 
 class _GnnTrain(torch.autograd.Function):
@@ -282,16 +292,19 @@ def _update_running_stats(emb, stats, n, E):
     mods_on = [m for m in mods if m.track_running_stats and m.running_mean is not None]
     if not mods_on:
         return
+    unbiased = stats.clone()                                   # biased -> unbiased variance (nn.BatchNorm1d's running_var)
+    unbiased[:, :, 2] *= n / max(n - 1, 1)
+    unbiased[:, :, 5] *= E / max(E - 1, 1)
     for b in range(stats.shape[0]):
         means, uvars, rms, rvs, moms, nbts = [], [], [], [], [], []
         for l in range(DEPTH):
-            for m, base, cnt in ((emb.v_bns[l].module, 0, n), (emb.e_bns[l].module, 3, E)):
+            for m, base in ((emb.v_bns[l].module, 0), (emb.e_bns[l].module, 3)):
                 if not (m.track_running_stats and m.running_mean is not None):
                     continue
                 nbts.append(m.num_batches_tracked)
                 mom = m.momentum if m.momentum is not None else 1.0 / float(m.num_batches_tracked + 1)   # cumulative average
-                means.append(stats[b, l, base])
-                uvars.append(stats[b, l, base + 2] * (cnt / max(cnt - 1, 1)))
+                means.append(unbiased[b, l, base])
+                uvars.append(unbiased[b, l, base + 2])
                 rms.append(m.running_mean)
                 rvs.append(m.running_var)
                 moms.append(mom)

@@ -184,11 +184,14 @@ int deepaco_gnn_forward(const float* x, const int32_t* row_ptr, const int32_t* d
  * Every instance b of the batch is an independent forward call (own batch statistics).
  * Graph arrays as for deepaco_gnn_forward plus src_sorted int32 [B][E] (source of each sorted edge) and, for the
  * backward pass, the same edges grouped by destination: col_ptr int32 [B][n+1], in_edges int32 [B][E] (indices into
- * the source-sorted order).  ctas_per_instance in {1, 2, 4, 8}: thread-block cluster size cooperating on one graph.
+ * the source-sorted order).  ctas_per_instance: CTAs cooperating on one graph -- 1, or a thread-block cluster of 2 / 4 / 8
+ * (hardware cluster barrier), or 16 / 32 / 64 co-resident CTAs of a cooperative launch (arrival-counter barrier; instances
+ * are launched in as many waves as co-residency requires).
  * Buffers (fp32, device):  xs [B][13][n][32], ws [B][13][E][32], zv [B][12][n][32], ze [B][12][E][32] -- activations
  * saved by the forward for the backward;  stats [B][12][6][32] -- per layer the batch mean, 1/sqrt(var + eps) and
  * biased variance of the node BatchNorm, then of the edge BatchNorm (the caller updates running_mean / running_var
- * from them);  node_ws [B][n][224], edge_ws [B][E][64] (backward only), red [B][36][8][128] -- scratch.
+ * from them);  node_ws [B][n][224], edge_ws [B][E][96] (backward only), red [B][36][64][128], sync_ws uint32 [B]
+ * (zeroed by the call) -- scratch.
  * forward:  heu_out [B][E] = Net.forward(pyg) per ORIGINAL edge id.
  * backward: grad_heu [B][E] = dL/d heu_out;  grad_weights [B][ctas_per_instance][deepaco_gnn_weight_count(feats)],
  *           zero-initialised by the caller, receives partial parameter gradients in the packed weight layout: the
@@ -213,6 +216,7 @@ typedef struct deepaco_gnn_train_args {
     float* node_ws;
     float* edge_ws;
     float* red;
+    uint32_t* sync_ws;
     float* heu_out;
     const float* grad_heu;
     float* grad_weights;

@@ -6,6 +6,7 @@
 // placement are checked against torch autograd without a GPU.  Nothing under deepaco_b200/ includes or loads this.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -88,6 +89,14 @@ namespace gnnt {
 static inline unsigned cta_rank() { return emu::ctx.rank; }
 static inline unsigned cta_count() { return emu::ctx.ncta; }
 static inline void cluster_barrier() { pthread_barrier_wait(emu::ctx.cluster_bar); }
+static inline void counter_barrier(unsigned* ctr, unsigned target) {   // same protocol as the device version
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __atomic_fetch_add(ctr, 1u, __ATOMIC_ACQ_REL);
+        while (__atomic_load_n(ctr, __ATOMIC_ACQUIRE) < target) sched_yield();
+    }
+    __syncthreads();
+}
 static inline float ld_cg(const float* p) { return *p; }
 static inline float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 }  // namespace gnnt

@@ -10,6 +10,7 @@ using namespace deepaco::gnnt;
 extern "C" const char* emu_gnn_train_forward(const deepaco_gnn_train_args* a, int threads) {
     TrainParams p;
     if (const char* err = gnn_train_params(a, false, p)) return err;
+    memset(a->sync_ws, 0, sizeof(uint32_t) * a->n_instances);
     emu::launch(gnn_train_forward_kernel, p, a->n_instances, a->ctas_per_instance, threads, smem_floats_fwd(threads) * 4);
     return nullptr;
 }
@@ -17,6 +18,7 @@ extern "C" const char* emu_gnn_train_forward(const deepaco_gnn_train_args* a, in
 extern "C" const char* emu_gnn_train_backward(const deepaco_gnn_train_args* a, int threads) {
     TrainParams p;
     if (const char* err = gnn_train_params(a, true, p)) return err;
+    memset(a->sync_ws, 0, sizeof(uint32_t) * a->n_instances);
     emu::launch(gnn_train_backward_kernel, p, a->n_instances, a->ctas_per_instance, threads, smem_floats_bwd(threads) * 4);
     return nullptr;
 }

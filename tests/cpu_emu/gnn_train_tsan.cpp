@@ -33,13 +33,15 @@ int main(int argc, char** argv) {
     for (auto& v : attr) v = uni(rng) + 0.5f;
     for (auto& v : g_heu) v = uni(rng);
     std::vector<float> xs((size_t)B * 13 * n * 32), ws((size_t)B * 13 * E * 32), zv((size_t)B * 12 * n * 32), ze((size_t)B * 12 * E * 32),
-        stats((size_t)B * 12 * 6 * 32), node_ws((size_t)B * n * 224), edge_ws((size_t)B * E * 64), red((size_t)B * 36 * 8 * 128),
+        stats((size_t)B * 12 * 6 * 32), node_ws((size_t)B * n * 224), edge_ws((size_t)B * E * 96), red((size_t)B * 36 * 64 * 128),
         heu((size_t)B * E), grad((size_t)B * ctas * wc, 0.f);
     deepaco_gnn_train_args a = {};
     a.n_nodes = n; a.n_edges = E; a.feats = F; a.n_instances = B; a.ctas_per_instance = ctas; a.bn_eps = 1e-5f;
     a.x = x.data(); a.row_ptr = row_ptr_b.data(); a.src_sorted = src_b.data(); a.dst_sorted = dst_b.data(); a.attr_sorted = attr.data();
     a.order = order_b.data(); a.col_ptr = col_ptr_b.data(); a.in_edges = in_b.data(); a.weights = weights.data();
     a.xs = xs.data(); a.ws = ws.data(); a.zv = zv.data(); a.ze = ze.data(); a.stats = stats.data(); a.node_ws = node_ws.data();
+    std::vector<uint32_t> sync_ws(B, 0);
+    a.sync_ws = sync_ws.data();
     a.edge_ws = edge_ws.data(); a.red = red.data(); a.heu_out = heu.data(); a.grad_heu = g_heu.data(); a.grad_weights = grad.data();
     if (const char* err = emu_gnn_train_forward(&a, nth_f)) { printf("forward: %s\n", err); return 2; }
     if (const char* err = emu_gnn_train_backward(&a, nth_b)) { printf("backward: %s\n", err); return 2; }

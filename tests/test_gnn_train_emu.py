@@ -65,7 +65,7 @@ def _check_against_golden(net, g, heu, grads, bufs, tag):
     for name, _ in net.named_parameters():
         key = "grad__" + name.replace(".", "__")
         if key not in g:
-            assert grads.get(name) is None or float(grads[name].abs().max()) == 0.0, name
+            assert grads.get(name) is None, name                   # None in the reference -> None here (not zeros)
             continue
         assert torch.allclose(grads[name], torch.from_numpy(g[key]), rtol=2e-3, atol=2e-5 * gmax), (tag, name)
         checked += 1
@@ -101,7 +101,8 @@ def _emu_run(emu, net, pyg, c, ctas, threads_f, threads_b, n_copies=1):
     w = flat.detach().contiguous()
     bufs = N.train_buffers(n_copies, n, graph["E"], "cpu")
     for t in bufs.values():
-        t.fill_(float("nan"))                      # anything read before it is written poisons the result
+        if t.is_floating_point():
+            t.fill_(float("nan"))                      # anything read before it is written poisons the result
     heu = torch.full((n_copies, graph["E"]), float("nan"))
     eps = float(net.emb_net.v_bns[0].module.eps)
     a, keep = N.train_args(x, graph, w, bufs, net.emb_net.feats, ctas, eps, heu_out=heu)
@@ -117,7 +118,7 @@ def _emu_run(emu, net, pyg, c, ctas, threads_f, threads_b, n_copies=1):
 
 
 @pytest.mark.parametrize("kind,fixture", CASES)
-@pytest.mark.parametrize("ctas,threads_f,threads_b", [(1, 256, 256), (2, 128, 128), (4, 64, 192), (8, 64, 128)])
+@pytest.mark.parametrize("ctas,threads_f,threads_b", [(1, 256, 256), (2, 128, 128), (4, 64, 192), (8, 64, 128), (16, 64, 128)])
 def test_kernel_source_on_host_matches_the_reference(emu, golden, kind, fixture, ctas, threads_f, threads_b):
     from deepaco_b200 import net as N
     g = golden(fixture)
@@ -199,7 +200,7 @@ def test_python_wiring_autograd_function_and_running_stats(emu, golden, monkeypa
 
 
 def test_barrier_placement_under_thread_sanitizer():
-    """`make tsan`: both kernels on an irregular synthetic graph with 1, 2 and 4 CTAs per graph under ThreadSanitizer;
+    """`make tsan`: both kernels on an irregular synthetic graph with 1, 2, 4 (cluster barrier) and 16 (arrival-counter barrier) CTAs per graph under ThreadSanitizer;
     any cross-thread dependency not ordered by __syncthreads / the cluster barrier fails the run."""
     import shutil
     if not (os.path.exists("/usr/bin/g++") and shutil.which("make")):
@@ -210,4 +211,4 @@ def test_barrier_placement_under_thread_sanitizer():
         pytest.skip("libtsan not installed")
     r = subprocess.run(["make", "-C", EMU_DIR, "tsan"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("tsan run ok") == 3
+    assert r.stdout.count("tsan run ok") == 4

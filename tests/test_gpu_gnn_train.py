@@ -46,7 +46,7 @@ def _compare_grads(net, ref_grads, tag, rtol=2e-3):
     for name, p in net.named_parameters():
         want = ref_grads.get(name)
         if want is None:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            assert p.grad is None, name                              # None in the reference -> None here (not zeros)
             continue
         assert p.grad is not None, name
         assert torch.allclose(p.grad, want, rtol=rtol, atol=2e-5 * gmax), (tag, name, float((p.grad - want).abs().max()), gmax)
@@ -55,7 +55,7 @@ def _compare_grads(net, ref_grads, tag, rtol=2e-3):
 
 
 @pytest.mark.parametrize("kind,fixture", [("tsp", "tsp_n40_gnn_train_grads"), ("cvrp", "cvrp_n14_gnn_train_grads")])
-@pytest.mark.parametrize("ctas", [1, 2, 4, 8])
+@pytest.mark.parametrize("ctas", [1, 2, 4, 8, 16, 64])
 def test_train_mode_matches_the_reference_goldens(golden, monkeypatch, kind, fixture, ctas):
     monkeypatch.setenv("DEEPACO_GNN_CTAS", str(ctas))
     g = golden(fixture)
@@ -99,7 +99,9 @@ def test_train_mode_matches_torch_autograd_at_baseline_sizes(kind):
     (heu * c).sum().backward()
     want = net_torch.net_forward(ref_net, pyg)
     (want * c).sum().backward()
-    assert torch.allclose(heu.detach(), want.detach(), rtol=5e-4, atol=1e-7)
+    # tsp_nls (k = 50): most of the 25 000 outputs sit in the sigmoid tail (1e-9 .. 1e-13), where the relative error of
+    # the output is the absolute error of the logit (same allowance as the eval-mode test in test_gpu_gnn.py)
+    assert torch.allclose(heu.detach(), want.detach(), rtol=5e-3 if kind == "tsp_nls" else 5e-4, atol=1e-7)
     _compare_grads(net, {k: p.grad for k, p in ref_net.named_parameters()}, kind, rtol=5e-3)
     for (name, b1), (_, b2) in zip(net.named_buffers(), ref_net.named_buffers()):
         assert torch.allclose(b1.float(), b2.float(), rtol=1e-4, atol=1e-6), name
