@@ -235,37 +235,121 @@ def default_train_ctas(n_edges):
     return 1 if n_edges < 512 else (8 if n_edges < 4096 else (32 if n_edges < 16384 else 64))
 
 
+def _packed_entries(net):
+    """[(tensor-or-None, numel)] in the packed weight order of pack_weights (None = the unused mean / invstd slots)."""
+    e = net.emb_net
+    out = [e.v_lin0.weight, e.v_lin0.bias, e.e_lin0.weight, e.e_lin0.bias]
+    for i in range(e.depth):
+        for lins in (e.v_lins1, e.v_lins2, e.v_lins3, e.v_lins4):
+            out += [lins[i].weight, lins[i].bias]
+        out += [e.e_lins0[i].weight, e.e_lins0[i].bias]
+        for bn in (e.v_bns[i].module, e.e_bns[i].module):
+            out += [bn.weight, bn.bias, None]
+    h = net.par_net_heu.lins
+    out += [h[0].weight, h[0].bias, h[1].weight, h[1].bias, h[2].weight, h[2].bias]
+    return [(t, 2 * UNITS if t is None else t.numel()) for t in out]
+
+
+class _FlatState:
+    """The parameters of emb_net / par_net_heu re-homed as views of ONE fp32 buffer in the packed weight order, and the
+    BatchNorm running statistics as rows of two [12, 2, 32] buffers (the flat-parameter idiom of DDP / FSDP): the
+    training kernels read the buffer directly -- no per-call packing -- and the packed gradient is handed back to
+    autograd as views.  Parameter / buffer objects, names, shapes and state_dict keys are unchanged."""
+
+    def __init__(self, net):
+        e = net.emb_net
+        entries = _packed_entries(net)
+        dev = e.v_lin0.weight.device
+        for t, _ in entries:
+            if t is not None and (t.dtype != torch.float32 or t.device != dev):
+                raise _lib.DeepAcoError("deepaco_b200.Net: parameters must be fp32 on one device")
+        self.flat = torch.zeros(sum(k for _, k in entries), dtype=torch.float32, device=dev)
+        assert self.flat.numel() == weight_count(e.feats)
+        self.slots = []                                           # (param, offset, numel, shape)
+        dead = {id(t) for t in (e.v_lins1[-1].weight, e.v_lins1[-1].bias, e.v_lins2[-1].weight, e.v_lins2[-1].bias,
+                                e.v_bns[-1].module.weight, e.v_bns[-1].module.bias)}
+        off = 0
+        with torch.no_grad():
+            for t, k in entries:
+                if t is not None:
+                    view = self.flat[off:off + k].view(t.shape)
+                    view.copy_(t.data)
+                    t.data = view
+                    # the last layer's node update never reaches the output (EmbNet.forward returns w, tsp/net.py:45):
+                    # the reference's autograd leaves those .grad at None, so they are not autograd inputs here either
+                    self.slots.append((t, off, k, tuple(t.shape), id(t) not in dead))
+                off += k
+            bns = [m.module for l in range(e.depth) for m in (e.v_bns[l], e.e_bns[l])]
+            self.bns = bns
+            self.track = all(m.track_running_stats and m.running_mean is not None for m in bns)
+            if self.track:
+                self.rm = torch.stack([m.running_mean.to(torch.float32) for m in bns]).view(e.depth, 2, UNITS).contiguous()
+                self.rv = torch.stack([m.running_var.to(torch.float32) for m in bns]).view(e.depth, 2, UNITS).contiguous()
+                self.nbt = torch.stack([m.num_batches_tracked for m in bns])
+                for j, m in enumerate(bns):
+                    m.running_mean.data = self.rm.view(-1, UNITS)[j]
+                    m.running_var.data = self.rv.view(-1, UNITS)[j]
+                    m.num_batches_tracked.data = self.nbt[j]
+        self.base = self.flat.data_ptr()
+
+    def intact(self):
+        """False once something re-allocated a parameter / buffer (net.to(...), net.float(), a manual `.data =`)."""
+        base = self.base
+        if self.flat.data_ptr() != base:
+            return False
+        for t, off, _, _, _ in self.slots:
+            if t.data_ptr() != base + 4 * off:
+                return False
+        if self.track:
+            rm, rv = self.rm.data_ptr(), self.rv.data_ptr()
+            for j, m in enumerate(self.bns):
+                if m.running_mean is None or m.running_mean.data_ptr() != rm + 4 * UNITS * j or m.running_var.data_ptr() != rv + 4 * UNITS * j:
+                    return False
+        return True
+
+
+def flat_state(net):
+    st = net.__dict__.get("_flat_train_state")
+    if st is None or not st.intact():
+        st = _FlatState(net)
+        net.__dict__["_flat_train_state"] = st
+    return st
+
+
 class _GnnTrain(torch.autograd.Function):
-    """heu [B, E], stats [B, 12, 6, 32] = f(packed weights, graph); gradient w.r.t. the packed weights only (graph inputs are data)."""
+    """heu [B, E], stats [B, 12, 6, 32] = f(parameters, graph).  `flat` is the packed weight buffer the parameters alias;
+    `params` are the live, trainable parameters (autograd inputs), `slots[j]` = (offset, numel, shape) of params[j]."""
 
     @staticmethod
-    def forward(ctx, flat, x, graph, feats, ctas, bn_eps):
+    def forward(ctx, flat, x, graph, feats, ctas, bn_eps, slots, *params):
         import ctypes
         dev = x.device
-        flat = flat.detach().contiguous()
         bufs = train_buffers(graph["B"], graph["n"], graph["E"], dev)
         heu = torch.empty((graph["B"], graph["E"]), dtype=torch.float32, device=dev)
         a, keep = train_args(x, graph, flat, bufs, feats, ctas, bn_eps, heu_out=heu)
         with torch.cuda.device(dev):
             check(lib().deepaco_gnn_train_forward(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_train_forward")
-        ctx.state = (flat, x, graph, bufs, feats, ctas, bn_eps)
+        ctx.state = (flat, x, graph, bufs, feats, ctas, bn_eps, slots)
         ctx.mark_non_differentiable(bufs["stats"])
         return heu, bufs["stats"]
 
     @staticmethod
     def backward(ctx, g_heu, _g_stats):
         import ctypes
-        flat, x, graph, bufs, feats, ctas, bn_eps = ctx.state
+        flat, x, graph, bufs, feats, ctas, bn_eps, slots = ctx.state
         dev = x.device
         g_heu = g_heu.to(torch.float32).contiguous()
-        grad = torch.zeros((graph["B"], ctas, flat.numel()), dtype=torch.float32, device=dev)
+        grad = torch.zeros((graph["B"] * ctas, flat.numel()), dtype=torch.float32, device=dev)
         a, keep = train_args(x, graph, flat, bufs, feats, ctas, bn_eps, grad_heu=g_heu, grad_weights=grad)
         with torch.cuda.device(dev):
             check(lib().deepaco_gnn_train_backward(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_train_backward")
-        return grad.sum(dim=(0, 1)), None, None, None, None, None
+        total = grad.sum(dim=0) if grad.shape[0] > 1 else grad[0]
+        need = ctx.needs_input_grad[7:]
+        grads = tuple(total[off:off + k].view(shape) if nd else None for (off, k, shape), nd in zip(slots, need))
+        return (None,) * 7 + grads
 
 
-def gnn_train_forward(net, x, edge_index, edge_attr, ctas=None):
+def gnn_train_forward(net, x, edge_index, edge_attr, ctas=None, graph=None):
     """Training-mode Net.forward for one graph or a batch ([B, ...] tensors with identical n and E; every graph is its
     own forward call as far as BatchNorm is concerned).  Differentiable w.r.t. the parameters of `net`; updates the
     BatchNorm running statistics like the sequence of per-graph calls would (tsp/net.py:41-44 with PyG BatchNorm)."""
@@ -273,50 +357,42 @@ def gnn_train_forward(net, x, edge_index, edge_attr, ctas=None):
     if not batched:
         x, edge_index, edge_attr = x[None], edge_index[None], edge_attr[None]
     _lib.require_cuda(x, "pyg.x")
-    B, n = x.shape[0], x.shape[1]
-    graph = train_graph(edge_index, edge_attr, n)
+    n = x.shape[1]
+    if graph is None:
+        graph = train_graph(edge_index, edge_attr, n)
     e = net.emb_net
-    eps = float(e.v_bns[0].module.eps)
-    flat = pack_weights(net, for_training=True)
-    heu, stats = _GnnTrain.apply(flat, x.to(torch.float32).contiguous(), graph, e.feats,
-                                 ctas or default_train_ctas(graph["E"]), eps)
-    _update_running_stats(e, stats, n, graph["E"])
+    st = flat_state(net)
+    live = [(t, off, k, shape) for t, off, k, shape, alive in st.slots if alive and t.requires_grad]
+    heu, stats = _GnnTrain.apply(st.flat, x.to(torch.float32).contiguous(), graph, e.feats,
+                                 ctas or default_train_ctas(graph["E"]), float(st.bns[0].eps),
+                                 [(off, k, shape) for _, off, k, shape in live], *[t for t, _, _, _ in live])
+    _update_running_stats(st, stats, n, graph["E"])
     return heu if batched else heu[0]
 
 
 @torch.no_grad()
-def _update_running_stats(emb, stats, n, E):
+def _update_running_stats(st, stats, n, E):
     """running_mean / running_var / num_batches_tracked exactly as nn.BatchNorm1d.forward does in training mode
-    (exponential moving average with the module's momentum, unbiased variance), one update per graph."""
-    mods = [m.module for m in emb.v_bns] + [m.module for m in emb.e_bns]
-    mods_on = [m for m in mods if m.track_running_stats and m.running_mean is not None]
-    if not mods_on:
+    (exponential moving average with the module's momentum, unbiased variance), one update per graph, on the stacked
+    [12, 2, 32] buffers the modules' running statistics alias."""
+    if not st.track:
         return
-    unbiased = stats.clone()                                   # biased -> unbiased variance (nn.BatchNorm1d's running_var)
-    unbiased[:, :, 2] *= n / max(n - 1, 1)
-    unbiased[:, :, 5] *= E / max(E - 1, 1)
+    s5 = stats.view(stats.shape[0], DEPTH, 2, 3, UNITS)            # [B][layer][node | edge][mean, invstd, biased var][32]
+    scale = torch.tensor([n / max(n - 1, 1), E / max(E - 1, 1)], dtype=torch.float32).view(1, 1, 2, 1).to(stats.device, non_blocking=True)
+    uvar = s5[:, :, :, 2] * scale
+    moms = {m.momentum for m in st.bns}
     for b in range(stats.shape[0]):
-        means, uvars, rms, rvs, moms, nbts = [], [], [], [], [], []
-        for l in range(DEPTH):
-            for m, base in ((emb.v_bns[l].module, 0), (emb.e_bns[l].module, 3)):
-                if not (m.track_running_stats and m.running_mean is not None):
-                    continue
-                nbts.append(m.num_batches_tracked)
-                mom = m.momentum if m.momentum is not None else 1.0 / float(m.num_batches_tracked + 1)   # cumulative average
-                means.append(unbiased[b, l, base])
-                uvars.append(unbiased[b, l, base + 2])
-                rms.append(m.running_mean)
-                rvs.append(m.running_var)
-                moms.append(mom)
-        torch._foreach_add_(nbts, 1)
-        if len(set(moms)) == 1:
-            mom = moms[0]
-            torch._foreach_mul_(rms + rvs, 1.0 - mom)
-            torch._foreach_add_(rms + rvs, means + uvars, alpha=mom)
+        if len(moms) == 1 and None not in moms:
+            mom = next(iter(moms))
+            st.rm.mul_(1.0 - mom).add_(s5[b, :, :, 0], alpha=mom)
+            st.rv.mul_(1.0 - mom).add_(uvar[b], alpha=mom)
         else:
-            for rm, rv, mu, uv, mom in zip(rms, rvs, means, uvars, moms):
-                rm.mul_(1.0 - mom).add_(mu, alpha=mom)
-                rv.mul_(1.0 - mom).add_(uv, alpha=mom)
+            for j, m in enumerate(st.bns):
+                mom = m.momentum if m.momentum is not None else 1.0 / float(m.num_batches_tracked + 1)   # cumulative average
+                l, k = divmod(j, 2)
+                m.running_mean.mul_(1.0 - mom).add_(s5[b, l, k, 0], alpha=mom)
+                m.running_var.mul_(1.0 - mom).add_(uvar[b, l, k], alpha=mom)
+        st.nbt += 1
 
 
 class Net(nn.Module):

@@ -126,7 +126,7 @@ def test_kernel_source_on_host_matches_the_reference(emu, golden, kind, fixture,
     pyg = _pyg(g)
     heu, grads, stats, graph = _emu_run(emu, net, pyg, torch.from_numpy(g["c"]), ctas, threads_f, threads_b)
     assert torch.isfinite(heu).all() and torch.isfinite(stats).all()
-    N._update_running_stats(net.emb_net, stats, graph["n"], graph["E"])
+    N._update_running_stats(N.flat_state(net), stats, graph["n"], graph["E"])
     _check_against_golden(net, g, heu[0], grads, dict(net.named_buffers()), f"emu ctas={ctas}")
 
 

@@ -117,9 +117,13 @@ def test_train_instance_parameter_gradients_match_reference_pipeline():
     gmax = max(float(p.grad.abs().max()) for p in ref_net.parameters() if p.grad is not None)
     for (name, p1), (_, p2) in zip(net.named_parameters(), ref_net.named_parameters()):
         if p2.grad is None:
-            assert p1.grad is None
+            assert p1.grad is None, name
             continue
-        assert torch.allclose(p1.grad, p2.grad, rtol=5e-3, atol=2e-5 * gmax), name
+        if name.endswith(".bias") and any(t in name for t in ("v_lins1.", "v_lins3.", "v_lins4.", "e_lins0.")):
+            # a bias in front of a train-mode BatchNorm: the true gradient is exactly zero, both sides hold rounding noise
+            assert float(p1.grad.abs().max()) <= 1e-3 * gmax and float(p2.grad.abs().max()) <= 1e-3 * gmax, name
+            continue
+        assert torch.allclose(p1.grad, p2.grad, rtol=5e-3, atol=2e-5 * gmax), (name, float((p1.grad - p2.grad).abs().max()), gmax)
         checked += 1
     assert checked > 50
     opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
