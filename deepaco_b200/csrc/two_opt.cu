@@ -9,6 +9,15 @@
 // distance rows d[p,:] and d[ni,:] in shared memory with coalesced loads (the row of ni is reused as the
 // row of p for i+1), lanes sweep j, and the (change, i*n+j) minimum is reduced over the CTA with the same
 // tie rule.  The terms d[p,ni] and d[nj,nx] are tour edges, cached per pass.
+//
+// n <= 510 runs two_opt_call_v2: with G(a, m) = d[tour[a], tour[m]] the candidate is
+// change(i, j) = G(i-1, j) + G(i, j+1) - edge[i] - edge[j+1], so the row of gathers made for i is reused as the first
+// term of i+1.  Lane l owns the tour positions m = 32k + l for the whole pass (node ids and edge[m+1] in registers),
+// gathers g_i[m] once per row from the staged distance row, keeps g_{i-1}[m] in registers and takes g_i[m+1] from its
+// neighbour lane by shuffle: one shared-memory gather per candidate instead of two plus three index / edge loads.
+// Rows are dealt to warps in mirrored pairs (i with n-1-i), so every warp gets the same number of candidates AND the
+// same number of row fetches (contiguous bands by candidate count leave the last warp with n/4 nearly empty rows, each
+// a full L2 round trip).
 #include "common.cuh"
 #include "host_util.h"
 
@@ -137,34 +146,150 @@ __device__ int two_opt_call(const float* __restrict__ D, int n, int max_iteratio
     return it;
 }
 
+// same contract as two_opt_call for n + 1 <= 32 * KMAX (see the header comment)
+template <int KMAX>
+__device__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    float* rowbuf = S.rows + (size_t)warp * 3 * n;
+    const bool vec16 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+    auto prefetch_row = [&](float* dst, int node) {
+        const float* src = D + (size_t)node * n;
+        if (vec16) {
+            for (int c = lane * 4; c < n; c += 128)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+        } else {
+            for (int c = lane; c < n; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // rows 1 .. n-2 in mirrored pairs: row i has n-1-i candidates, row n-1-i has i
+    const int F = (n - 2) / 2;
+    const int lo1 = 1 + F * warp / W;
+    int hi1 = 1 + F * (warp + 1) / W;
+    const int lo2 = n - hi1, hi2 = n - lo1;
+    if (warp == W - 1 && ((n - 2) & 1)) hi1 = F + 2;   // the unpaired middle row
+    int it = 0;
+    while (it < max_iterations) {
+        __syncthreads();
+        for (int k = tid + 1; k <= n; k += blockDim.x)   // tour[n] == tour[0]: edge[n] closes the tour
+            S.edge[k] = __ldg(D + (size_t)S.tour[k - 1] * n + S.tour[k]);
+        __syncthreads();
+        uint32_t tn[KMAX];   // tour[m] | tour[m+1] << 16 at m = 32k + lane
+        float en[KMAX];      // edge[m+1]; -inf where m is not a candidate position (change becomes +inf)
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int m = 32 * k + lane;
+            const uint32_t t0 = m <= n ? S.tour[m] : 0, t1 = m + 1 <= n ? S.tour[m + 1] : 0;
+            tn[k] = t0 | (t1 << 16);
+            en[k] = m <= n - 1 ? S.edge[m + 1] : __int_as_float(0xff800000);
+        }
+        float best = 0.f;                 // delta starts at 0 (two_opt.py:10)
+        uint32_t bestkey = 0xffffffffu;
+#pragma unroll 1
+        for (int run = 0; run < 2; ++run) {
+            const int lo = run ? lo2 : lo1, hi = run ? hi2 : hi1;
+            if (lo >= hi) continue;
+            float prev[KMAX];             // g_{r-1}[m]
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) prev[k] = 0.f;
+            prefetch_row(rowbuf, S.tour[lo - 1]);
+            prefetch_row(rowbuf + n, S.tour[lo]);
+#pragma unroll 1
+            for (int r = lo - 1; r < hi; ++r) {
+                const int slot = (r - (lo - 1)) % 3;
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                if (r + 2 < hi) prefetch_row(rowbuf + (size_t)((slot + 2) % 3) * n, S.tour[r + 2]);
+                else asm volatile("cp.async.commit_group;" ::: "memory");
+                const float* row = rowbuf + (size_t)slot * n;     // d[tour[r], :]
+                const int k0 = (r + 1) >> 5;                      // positions m >= r+1 only
+                float cur[KMAX + 1];                              // g_r[m]
+                cur[KMAX] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) cur[k] = (k >= k0) ? row[tn[k] & 0xffffu] : 0.f;
+                if (r >= lo) {                                    // candidates (i = r, j = m), m = i+1 .. n-1
+                    const uint32_t pk = (uint32_t)S.tour[r - 1] | ((uint32_t)S.tour[r] << 16);
+                    const float e_i = S.edge[r];
+                    const uint32_t keybase = (uint32_t)r * (uint32_t)n + (uint32_t)lane;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        if (k < k0) continue;                     // warp-uniform
+                        const float mine = lane == 0 ? cur[k + 1] : cur[k];
+                        const float b = __shfl_sync(DACO_FULL, mine, (lane + 1) & 31);    // g_r[m+1]
+                        const float change = __fsub_rn(__fsub_rn(__fadd_rn(prev[k], b), e_i), en[k]);
+                        const uint32_t x = tn[k] ^ pk;            // node_prev == node_j or node_next == node_i (two_opt.py:16)
+                        const bool dup = (x & 0xffffu) == 0 || (x >> 16) == 0;
+                        if (32 * k + lane > r && !dup && change < best) {   // strict: first minimum in (i, j) order
+                            best = change;
+                            bestkey = keybase + 32u * k;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) prev[k] = cur[k];
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
+        // CTA arg-min with lowest key on ties (== first strict minimum of the sequential scan)
+        for (int off = 16; off > 0; off >>= 1) {
+            const float oc = __shfl_xor_sync(DACO_FULL, best, off);
+            const uint32_t ok = __shfl_xor_sync(DACO_FULL, bestkey, off);
+            if (oc < best || (oc == best && ok < bestkey)) { best = oc; bestkey = ok; }
+        }
+        if (lane == 0) { S.red_c[warp] = best; S.red_k[warp] = bestkey; }
+        __syncthreads();
+        best = S.red_c[0];
+        bestkey = S.red_k[0];
+        for (int w = 1; w < W; ++w) {
+            const float oc = S.red_c[w];
+            const uint32_t ok = S.red_k[w];
+            if (oc < best || (oc == best && ok < bestkey)) { best = oc; bestkey = ok; }
+        }
+        ++it;
+        if (!((double)best < -1e-6)) break;   // two_opt.py:24,36
+        const int i = (int)(bestkey / (uint32_t)n), j = (int)(bestkey % (uint32_t)n);
+        __syncthreads();
+        for (int k = tid; k < (j - i + 1) / 2; k += blockDim.x) {
+            const uint16_t x = S.tour[i + k];
+            S.tour[i + k] = S.tour[j - k];
+            S.tour[j - k] = x;
+        }
+    }
+    __syncthreads();
+    return it;
+}
+
 __device__ float tour_cost_numpy(const float* __restrict__ D, int n, const uint16_t* tour) {
     auto f = [&](int k) -> float { return __ldg(D + (size_t)tour[k] * n + tour[k == 0 ? n - 1 : k - 1]); };
     return numpy_pairwise_sum(f, 0, n);
 }
 
-// mode 0: one 2-opt call (ACO.two_opt); mode 1: NLS (ACO.nls)
-__global__ void __launch_bounds__(512) two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dist,
-                                                      uint16_t* __restrict__ tours, int n, int A, int mode, int maxt,
-                                                      int T_nls, int T_p, float* __restrict__ costs_out,
-                                                      int32_t* __restrict__ passes_out) {
+// mode 0: one 2-opt call (ACO.two_opt); mode 1: NLS (ACO.nls).  KMAX = 0: two_opt_call (any n that fits shared memory,
+// up to 16 warps); KMAX > 0: two_opt_call_v2 (n + 1 <= 32 * KMAX, 8 warps, two CTAs per SM).
+template <int KMAX>
+__global__ void __launch_bounds__(KMAX ? 256 : 512, KMAX ? 2 : 1)
+two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dist, uint16_t* __restrict__ tours, int n, int A,
+               int mode, int maxt, int T_nls, int T_p, float* __restrict__ costs_out, int32_t* __restrict__ passes_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, W = blockDim.x >> 5;
     const int a = blockIdx.x, b = blockIdx.y;
     TwoOptShared S;
     S.rows = reinterpret_cast<float*>(smem);
-    S.edge = S.rows + (size_t)W * 3 * n;
-    S.red_c = S.edge + n;
+    S.edge = S.rows + (size_t)W * 3 * n;   // [n + 1]
+    S.red_c = S.edge + n + 1;
     S.red_k = reinterpret_cast<uint32_t*>(S.red_c + W);
     S.band = reinterpret_cast<int*>(S.red_k + W);
     S.tour = reinterpret_cast<uint16_t*>(S.band + W + 1);
-    uint16_t* best_tour = S.tour + n;   // NLS only
+    uint16_t* best_tour = S.tour + n + 1;   // NLS only; tour[n] mirrors tour[0] (position 0 never moves)
     __shared__ float s_best_cost, s_new_cost;
 
     const float* D = dist + (size_t)b * n * n;
     const float* H = heu_dist ? heu_dist + (size_t)b * n * n : nullptr;
     uint16_t* T = tours + ((size_t)b * A + a) * n;
-    for (int k = tid; k < n; k += blockDim.x) S.tour[k] = T[k];
-    if (tid == 0) {
+    for (int k = tid; k <= n; k += blockDim.x) S.tour[k] = T[k == n ? 0 : k];
+    if (KMAX == 0 && tid == 0) {
         // bands of i in [1, n-1) with ~equal numbers of (i, j) pairs
         const long total = (long)(n - 2) * (n - 1) / 2;
         int i = 1;
@@ -177,14 +302,18 @@ __global__ void __launch_bounds__(512) two_opt_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
-    int passes = two_opt_call(D, n, maxt, S);
+    auto call = [&](const float* M, int max_iterations) -> int {
+        if constexpr (KMAX == 0) return two_opt_call(M, n, max_iterations, S);
+        else return two_opt_call_v2<KMAX>(M, n, max_iterations, S);
+    };
+    int passes = call(D, maxt);
     if (mode == 1) {
         for (int k = tid; k < n; k += blockDim.x) best_tour[k] = S.tour[k];
         if (tid == 0) s_best_cost = tour_cost_numpy(D, n, S.tour);
         __syncthreads();
         for (int r = 0; r < T_nls; ++r) {
-            passes += two_opt_call(H, n, T_p, S);      // perturbation on the heuristic "distance"
-            passes += two_opt_call(D, n, maxt, S);
+            passes += call(H, T_p);      // perturbation on the heuristic "distance"
+            passes += call(D, maxt);
             if (tid == 0) s_new_cost = tour_cost_numpy(D, n, S.tour);
             __syncthreads();
             if (s_new_cost < s_best_cost) {            // tsp_nls/aco.py:252-254
@@ -213,13 +342,25 @@ static int launch_two_opt(const float* dist, const float* heu_dist, uint16_t* to
     DACO_CHECK_ARG(dist && tours, "deepaco_two_opt: NULL argument");
     DACO_CHECK_ARG(n >= 4 && n <= 65535 && A >= 1 && B >= 1 && B <= 65535, "deepaco_two_opt: bad sizes (n >= 4)");
     DACO_CHECK_ARG(maxt >= 0 && T_nls >= 0 && T_p >= 0, "deepaco_two_opt: negative iteration count");
-    int W = n >= 256 ? 16 : 8;   // more warps per tour once a pass has enough (i, j) pairs to feed them
-    if (const char* e = getenv("DEEPACO_2OPT_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) W = w; }
-    const size_t smem = ((size_t)W * 3 * n + n + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)2 * n * 2 + 16;
+    int variant = n + 1 <= 128 ? 4 : (n + 1 <= 256 ? 8 : (n + 1 <= 512 ? 16 : 0));
+    if (const char* e = getenv("DEEPACO_2OPT_LEGACY")) { if (atoi(e) != 0) variant = 0; }
+    int W = variant ? 8 : (n >= 256 ? 16 : 8);   // legacy: more warps per tour once a pass has enough (i, j) pairs to feed them
+    if (variant == 0) { if (const char* e = getenv("DEEPACO_2OPT_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) W = w; } }
+    const size_t smem = ((size_t)W * 3 * n + n + 1 + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)(2 * n + 1) * 2 + 16;
     DACO_CHECK_ARG(smem <= (size_t)di->max_smem_optin - 1024, "deepaco_two_opt: n=%d does not fit shared memory", n);
-    DACO_CHECK_CUDA(cudaFuncSetAttribute(two_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(A, B);
-    two_opt_kernel<<<grid, W * 32, smem, st>>>(dist, heu_dist, tours, n, A, mode, maxt, T_nls, T_p, costs_out, passes_out);
+#define DACO_LAUNCH_2OPT(K)                                                                                                  \
+    do {                                                                                                                     \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(two_opt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        two_opt_kernel<K><<<grid, W * 32, smem, st>>>(dist, heu_dist, tours, n, A, mode, maxt, T_nls, T_p, costs_out, passes_out); \
+    } while (0)
+    switch (variant) {
+        case 4: DACO_LAUNCH_2OPT(4); break;
+        case 8: DACO_LAUNCH_2OPT(8); break;
+        case 16: DACO_LAUNCH_2OPT(16); break;
+        default: DACO_LAUNCH_2OPT(0); break;
+    }
+#undef DACO_LAUNCH_2OPT
     DACO_CHECK_LAUNCH();
     return DEEPACO_OK;
 }
