@@ -54,7 +54,9 @@ __device__ float numpy_pairwise_sum(F f, int lo, int n) {
 }
 
 struct TwoOptShared {
-    uint16_t* tour;   // [n]
+    uint64_t* bars;   // [W][3]  mbarriers of the row buffers (two_opt_call_v2, TMA rows)
+    uint32_t* phase;  // [W]     their parities, carried from call to call
+    uint16_t* tour;   // [n + 1] tour[n] mirrors tour[0]
     float* edge;      // [n]  edge[k] = d[tour[k-1], tour[k]], edge[0] = d[tour[n-1], tour[0]]
     float* rows;      // [W][3][n]  triple-buffered distance rows (cp.async prefetch of the next row)
     float* red_c;     // [W]
@@ -63,7 +65,7 @@ struct TwoOptShared {
 };
 
 // one 2-opt call: up to max_iterations passes on the tour in shared memory; returns passes done
-__device__ int two_opt_call(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
+__device__ __noinline__ int two_opt_call(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     float* rowbuf = S.rows + (size_t)warp * 3 * n;
     const bool vec16 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
@@ -146,22 +148,64 @@ __device__ int two_opt_call(const float* __restrict__ D, int n, int max_iteratio
     return it;
 }
 
-// same contract as two_opt_call for n + 1 <= 32 * KMAX (see the header comment)
+// same contract as two_opt_call for a PERMUTATION tour with n + 1 <= 32 * KMAX (see the header comment).  For a
+// permutation the reference's skip test (node_prev == node_j or node_next == node_i, two_opt.py:16) can never fire
+// for 1 <= i < j <= n-1, so it is not evaluated here; the kernel checks the tour once and sends anything else to
+// two_opt_call.
+#define DACO_2OPT_CASES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15)
+
+// one row r of the sweep: cur[k] = g_r[m] for the positions m = 32k + lane >= r+1, then (EVAL) the candidates
+// (i = r, j = m) from prev = g_{r-1}.  The k loop is entered at k0 = (r+1)/32 through a jump table.
+template <int KMAX, bool EVAL>
+__device__ __forceinline__ void two_opt_row(const float* row, int r, int n, int lane, const uint32_t (&off)[KMAX],
+                                            const float (&en)[KMAX], const float (&prev)[KMAX + 1], float (&cur)[KMAX + 1],
+                                            float e_i, float& best, uint32_t& bestkey) {
+    const int k0 = (r + 1) >> 5;
+    const char* rowb = reinterpret_cast<const char*>(row);
+#define DACO_G(k) case k: if constexpr (k < KMAX) cur[k] = *reinterpret_cast<const float*>(rowb + off[k]);
+    switch (k0) { DACO_2OPT_CASES(DACO_G) default: break; }
+#undef DACO_G
+    if constexpr (EVAL) {
+        const int rl = r - lane;                                  // 32k + lane > r  <=>  32k > rl
+        const uint32_t keybase = (uint32_t)r * (uint32_t)n + (uint32_t)lane;
+        const int next = (lane + 1) & 31;
+        const bool first = lane == 0;
+#define DACO_E(k)                                                                                         \
+    case k:                                                                                               \
+        if constexpr (k < KMAX) {                                                                         \
+            const float b = __shfl_sync(DACO_FULL, first ? cur[k + 1] : cur[k], next); /* g_r[m+1] */     \
+            const float change = __fsub_rn(__fsub_rn(__fadd_rn(prev[k], b), e_i), en[k]);                 \
+            const bool take = (32 * k > rl) & (change < best); /* strict: first minimum in (i, j) order */ \
+            best = take ? change : best;                                                                  \
+            bestkey = take ? keybase + 32u * k : bestkey;                                                 \
+        }
+        switch (k0) { DACO_2OPT_CASES(DACO_E) default: break; }
+#undef DACO_E
+    }
+}
+
 template <int KMAX>
-__device__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
+__device__ __noinline__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     float* rowbuf = S.rows + (size_t)warp * 3 * n;
-    const bool vec16 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
-    auto prefetch_row = [&](float* dst, int node) {
+    uint64_t* bars = S.bars + warp * 3;
+    // distance rows arrive by TMA bulk copy (one instruction per row, completion on an mbarrier per buffer) when the
+    // rows are 16-byte granular, else by 4-byte cp.async
+    const bool tma = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+    uint32_t ph = S.phase[warp];          // parity of the next completion of each of the three row buffers
+    auto issue = [&](int slot, int node) {
+        float* dst = rowbuf + slot * n;
         const float* src = D + (size_t)node * n;
-        if (vec16) {
-            for (int c = lane * 4; c < n; c += 128)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+        if (tma) {
+            if (lane == 0) {
+                mbar_expect_tx(bars + slot, 4u * n);
+                tma_bulk_g2s(dst, src, 4u * n, bars + slot);
+            }
         } else {
             for (int c = lane; c < n; c += 32)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // rows 1 .. n-2 in mirrored pairs: row i has n-1-i candidates, row n-1-i has i
     const int F = (n - 2) / 2;
@@ -175,13 +219,12 @@ __device__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_itera
         for (int k = tid + 1; k <= n; k += blockDim.x)   // tour[n] == tour[0]: edge[n] closes the tour
             S.edge[k] = __ldg(D + (size_t)S.tour[k - 1] * n + S.tour[k]);
         __syncthreads();
-        uint32_t tn[KMAX];   // tour[m] | tour[m+1] << 16 at m = 32k + lane
+        uint32_t off[KMAX];  // byte offset of tour[m] in a distance row, m = 32k + lane
         float en[KMAX];      // edge[m+1]; -inf where m is not a candidate position (change becomes +inf)
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int m = 32 * k + lane;
-            const uint32_t t0 = m <= n ? S.tour[m] : 0, t1 = m + 1 <= n ? S.tour[m + 1] : 0;
-            tn[k] = t0 | (t1 << 16);
+            off[k] = m <= n ? 4u * S.tour[m] : 0u;
             en[k] = m <= n - 1 ? S.edge[m + 1] : __int_as_float(0xff800000);
         }
         float best = 0.f;                 // delta starts at 0 (two_opt.py:10)
@@ -190,52 +233,40 @@ __device__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_itera
         for (int run = 0; run < 2; ++run) {
             const int lo = run ? lo2 : lo1, hi = run ? hi2 : hi1;
             if (lo >= hi) continue;
-            float prev[KMAX];             // g_{r-1}[m]
+            float ga[KMAX + 1], gb[KMAX + 1];   // g of the previous / current row, roles alternate
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) prev[k] = 0.f;
-            prefetch_row(rowbuf, S.tour[lo - 1]);
-            prefetch_row(rowbuf + n, S.tour[lo]);
-#pragma unroll 1
-            for (int r = lo - 1; r < hi; ++r) {
-                const int slot = (r - (lo - 1)) % 3;
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-                __syncwarp();
-                if (r + 2 < hi) prefetch_row(rowbuf + (size_t)((slot + 2) % 3) * n, S.tour[r + 2]);
-                else asm volatile("cp.async.commit_group;" ::: "memory");
-                const float* row = rowbuf + (size_t)slot * n;     // d[tour[r], :]
-                const int k0 = (r + 1) >> 5;                      // positions m >= r+1 only
-                float cur[KMAX + 1];                              // g_r[m]
-                cur[KMAX] = 0.f;
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) cur[k] = (k >= k0) ? row[tn[k] & 0xffffu] : 0.f;
-                if (r >= lo) {                                    // candidates (i = r, j = m), m = i+1 .. n-1
-                    const uint32_t pk = (uint32_t)S.tour[r - 1] | ((uint32_t)S.tour[r] << 16);
-                    const float e_i = S.edge[r];
-                    const uint32_t keybase = (uint32_t)r * (uint32_t)n + (uint32_t)lane;
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        if (k < k0) continue;                     // warp-uniform
-                        const float mine = lane == 0 ? cur[k + 1] : cur[k];
-                        const float b = __shfl_sync(DACO_FULL, mine, (lane + 1) & 31);    // g_r[m+1]
-                        const float change = __fsub_rn(__fsub_rn(__fadd_rn(prev[k], b), e_i), en[k]);
-                        const uint32_t x = tn[k] ^ pk;            // node_prev == node_j or node_next == node_i (two_opt.py:16)
-                        const bool dup = (x & 0xffffu) == 0 || (x >> 16) == 0;
-                        if (32 * k + lane > r && !dup && change < best) {   // strict: first minimum in (i, j) order
-                            best = change;
-                            bestkey = keybase + 32u * k;
-                        }
-                    }
+            for (int k = 0; k <= KMAX; ++k) ga[k] = gb[k] = 0.f;
+            int slot = 0;                       // buffer of row r; r+1 is in flight in slot+1, r+2 goes to slot+2 (mod 3)
+            issue(0, S.tour[lo - 1]);
+            issue(1, S.tour[lo]);
+            auto stage = [&](int r) -> const float* {     // row r landed and visible; row r+2 on its way
+                if (tma) {
+                    mbar_wait(bars + slot, (ph >> slot) & 1u);
+                    ph ^= 1u << slot;
+                } else {
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
                 }
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) prev[k] = cur[k];
+                __syncwarp();
+                const int s2 = slot == 0 ? 2 : slot - 1;
+                if (r + 2 < hi) issue(s2, S.tour[r + 2]);
+                else if (!tma) asm volatile("cp.async.commit_group;" ::: "memory");
+                const float* row = rowbuf + slot * n;
+                slot = slot == 2 ? 0 : slot + 1;
+                return row;
+            };
+            two_opt_row<KMAX, false>(stage(lo - 1), lo - 1, n, lane, off, en, gb, ga, 0.f, best, bestkey);
+#pragma unroll 1
+            for (int r = lo; r < hi; r += 2) {
+                two_opt_row<KMAX, true>(stage(r), r, n, lane, off, en, ga, gb, S.edge[r], best, bestkey);
+                if (r + 1 < hi) two_opt_row<KMAX, true>(stage(r + 1), r + 1, n, lane, off, en, gb, ga, S.edge[r + 1], best, bestkey);
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (!tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
         }
         // CTA arg-min with lowest key on ties (== first strict minimum of the sequential scan)
-        for (int off = 16; off > 0; off >>= 1) {
-            const float oc = __shfl_xor_sync(DACO_FULL, best, off);
-            const uint32_t ok = __shfl_xor_sync(DACO_FULL, bestkey, off);
+        for (int o = 16; o > 0; o >>= 1) {
+            const float oc = __shfl_xor_sync(DACO_FULL, best, o);
+            const uint32_t ok = __shfl_xor_sync(DACO_FULL, bestkey, o);
             if (oc < best || (oc == best && ok < bestkey)) { best = oc; bestkey = ok; }
         }
         if (lane == 0) { S.red_c[warp] = best; S.red_k[warp] = bestkey; }
@@ -257,6 +288,7 @@ __device__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_itera
             S.tour[j - k] = x;
         }
     }
+    if (lane == 0) S.phase[warp] = ph;
     __syncthreads();
     return it;
 }
@@ -276,7 +308,9 @@ two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dis
     const int tid = threadIdx.x, W = blockDim.x >> 5;
     const int a = blockIdx.x, b = blockIdx.y;
     TwoOptShared S;
-    S.rows = reinterpret_cast<float*>(smem);
+    S.bars = reinterpret_cast<uint64_t*>(smem);
+    S.phase = reinterpret_cast<uint32_t*>(S.bars + 3 * W);
+    S.rows = reinterpret_cast<float*>(S.phase + W);      // W is a multiple of 4: 16-byte aligned
     S.edge = S.rows + (size_t)W * 3 * n;   // [n + 1]
     S.red_c = S.edge + n + 1;
     S.red_k = reinterpret_cast<uint32_t*>(S.red_c + W);
@@ -289,7 +323,10 @@ two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dis
     const float* H = heu_dist ? heu_dist + (size_t)b * n * n : nullptr;
     uint16_t* T = tours + ((size_t)b * A + a) * n;
     for (int k = tid; k <= n; k += blockDim.x) S.tour[k] = T[k == n ? 0 : k];
-    if (KMAX == 0 && tid == 0) {
+    if (tid < 3 * W) mbar_init(S.bars + tid, 1);
+    if (tid < W) S.phase[tid] = 0;
+    fence_barrier_init();
+    if (tid == 0) {
         // bands of i in [1, n-1) with ~equal numbers of (i, j) pairs
         const long total = (long)(n - 2) * (n - 1) / 2;
         int i = 1;
@@ -302,9 +339,25 @@ two_opt_kernel(const float* __restrict__ dist, const float* __restrict__ heu_dis
         }
     }
     __syncthreads();
+    bool permutation = false;
+    if constexpr (KMAX > 0) {            // every node exactly once?  (reversals keep it that way)
+        int* seen = reinterpret_cast<int*>(S.edge);
+        for (int k = tid; k < n; k += blockDim.x) seen[k] = 0;
+        __syncthreads();
+        for (int k = tid; k < n; k += blockDim.x) {
+            const int t = S.tour[k];
+            if (t < n) atomicAdd(&seen[t], 1);
+        }
+        __syncthreads();
+        int bad = 0;
+        for (int k = tid; k < n; k += blockDim.x) bad |= seen[k] != 1;
+        permutation = !__syncthreads_or(bad);
+    }
     auto call = [&](const float* M, int max_iterations) -> int {
-        if constexpr (KMAX == 0) return two_opt_call(M, n, max_iterations, S);
-        else return two_opt_call_v2<KMAX>(M, n, max_iterations, S);
+        if constexpr (KMAX > 0) {
+            if (permutation) return two_opt_call_v2<KMAX>(M, n, max_iterations, S);
+        }
+        return two_opt_call(M, n, max_iterations, S);
     };
     int passes = call(D, maxt);
     if (mode == 1) {
@@ -345,8 +398,8 @@ static int launch_two_opt(const float* dist, const float* heu_dist, uint16_t* to
     int variant = n + 1 <= 128 ? 4 : (n + 1 <= 256 ? 8 : (n + 1 <= 512 ? 16 : 0));
     if (const char* e = getenv("DEEPACO_2OPT_LEGACY")) { if (atoi(e) != 0) variant = 0; }
     int W = variant ? 8 : (n >= 256 ? 16 : 8);   // legacy: more warps per tour once a pass has enough (i, j) pairs to feed them
-    if (variant == 0) { if (const char* e = getenv("DEEPACO_2OPT_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 16) W = w; } }
-    const size_t smem = ((size_t)W * 3 * n + n + 1 + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)(2 * n + 1) * 2 + 16;
+    if (variant == 0) { if (const char* e = getenv("DEEPACO_2OPT_WARPS")) { const int w = atoi(e); if (w == 4 || w == 8 || w == 12 || w == 16) W = w; } }
+    const size_t smem = (size_t)W * 28 + ((size_t)W * 3 * n + n + 1 + 2 * W) * 4 + (size_t)(W + 1) * 4 + (size_t)(2 * n + 1) * 2 + 16;
     DACO_CHECK_ARG(smem <= (size_t)di->max_smem_optin - 1024, "deepaco_two_opt: n=%d does not fit shared memory", n);
     dim3 grid(A, B);
 #define DACO_LAUNCH_2OPT(K)                                                                                                  \
