@@ -152,43 +152,81 @@ __device__ __noinline__ int two_opt_call(const float* __restrict__ D, int n, int
 // permutation the reference's skip test (node_prev == node_j or node_next == node_i, two_opt.py:16) can never fire
 // for 1 <= i < j <= n-1, so it is not evaluated here; the kernel checks the tour once and sends anything else to
 // two_opt_call.
-#define DACO_2OPT_CASES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15)
+// shared-window loads by 32-bit address (the generic pointers inside TwoOptShared cost a 64-bit add per access)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
 
-// one row r of the sweep: cur[k] = g_r[m] for the positions m = 32k + lane >= r+1, then (EVAL) the candidates
-// (i = r, j = m) from prev = g_{r-1}.  The k loop is entered at k0 = (r+1)/32 through a jump table.
-template <int KMAX, bool EVAL>
-__device__ __forceinline__ void two_opt_row(const float* row, int r, int n, int lane, const uint32_t (&off)[KMAX],
+struct TwoOptBest {   // two running (change, key) minima per lane (even / odd k: two short dependency chains)
+    float c0, c1;
+    uint32_t k0, k1;
+};
+
+// one row r of the sweep: cur[k] = g_r[m] for the positions m = 32k + lane >= r+1, then the candidates (i = r, j = m)
+// from prev = g_{r-1}.  Steps come in blocks of four k (straight-line inside a block, so four gathers / shuffles /
+// compare chains overlap); blocks entirely below k0 = (r+1)/32 are skipped with one warp-uniform branch.  One code
+// copy serves every row -- a variant per k0 is faster per row but sixteen warps in sixteen variants thrash the
+// instruction cache.  e_i = -inf turns the row into a pure gather (first row of a run).
+template <int KMAX>
+__device__ __forceinline__ void two_opt_row(uint32_t row, int r, uint32_t keybase, int lane, const uint32_t (&off)[KMAX / 2],
                                             const float (&en)[KMAX], const float (&prev)[KMAX + 1], float (&cur)[KMAX + 1],
-                                            float e_i, float& best, uint32_t& bestkey) {
+                                            float e_i, TwoOptBest& B) {
     const int k0 = (r + 1) >> 5;
-    const char* rowb = reinterpret_cast<const char*>(row);
-#define DACO_G(k) case k: if constexpr (k < KMAX) cur[k] = *reinterpret_cast<const float*>(rowb + off[k]);
-    switch (k0) { DACO_2OPT_CASES(DACO_G) default: break; }
-#undef DACO_G
-    if constexpr (EVAL) {
-        const int rl = r - lane;                                  // 32k + lane > r  <=>  32k > rl
-        const uint32_t keybase = (uint32_t)r * (uint32_t)n + (uint32_t)lane;
-        const int next = (lane + 1) & 31;
-        const bool first = lane == 0;
-#define DACO_E(k)                                                                                         \
-    case k:                                                                                               \
-        if constexpr (k < KMAX) {                                                                         \
-            const float b = __shfl_sync(DACO_FULL, first ? cur[k + 1] : cur[k], next); /* g_r[m+1] */     \
-            const float change = __fsub_rn(__fsub_rn(__fadd_rn(prev[k], b), e_i), en[k]);                 \
-            const bool take = (32 * k > rl) & (change < best); /* strict: first minimum in (i, j) order */ \
-            best = take ? change : best;                                                                  \
-            bestkey = take ? keybase + 32u * k : bestkey;                                                 \
+#pragma unroll
+    for (int kb = 0; kb < KMAX; kb += 4) {
+        if (kb + 3 >= k0) {
+#pragma unroll
+            for (int k = kb; k < kb + 4; ++k) cur[k] = lds_f32(row + ((k & 1) ? off[k / 2] >> 16 : off[k / 2] & 0xffffu));
         }
-        switch (k0) { DACO_2OPT_CASES(DACO_E) default: break; }
-#undef DACO_E
     }
+    const int next = (lane + 1) & 31;
+    const bool first = lane == 0;
+    const int rl = r - lane;                                      // 32k + lane > r  <=>  32k > rl
+#pragma unroll
+    for (int kb = 0; kb < KMAX; kb += 4) {
+        if (kb + 3 >= k0) {
+            float nb[4];
+#pragma unroll
+            for (int k = kb; k < kb + 4; ++k) nb[k - kb] = __shfl_sync(DACO_FULL, first ? cur[k + 1] : cur[k], next);   // g_r[m+1]
+#pragma unroll
+            for (int k = kb; k < kb + 4; ++k) {
+                const float change = __fsub_rn(__fsub_rn(__fadd_rn(prev[k], nb[k - kb]), e_i), en[k]);
+                // strict <: first minimum in (i, j) order
+                const bool take = (32 * k > rl) & (change < ((k & 1) ? B.c1 : B.c0));
+                if (k & 1) {
+                    B.c1 = take ? change : B.c1;
+                    B.k1 = take ? keybase + 32u * k : B.k1;
+                } else {
+                    B.c0 = take ? change : B.c0;
+                    B.k0 = take ? keybase + 32u * k : B.k0;
+                }
+            }
+        }
+    }
+}
+
+// 4-byte cp.async copy of one row (n % 4 != 0 or unaligned matrices); out of line: not on the TMA path
+__device__ __noinline__ void two_opt_row_copy_async(float* dst, const float* src, int n, int lane) {
+    for (int c = lane; c < n; c += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 template <int KMAX>
 __device__ __noinline__ int two_opt_call_v2(const float* __restrict__ D, int n, int max_iterations, const TwoOptShared& S) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    float* rowbuf = S.rows + (size_t)warp * 3 * n;
-    uint64_t* bars = S.bars + warp * 3;
+    uint16_t* const tour = S.tour;
+    float* const edge = S.edge;
+    float* const rowbuf = S.rows + (size_t)warp * 3 * n;
+    uint64_t* const bars = S.bars + warp * 3;
+    const uint32_t rows_s = smem_u32(rowbuf), tour_s = smem_u32(tour), edge_s = smem_u32(edge);
     // distance rows arrive by TMA bulk copy (one instruction per row, completion on an mbarrier per buffer) when the
     // rows are 16-byte granular, else by 4-byte cp.async
     const bool tma = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
@@ -202,9 +240,7 @@ __device__ __noinline__ int two_opt_call_v2(const float* __restrict__ D, int n, 
                 tma_bulk_g2s(dst, src, 4u * n, bars + slot);
             }
         } else {
-            for (int c = lane; c < n; c += 32)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            two_opt_row_copy_async(dst, src, n, lane);
         }
     };
     // rows 1 .. n-2 in mirrored pairs: row i has n-1-i candidates, row n-1-i has i
@@ -213,33 +249,34 @@ __device__ __noinline__ int two_opt_call_v2(const float* __restrict__ D, int n, 
     int hi1 = 1 + F * (warp + 1) / W;
     const int lo2 = n - hi1, hi2 = n - lo1;
     if (warp == W - 1 && ((n - 2) & 1)) hi1 = F + 2;   // the unpaired middle row
+    const float ninf = __int_as_float(0xff800000);
     int it = 0;
     while (it < max_iterations) {
         __syncthreads();
         for (int k = tid + 1; k <= n; k += blockDim.x)   // tour[n] == tour[0]: edge[n] closes the tour
-            S.edge[k] = __ldg(D + (size_t)S.tour[k - 1] * n + S.tour[k]);
+            edge[k] = __ldg(D + (size_t)tour[k - 1] * n + tour[k]);
         __syncthreads();
-        uint32_t off[KMAX];  // byte offset of tour[m] in a distance row, m = 32k + lane
-        float en[KMAX];      // edge[m+1]; -inf where m is not a candidate position (change becomes +inf)
+        uint32_t off[KMAX / 2];  // byte offsets of tour[m] in a distance row, m = 32k + lane, two per register
+        float en[KMAX];          // edge[m+1]; -inf where m is not a candidate position (change becomes +inf)
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int m = 32 * k + lane;
-            off[k] = m <= n ? 4u * S.tour[m] : 0u;
-            en[k] = m <= n - 1 ? S.edge[m + 1] : __int_as_float(0xff800000);
+            const uint32_t o = m <= n ? 4u * tour[m] : 0u;
+            off[k / 2] = (k & 1) ? off[k / 2] | (o << 16) : o;
+            en[k] = m <= n - 1 ? edge[m + 1] : ninf;
         }
-        float best = 0.f;                 // delta starts at 0 (two_opt.py:10)
-        uint32_t bestkey = 0xffffffffu;
+        TwoOptBest B = {0.f, 0.f, 0xffffffffu, 0xffffffffu};   // delta starts at 0 (two_opt.py:10)
 #pragma unroll 1
         for (int run = 0; run < 2; ++run) {
             const int lo = run ? lo2 : lo1, hi = run ? hi2 : hi1;
             if (lo >= hi) continue;
-            float ga[KMAX + 1], gb[KMAX + 1];   // g of the previous / current row, roles alternate
+            float ga[KMAX + 1], gb[KMAX + 1];   // g of the previous row (ga on entry of a row pair) and of the current one
 #pragma unroll
             for (int k = 0; k <= KMAX; ++k) ga[k] = gb[k] = 0.f;
             int slot = 0;                       // buffer of row r; r+1 is in flight in slot+1, r+2 goes to slot+2 (mod 3)
-            issue(0, S.tour[lo - 1]);
-            issue(1, S.tour[lo]);
-            auto stage = [&](int r) -> const float* {     // row r landed and visible; row r+2 on its way
+            issue(0, tour[lo - 1]);
+            issue(1, tour[lo]);
+            auto stage = [&](int r) -> uint32_t {         // row r landed and visible; row r+2 on its way
                 if (tma) {
                     mbar_wait(bars + slot, (ph >> slot) & 1u);
                     ph ^= 1u << slot;
@@ -248,21 +285,30 @@ __device__ __noinline__ int two_opt_call_v2(const float* __restrict__ D, int n, 
                 }
                 __syncwarp();
                 const int s2 = slot == 0 ? 2 : slot - 1;
-                if (r + 2 < hi) issue(s2, S.tour[r + 2]);
+                if (r + 2 < hi) issue(s2, lds_u16(tour_s + 2 * (r + 2)));
                 else if (!tma) asm volatile("cp.async.commit_group;" ::: "memory");
-                const float* row = rowbuf + slot * n;
+                const uint32_t row = rows_s + 4u * slot * n;
                 slot = slot == 2 ? 0 : slot + 1;
                 return row;
             };
-            two_opt_row<KMAX, false>(stage(lo - 1), lo - 1, n, lane, off, en, gb, ga, 0.f, best, bestkey);
+            // row lo-1 is a pure gather, then the candidates of rows lo .. hi-1; ga / gb alternate as previous / current
 #pragma unroll 1
-            for (int r = lo; r < hi; r += 2) {
-                two_opt_row<KMAX, true>(stage(r), r, n, lane, off, en, ga, gb, S.edge[r], best, bestkey);
-                if (r + 1 < hi) two_opt_row<KMAX, true>(stage(r + 1), r + 1, n, lane, off, en, gb, ga, S.edge[r + 1], best, bestkey);
+            for (int r = lo - 1; r < hi; r += 2) {
+                uint32_t row = stage(r);
+                two_opt_row<KMAX>(row, r, (uint32_t)r * (uint32_t)n + (uint32_t)lane, lane, off, en, ga, gb,
+                                  r >= lo ? lds_f32(edge_s + 4 * r) : ninf, B);
+                if (r + 1 < hi) {
+                    row = stage(r + 1);
+                    two_opt_row<KMAX>(row, r + 1, (uint32_t)(r + 1) * (uint32_t)n + (uint32_t)lane, lane, off, en, gb, ga,
+                                      lds_f32(edge_s + 4 * (r + 1)), B);
+                }
             }
             if (!tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
         }
+        float best = B.c0;
+        uint32_t bestkey = B.k0;
+        if (B.c1 < best || (B.c1 == best && B.k1 < bestkey)) { best = B.c1; bestkey = B.k1; }
         // CTA arg-min with lowest key on ties (== first strict minimum of the sequential scan)
         for (int o = 16; o > 0; o >>= 1) {
             const float oc = __shfl_xor_sync(DACO_FULL, best, o);
@@ -283,9 +329,9 @@ __device__ __noinline__ int two_opt_call_v2(const float* __restrict__ D, int n, 
         const int i = (int)(bestkey / (uint32_t)n), j = (int)(bestkey % (uint32_t)n);
         __syncthreads();
         for (int k = tid; k < (j - i + 1) / 2; k += blockDim.x) {
-            const uint16_t x = S.tour[i + k];
-            S.tour[i + k] = S.tour[j - k];
-            S.tour[j - k] = x;
+            const uint16_t x = tour[i + k];
+            tour[i + k] = tour[j - k];
+            tour[j - k] = x;
         }
     }
     if (lane == 0) S.phase[warp] = ph;
