@@ -64,3 +64,33 @@ for B in (64, 8):
     r = E.TspRunner(d, heu, torch.ones_like(d), 256)
     t = timeit(lambda: r.run(1, 3, 0, [100000 * b for b in range(B)]), 5, 2)
     print(f"C5 TSP-200 x256 x{B} colonies: {t:8.3f} ms/iteration -> {B * 256 / t / 1e3:8.2f} M tours/s", flush=True)
+
+# heuristic network, eval mode (one-off per instance): single instance at the C2 / C3 / C4 graph sizes, and the batched
+# k-NN front end (instance -> graph -> network -> dense heuristic) the C2 / C5 drivers use
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+from bench_gnn_train import graph as _graph  # noqa: E402
+for kind in ("C2 tsp n=100 k=20", "C3 tsp_nls n=500 k=50", "C4 cvrp N=101 dense"):
+    Net, pyg = _graph(kind)
+    torch.manual_seed(0)
+    net = Net().to(dev).eval()
+    with torch.no_grad():
+        t = timeit(lambda: net(pyg), 20, 3)
+    print(f"GNN eval forward {kind}: {t:8.3f} ms / instance (Python front end included)", flush=True)
+from deepaco_b200.tsp.net import Net as _TspNet  # noqa: E402
+net = _TspNet().to(dev).eval()
+for B, n, k in ((256, 100, 20), (64, 200, 20)):
+    xy = torch.rand(B, n, 2, device=dev)
+    d = torch.cdist(xy, xy)
+    d[:, torch.arange(n), torch.arange(n)] = 1e9
+    t = timeit(lambda: net.heuristic_matrices(xy, d, k), 10, 3)
+    print(f"GNN batched front end {B} x TSP-{n} (k={k}): {t:8.3f} ms -> {t / B * 1e3:8.1f} us / instance", flush=True)
+
+# the reference's inference driver (tsp/test.ipynb cell 1: infer_instance) on one TSP-100 instance, 512 ants, T = 10
+from deepaco_b200.tsp.aco import ACO as _ACO  # noqa: E402
+from deepaco_b200.tsp.utils import gen_pyg_data as _gen  # noqa: E402
+pyg, dist = _gen(torch.rand(100, 2, device=dev), 20)
+def infer():
+    with torch.no_grad():
+        heu = net.reshape(pyg, net(pyg)) + 1e-10
+    return _ACO(dist, 512, heuristic=heu, device=dev).run(10)
+print(f"infer_instance TSP-100, 512 ants, T=10: {timeit(infer, 10, 3):8.3f} ms", flush=True)
