@@ -346,6 +346,60 @@ def cvrp_sample(pheromone, heuristic, demand, capacity, n_ants, *, seed=0, offse
     return {"paths": paths, "logp": logp, "tours": tours, "lens": lens, "tmax": tmax, "batched": pheromone.dim() == 3}
 
 
+def pick_move(pheromone_pow, heuristic_pow, prev, mask, mask2=None, *, seed=0, offset=0, want_logp=False):
+    """deepaco_pick_move: one construction step for explicit masks -> (actions int64 [A], log_probs [A] | None).
+    Raises (after one host read of a flag) if a `prev` index is outside the matrix."""
+    pheromone_pow = f32c(require_cuda(pheromone_pow, "pheromone"))
+    heuristic_pow = None if heuristic_pow is None else f32c(require_cuda(heuristic_pow, "heuristic"))
+    n = pheromone_pow.shape[-1]
+    dev = pheromone_pow.device
+    prev = require_cuda(prev, "prev").to(torch.int64).contiguous()
+    A = prev.shape[0]
+    mask = f32c(require_cuda(mask, "mask"))
+    if tuple(mask.shape) != (A, n):
+        raise _lib.DeepAcoError(f"pick_move: mask must be [{A}, {n}], got {tuple(mask.shape)}")
+    if mask2 is not None:
+        mask2 = f32c(require_cuda(mask2, "capacity_mask"))
+        if tuple(mask2.shape) != (A, n):
+            raise _lib.DeepAcoError(f"pick_move: capacity_mask must be [{A}, {n}], got {tuple(mask2.shape)}")
+    actions = torch.empty(A, dtype=torch.int64, device=dev)
+    logp = torch.empty(A, dtype=torch.float32, device=dev) if want_logp else None
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().deepaco_pick_move(ptr(pheromone_pow), ptr(heuristic_pow), ptr(prev), ptr(mask), ptr(mask2), n, A,
+                                      int(seed), int(offset), ptr(actions), ptr(logp), ptr(bad), stream_ptr(dev)),
+              "deepaco_pick_move")
+    if int(bad.item()):
+        raise IndexError("pick_move: `prev` holds a node index outside the problem")      # ATen raises from the gather
+    return actions, logp
+
+
+def pick_move_offset_increment(n, n_ants) -> int:
+    return int(lib().deepaco_pick_move_offset_increment(n, n_ants))
+
+
+def pick_move_for(aco, prev, mask, mask2, require_prob):
+    """ACO.pick_move of the reference classes (tsp/aco.py:165-177, cvrp/aco.py:167-174) on top of deepaco_pick_move:
+    consumes the default CUDA generator like `Categorical(...).sample()`.  When autograd needs the log-probabilities
+    (heuristic / pheromone require grad) they are re-expressed, for the action the kernel drew, with the tensor ops
+    Categorical itself applies, so the gradient reaches the heuristic exactly as in the reference."""
+    ph, heu = aco._weights()
+    n = ph.shape[-1]
+    gen, seed, offset = _lib.generator_state(aco.device)
+    differentiable = require_prob and torch.is_grad_enabled() and (ph.requires_grad or heu.requires_grad)
+    actions, logp = pick_move(ph.detach(), heu.detach(), prev, mask, mask2, seed=seed, offset=offset,
+                              want_logp=require_prob and not differentiable)
+    gen.set_offset(offset + pick_move_offset_increment(n, prev.shape[0]))
+    if differentiable:
+        x = ph[prev] * heu[prev] * mask
+        if mask2 is not None:
+            x = x * mask2
+        probs = x / x.sum(-1, keepdim=True)
+        eps = torch.finfo(probs.dtype).eps
+        logp = torch.log(probs.clamp(min=eps, max=1 - eps)).gather(-1, actions[:, None]).squeeze(-1)
+    return actions, logp
+
+
 def cvrp_step_offset_increment(n_nodes, n_ants) -> int:
     return int(lib().deepaco_cvrp_step_offset_increment(n_nodes, n_ants))
 

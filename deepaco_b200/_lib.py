@@ -38,6 +38,8 @@ _SIGNATURES = {
     "deepaco_cvrp_step_offset_increment": (_u64, [_i32, _i32]),
     "deepaco_cvrp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "deepaco_cvrp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
+    "deepaco_pick_move": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "deepaco_pick_move_offset_increment": (_u64, [_i32, _i32]),
     "deepaco_logp_backward": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp]),
     "deepaco_debug_exponential": (_i32, [_u64, _u64, _i64, _vp, _vp]),
     "deepaco_debug_randint": (_i32, [_u64, _u64, _i64, _i64, _vp, _vp]),

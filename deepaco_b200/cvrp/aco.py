@@ -91,6 +91,33 @@ class ACO:
         paths, logp = construct(ph.detach(), heu.detach())
         return (paths, logp) if require_prob else paths
 
+    # ---- the step-level pieces of the reference's gen_path (cvrp/aco.py:167-205), for callers that drive the
+    # construction themselves; gen_path above keeps all of this state inside one kernel ----------------------------
+    def pick_move(self, prev, visit_mask, capacity_mask, require_prob):
+        return E.pick_move_for(self, prev, visit_mask, capacity_mask, require_prob)
+
+    def update_visit_mask(self, visit_mask, actions):
+        '''cvrp/aco.py:176-180, in place: the chosen node becomes unavailable, the depot stays available unless the
+        ant sits on it while customers remain.'''
+        ants = torch.arange(self.n_ants, device=visit_mask.device)
+        visit_mask[ants, actions] = 0
+        customers_left = (visit_mask[:, 1:] != 0).any(dim=1)
+        visit_mask[:, 0] = torch.where((actions == 0) & customers_left, 0.0, 1.0).to(visit_mask.dtype)
+        return visit_mask
+
+    def update_capacity_mask(self, cur_nodes, used_capacity):
+        '''cvrp/aco.py:182-202: -> (used_capacity, capacity_mask [n_ants, problem_size]); the load resets at the depot
+        (in place, like the reference), then customers whose demand exceeds the remaining capacity are masked.'''
+        used_capacity[cur_nodes == 0] = 0
+        used_capacity = used_capacity + self.demand[cur_nodes]
+        remaining = (self.capacity - used_capacity).unsqueeze(-1)
+        capacity_mask = (~(self.demand.unsqueeze(0) > remaining)).to(torch.float32)
+        return used_capacity, capacity_mask
+
+    def check_done(self, visit_mask, actions):
+        '''cvrp/aco.py:204-205: every customer served and every ant back at the depot.'''
+        return (visit_mask[:, 1:] == 0).all() and (actions == 0).all()
+
     @torch.no_grad()
     def gen_path_costs(self, paths):
         costs, _ = E.cvrp_cost(self.distances, paths=paths)

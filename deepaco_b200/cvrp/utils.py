@@ -1,4 +1,4 @@
-"""Instance helpers with the reference's names (reference cvrp/utils.py:4-33)."""
+"""Instance helpers and the test-set loader with the reference's names (reference cvrp/utils.py:4-40)."""
 import torch
 
 from ..net import Data
@@ -9,9 +9,9 @@ DEMAND_HIGH = 9
 DEPOT_COOR = [0.5, 0.5]
 
 
-def gen_distance_matrix(coordinates):
-    n = len(coordinates)
-    d = torch.norm(coordinates[:, None] - coordinates, dim=2, p=2)
+def gen_distance_matrix(tsp_coordinates):
+    n = len(tsp_coordinates)
+    d = torch.norm(tsp_coordinates[:, None] - tsp_coordinates, dim=2, p=2)
     d[torch.arange(n), torch.arange(n)] = 1e-10      # cvrp/utils.py:21
     return d
 
@@ -31,3 +31,10 @@ def gen_pyg_data(demands, distances, device):
     nodes = torch.arange(n, device=device)
     edge_index = torch.stack((nodes.repeat(n), torch.repeat_interleave(nodes, n)))
     return Data(x=demands.unsqueeze(1), edge_attr=distances.reshape((n * n, 1)), edge_index=edge_index)
+
+
+def load_test_dataset(problem_size, device):
+    '''cvrp/utils.py:35-40: rows of the saved [count, n+2, n+1] tensor -> [(demands [n+1], distances [n+1, n+1])]
+    (the file is written by the reference's own `python utils.py`, seed 123456; path relative to the repo root).'''
+    dataset = torch.load(f'./data/cvrp/testDataset-{problem_size}.pt', map_location=device)
+    return [(inst[0], inst[1:]) for inst in dataset]

@@ -128,6 +128,12 @@ class ACO:
         paths, logp = construct(ph.detach(), heu.detach())
         return (paths, logp) if require_prob else paths
 
+    def pick_move(self, prev, mask, require_prob):
+        '''One construction step for caller-held state (tsp/aco.py:165-177): prev [n_ants] previous nodes, mask
+        [n_ants, problem_size] with 0 for visited cities -> (actions [n_ants], log_probs [n_ants] | None).  gen_path
+        does not go through here (its masks never leave the kernel).'''
+        return E.pick_move_for(self, prev, mask, None, require_prob)
+
     @torch.no_grad()
     def gen_path_costs(self, paths):
         assert paths.shape == (self.problem_size, self.n_ants)

@@ -1,4 +1,5 @@
-"""Instance -> graph helpers with the reference's names (reference tsp/utils.py:4-36).  One-off set-up per instance."""
+"""Instance -> graph helpers and dataset loaders with the reference's names (reference tsp/utils.py:4-54).
+One-off set-up per instance."""
 import torch
 
 from ..net import Data
@@ -12,7 +13,7 @@ def gen_distance_matrix(tsp_coordinates):
     return d
 
 
-def gen_pyg_data(tsp_coordinates, k_sparse, start_node=None):
+def knn_graph(tsp_coordinates, k_sparse, start_node=None):
     '''k-nearest-neighbour graph (tsp/utils.py:16-36; start_node one-hot node feature as tsp_nls/utils.py:37-43).'''
     n = len(tsp_coordinates)
     distances = gen_distance_matrix(tsp_coordinates)
@@ -25,3 +26,23 @@ def gen_pyg_data(tsp_coordinates, k_sparse, start_node=None):
         x = torch.zeros((n, 1), device=tsp_coordinates.device, dtype=tsp_coordinates.dtype)
         x[start_node, 0] = 1.0
     return Data(x=x, edge_index=edge_index, edge_attr=near_d.reshape(-1, 1)), distances
+
+
+def gen_pyg_data(tsp_coordinates, k_sparse):
+    '''tsp/utils.py:16-36 -> (pyg_data, distances).'''
+    return knn_graph(tsp_coordinates, k_sparse)
+
+
+def instances_to_graphs(coordinates, k_sparse, device, start_node=None):
+    '''[(pyg_data, distances)] for a [count, n, 2] tensor of instances, built on `device`.'''
+    return [knn_graph(instance.to(device), k_sparse, start_node) for instance in coordinates]
+
+
+def load_val_dataset(n_node, k_sparse, device):
+    '''tsp/utils.py:38-45: the shipped validation instances (path relative to the problem directory, as there).'''
+    return instances_to_graphs(torch.load(f'../data/tsp/valDataset-{n_node}.pt'), k_sparse, device)
+
+
+def load_test_dataset(n_node, k_sparse, device):
+    '''tsp/utils.py:47-54.'''
+    return instances_to_graphs(torch.load(f'../data/tsp/testDataset-{n_node}.pt'), k_sparse, device)

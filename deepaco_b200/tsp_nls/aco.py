@@ -37,6 +37,14 @@ class ACO(_TspACO):
         paths, log_probs = self.gen_path(require_prob=True)
         return self.gen_path_costs(paths), log_probs, paths
 
+    def gen_numpy_path_costs(self, paths, numpy_distances):
+        '''tsp_nls/aco.py:171-182: closed-tour lengths of host tours, paths numpy [n_ants, problem_size] (note the
+        shape) -> numpy [n_ants].  A host-array helper by definition (the reference's NLS compares tours with it on
+        the CPU); the device-side NLS reproduces the same float32 pairwise sum inside deepaco_tsp_nls.'''
+        import numpy as np
+        assert paths.shape == (self.n_ants, self.problem_size)
+        return np.sum(numpy_distances[paths, np.roll(paths, shift=1, axis=1)], axis=1)
+
     def sample_2opt(self, paths):
         paths = self.local_search(paths)
         return self.gen_path_costs(paths), paths

@@ -284,6 +284,17 @@ typedef struct {
 } deepaco_cvrp_run_args;
 int deepaco_cvrp_run(const deepaco_cvrp_run_args* args, int n_iterations, void* stream);
 
+/* ---- one construction step with caller-supplied masks: ACO.pick_move (tsp/aco.py:165-177, cvrp/aco.py:167-174)
+ * pheromone_pow / heuristic_pow: fp32 [n][n], already raised to alpha / beta (heuristic_pow may be NULL: ones);
+ * prev int64 [n_ants]; mask fp32 [n_ants][n]; mask2 fp32 [n_ants][n] or NULL (the CVRP capacity mask).
+ * actions int64 [n_ants]; log_probs fp32 [n_ants] or NULL; *bad_prev (device int, caller zeroes) is set if a prev
+ * index is outside [0, n).  The draw is the one `Categorical(x).sample()` makes for the [n_ants, n] tensor at generator
+ * (seed, offset); the caller advances the generator by deepaco_pick_move_offset_increment(n, n_ants). */
+int deepaco_pick_move(const float* pheromone_pow, const float* heuristic_pow, const int64_t* prev, const float* mask,
+                      const float* mask2, int n, int n_ants, uint64_t seed, uint64_t offset, int64_t* actions,
+                      float* log_probs, int* bad_prev, void* stream);
+uint64_t deepaco_pick_move_offset_increment(int n, int n_ants);
+
 /* ---- backward of the log-probabilities (ACO.sample -> REINFORCE loss; tsp/aco.py:165-177, cvrp/aco.py:167-174)
  * Analytic gradient of sum_{t,a} grad_log_probs[t][a] * log_probs[t][a] with respect to the (powered) heuristic
  * and optionally the (powered) pheromone, by replaying the paths (int64 [path_rows][n_ants]).  demand = NULL:
