@@ -80,6 +80,7 @@ class GnnTrainArgs(C.Structure):
 
 _SIGNATURES["deepaco_gnn_train_forward"] = (_i32, [C.POINTER(GnnTrainArgs), _vp])
 _SIGNATURES["deepaco_gnn_train_backward"] = (_i32, [C.POINTER(GnnTrainArgs), _vp])
+_SIGNATURES["deepaco_gnn_forward_group"] = (_i32, [C.POINTER(GnnTrainArgs), _vp])
 _SIGNATURES["deepaco_cvrp_run"] = (_i32, [C.POINTER(CvrpRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp])

@@ -48,16 +48,26 @@ static int launch_groups(Kernel kernel, TrainParams p, int n_instances, int ctas
 
 extern "C" int deepaco_gnn_train_forward(const deepaco_gnn_train_args* a, void* stream) {
     TrainParams p;
-    if (const char* err = gnn_train_params(a, false, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_forward: %s", err);
+    if (const char* err = gnn_train_params(a, kTrainForward, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_forward: %s", err);
     const int threads = a->n_edges >= 2048 * a->ctas_per_instance ? 512 : 256;
-    return launch_groups(gnn_train_forward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
+    return launch_groups(gnn_group_forward_kernel<true>, p, a->n_instances, a->ctas_per_instance, threads,
                             smem_floats_fwd(threads) * 4, (cudaStream_t)stream);
 }
 
 extern "C" int deepaco_gnn_train_backward(const deepaco_gnn_train_args* a, void* stream) {
     TrainParams p;
-    if (const char* err = gnn_train_params(a, true, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_backward: %s", err);
+    if (const char* err = gnn_train_params(a, kTrainBackward, p)) DACO_CHECK_ARG(false, "deepaco_gnn_train_backward: %s", err);
     const int threads = 256;
     return launch_groups(gnn_train_backward_kernel, p, a->n_instances, a->ctas_per_instance, threads,
                             smem_floats_bwd(threads) * 4, (cudaStream_t)stream);
+}
+
+// eval-mode forward (running-statistics BatchNorm) by a group of CTAs per graph: the low-latency form of
+// deepaco_gnn_forward for one or a few instances (Net.forward in eval mode, tsp/net.py:84-88)
+extern "C" int deepaco_gnn_forward_group(const deepaco_gnn_train_args* a, void* stream) {
+    TrainParams p;
+    if (const char* err = gnn_train_params(a, kEvalForward, p)) DACO_CHECK_ARG(false, "deepaco_gnn_forward_group: %s", err);
+    const int threads = a->n_edges >= 2048 * a->ctas_per_instance ? 512 : 256;
+    return launch_groups(gnn_group_forward_kernel<false>, p, a->n_instances, a->ctas_per_instance, threads,
+                         smem_floats_fwd(threads) * 4, (cudaStream_t)stream);
 }

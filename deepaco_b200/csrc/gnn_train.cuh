@@ -292,9 +292,15 @@ inline size_t smem_floats_bwd(int nth) {
 }
 
 // =================================================================================================================
-// forward, training mode
+// forward.  TRAIN: batch-statistics BatchNorm, every activation the backward needs is saved (XS / WS hold all 13
+// layers, ZV / ZE the pre-BatchNorm values).  !TRAIN (eval mode, deepaco_gnn_forward_group): running statistics from
+// the mean / invstd slots of the packed weights, so a layer is two phases instead of four with no group reduction;
+// XS / WS are two-layer ping-pong buffers; ZV / ZE / stats / red are not touched.  The point of the eval variant is
+// latency: the reference's inference drivers run one instance at a time (tsp/test.ipynb infer_instance), and one
+// instance on one CTA (gnn.cu) leaves 147 SMs idle.
 // =================================================================================================================
-__global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParams p) {
+template <bool TRAIN>
+__global__ void __launch_bounds__(512) gnn_group_forward_kernel(const TrainParams p) {
     DACO_DYN_SMEM(smem_raw);
     Cta c;
     c.init(p.grid_ctas, p.sync_ctr, p.b0);
@@ -304,17 +310,39 @@ __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParam
     const int32_t* rp = p.row_ptr + (size_t)b * (n + 1);
     const int32_t* srcs = p.src + (size_t)b * E;
     const int32_t* dsts = p.dst + (size_t)b * E;
-    float* XS = p.XS + (size_t)b * (kDepth + 1) * n * U;
-    float* WS = p.WS + (size_t)b * (kDepth + 1) * E * U;
-    float* ZV = p.ZV + (size_t)b * kDepth * n * U;
-    float* ZE = p.ZE + (size_t)b * kDepth * E * U;
-    float* NW = p.node_ws + (size_t)b * n * 7 * U;
+    constexpr int kKept = TRAIN ? kDepth + 1 : 2;              // layers of x / w kept per instance
+    float* XS = p.XS + (size_t)b * kKept * n * U;
+    float* WS = p.WS + (size_t)b * kKept * E * U;
+    float* ZV = TRAIN ? p.ZV + (size_t)b * kDepth * n * U : nullptr;
+    float* ZE = TRAIN ? p.ZE + (size_t)b * kDepth * E * U : nullptr;
+    float* NW = p.node_ws + (size_t)b * n * (TRAIN ? 7 : 4) * U;
     float* X1 = NW, *X2 = NW + (size_t)n * U, *X3 = NW + (size_t)2 * n * U, *X4 = NW + (size_t)3 * n * U;
-    float* red = p.red + (size_t)b * kRedSlots * kMaxCtas * kRedStride;
+    float* red = TRAIN ? p.red + (size_t)b * kRedSlots * kMaxCtas * kRedStride : nullptr;
     const int off_layers = U * F + 3 * U;
     const float* layers_g = p.weights + off_layers;
     const float* head_g = layers_g + (size_t)kDepth * kLayerFloats;
     const float inv_n = 1.0f / (float)n, inv_E = 1.0f / (float)E;
+    // pre-BatchNorm node activation of (node i, feature f): x1 + mean over the out-edges of sigmoid(w) * x2[dst]
+    auto node_pre = [&](const float* Wl, int i, int f) -> float {
+        const int e0 = rp[i], e1 = rp[i + 1];
+        float a = 0.f;
+        int e = e0;
+        for (; e + 8 <= e1; e += 8) {                          // 8 independent gathers in flight; same summation order
+            int d[8];
+            float wv[8], xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = dsts[e + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[j] = ld_cg(Wl + (size_t)(e + j) * U + f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = ld_cg(X2 + (size_t)d[j] * U + f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a += sigmoid_f(wv[j]) * xv[j];
+        }
+        for (; e < e1; ++e) a += sigmoid_f(ld_cg(Wl + (size_t)e * U + f)) * ld_cg(X2 + (size_t)dsts[e] * U + f);
+        const int deg = e1 - e0;
+        return ld_cg(X1 + (size_t)i * U + f) + a / (float)(deg > 0 ? deg : 1);
+    };
 
     for (int i = tid; i < off_layers; i += nth) s.w0s[i] = p.weights[i];
     for (int i = tid; i < kHeadFloats; i += nth) s.head[i] = head_g[i];
@@ -336,12 +364,14 @@ __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParam
     }
 
     for (int l = 0; l < kDepth; ++l) {
-        const float* Xl = XS + (size_t)l * n * U;
-        float* Xn = XS + (size_t)(l + 1) * n * U;
-        const float* Wl = WS + (size_t)l * E * U;
-        float* Wn = WS + (size_t)(l + 1) * E * U;
-        float* Zv = ZV + (size_t)l * n * U;
-        float* Ze = ZE + (size_t)l * E * U;
+        const float* Xl = XS + (size_t)(TRAIN ? l : l & 1) * n * U;
+        float* Xn = XS + (size_t)(TRAIN ? l + 1 : (l + 1) & 1) * n * U;
+        const float* Wl = WS + (size_t)(TRAIN ? l : l & 1) * E * U;
+        float* Wn = WS + (size_t)(TRAIN ? l + 1 : (l + 1) & 1) * E * U;
+        float* Zv = TRAIN ? ZV + (size_t)l * n * U : nullptr;
+        float* Ze = TRAIN ? ZE + (size_t)l * E * U : nullptr;
+        // eval: x_12 is never read (EmbNet.forward returns w, tsp/net.py:45) -> no node update in the last layer
+        const bool node_update = TRAIN || l + 1 < kDepth;
         c.sync_all();                                          // x_l, w_l complete; s.wl no longer read
         for (int i = tid; i < kLayerFloats; i += nth) s.wl[i] = layers_g[(size_t)l * kLayerFloats + i];
         __syncthreads();
@@ -351,34 +381,43 @@ __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParam
         // ---- P1 node linears: task = (node, which linear)
         for (int t = c.gt; t < n * 4; t += c.gn) {
             const int i = t >> 2, q = t & 3;
+            if (!node_update && q < 2) continue;               // x1, x2 only feed the node update
             float in[U], out[U];
             load_row(Xl + (size_t)i * U, in);
             linear32(s.wl + q * LIN, in, out);
             store_row((q == 0 ? X1 : q == 1 ? X2 : q == 2 ? X3 : X4) + (size_t)i * U, out);
         }
         c.sync_all();
+        if constexpr (!TRAIN) {
+            // ---- eval: pre-activation, BatchNorm with the running statistics, activation and residual in one phase
+            const float* mean_v = bnv + 2 * U, *istd_v = bnv + 3 * U, *mean_e = bne + 2 * U, *istd_e = bne + 3 * U;
+            if (node_update) {
+                for (int t = c.gt; t < n * U; t += c.gn) {
+                    const int i = t / U, f = t % U;
+                    const float z = node_pre(Wl, i, f);
+                    // same expression as gnn.cu (no fused multiply-add): both eval kernels return the same bits
+                    Xn[t] = ld_cg(Xl + t) + silu_f((z - mean_v[f]) * istd_v[f] * bnv[f] + bnv[U + f]);
+                }
+            }
+            for (int e = c.gt; e < E; e += c.gn) {
+                float w[U], z[U], a3[U], a4[U];
+                load_row(Wl + (size_t)e * U, w);
+                linear32(We, w, z);
+                load_row(X3 + (size_t)srcs[e] * U, a3);
+                load_row(X4 + (size_t)dsts[e] * U, a4);
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const float zk = z[k] + a3[k] + a4[k];
+                    w[k] += silu_f((zk - mean_e[k]) * istd_e[k] * bne[k] + bne[U + k]);
+                }
+                store_row(Wn + (size_t)e * U, w);
+            }
+            continue;                                          // the barrier at the top of the next iteration orders the stores
+        }
         // ---- P2 pre-BatchNorm activations + per-feature sums
         float sv = 0.f;
         for (int t = c.gt; t < n * U; t += c.gn) {             // gn is a multiple of 32: feature = tid % 32
-            const int i = t / U, f = t % U;
-            const int e0 = rp[i], e1 = rp[i + 1];
-            float a = 0.f;
-            int e = e0;
-            for (; e + 8 <= e1; e += 8) {                      // 8 independent gathers in flight; same summation order
-                int d[8];
-                float wv[8], xv[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) d[j] = dsts[e + j];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) wv[j] = ld_cg(Wl + (size_t)(e + j) * U + f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xv[j] = ld_cg(X2 + (size_t)d[j] * U + f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a += sigmoid_f(wv[j]) * xv[j];
-            }
-            for (; e < e1; ++e) a += sigmoid_f(ld_cg(Wl + (size_t)e * U + f)) * ld_cg(X2 + (size_t)dsts[e] * U + f);
-            const int deg = e1 - e0;
-            const float z = ld_cg(X1 + t) + a / (float)(deg > 0 ? deg : 1);
+            const float z = node_pre(Wl, t / U, t % U);
             Zv[t] = z;
             sv += z;
         }
@@ -450,7 +489,7 @@ __global__ void __launch_bounds__(512) gnn_train_forward_kernel(const TrainParam
     // ---- head MLP per edge (net.py:62-75); every thread reads only the w_12 rows it wrote itself
     const float* H0 = s.head, *H1 = s.head + LIN, *H2 = s.head + 2 * LIN;
     const int32_t* order = p.order + (size_t)b * E;
-    const float* W12 = WS + (size_t)kDepth * E * U;
+    const float* W12 = WS + (size_t)(TRAIN ? kDepth : kDepth & 1) * E * U;
     for (int e = c.gt; e < E; e += c.gn) {
         float in[U], h[U];
         load_row(W12 + (size_t)e * U, in);

@@ -6,14 +6,18 @@
 namespace deepaco {
 namespace gnnt {
 
+enum GroupCall { kTrainForward, kTrainBackward, kEvalForward };
+
 // returns NULL on success, otherwise the reason
-inline const char* gnn_train_params(const deepaco_gnn_train_args* a, bool backward, TrainParams& p) {
+inline const char* gnn_train_params(const deepaco_gnn_train_args* a, GroupCall call, TrainParams& p) {
     if (!a) return "NULL args";
     if (!(a->x && a->row_ptr && a->src_sorted && a->dst_sorted && a->attr_sorted && a->order && a->weights && a->xs && a->ws &&
-          a->zv && a->ze && a->stats && a->node_ws && a->red && a->sync_ws))
+          a->node_ws && a->sync_ws))
         return "NULL argument";
-    if (!backward && !a->heu_out) return "NULL heu_out";
-    if (backward && !(a->grad_heu && a->grad_weights && a->edge_ws && a->col_ptr && a->in_edges)) return "NULL backward argument";
+    if (call != kEvalForward && !(a->zv && a->ze && a->stats && a->red)) return "NULL argument";
+    if (call != kTrainBackward && !a->heu_out) return "NULL heu_out";
+    if (call == kTrainBackward && !(a->grad_heu && a->grad_weights && a->edge_ws && a->col_ptr && a->in_edges))
+        return "NULL backward argument";
     if (!(a->n_nodes >= 1 && a->n_edges >= 1 && a->feats >= 1 && a->feats <= 8 && a->n_instances >= 1)) return "bad sizes";
     const int c = a->ctas_per_instance;
     if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 16 || c == 32 || c == 64)) return "ctas_per_instance must be 1, 2, 4, 8, 16, 32 or 64";

@@ -154,6 +154,11 @@ def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None):
     B, n = x.shape[0], x.shape[1]
     E = edge_index.shape[-1]
     _lib.require_cuda(x, "pyg.x")
+    if dense_eps is None:
+        ctas = group_ctas(E, B)
+        if ctas > 1:                          # few instances: several CTAs per graph instead of one (latency)
+            out = gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas)
+            return out if batched else out[0]
     rps, orders = zip(*(csr_by_source(edge_index[b], n) for b in range(B)))
     row_ptr, order = torch.stack(rps).contiguous(), torch.stack(orders).contiguous()
     ol = order.long()
@@ -184,16 +189,15 @@ def knn_heuristic_matrices(weights, feats, node_features, distances, k_sparse, e
 # ---------------------------------------------------------------------------------------------------------------
 # training mode (deepaco_gnn_train_forward / _backward)
 # ---------------------------------------------------------------------------------------------------------------
-def train_graph(edge_index, edge_attr, n_nodes):
+def train_graph(edge_index, edge_attr, n_nodes, backward=True):
     """Graph arrays of deepaco_gnn_train_args for edge_index [B, 2, E], edge_attr [B, E(,1)]: edges sorted by source
-    (stable) with their CSR, and the same edges grouped by destination (stable) with their CSC."""
+    (stable) with their CSR, and (backward=True) the same edges grouped by destination (stable) with their CSC."""
     B, E = edge_index.shape[0], edge_index.shape[-1]
     dev = edge_index.device
     src, dst = edge_index[:, 0], edge_index[:, 1]
     order = torch.argsort(src, dim=1, stable=True)
     src_s, dst_s = torch.gather(src, 1, order), torch.gather(dst, 1, order)
     attr_s = torch.gather(edge_attr.reshape(B, E).to(torch.float32), 1, order)
-    in_edges = torch.argsort(dst_s, dim=1, stable=True)
 
     def ptrs(keys):
         counts = torch.zeros((B, n_nodes), dtype=torch.int64, device=dev).scatter_add_(1, keys, torch.ones_like(keys))
@@ -202,8 +206,11 @@ def train_graph(edge_index, edge_attr, n_nodes):
         return out
 
     i32 = lambda t: t.to(torch.int32).contiguous()
-    return {"row_ptr": ptrs(src_s), "src": i32(src_s), "dst": i32(dst_s), "attr": attr_s.contiguous(), "order": i32(order),
-            "col_ptr": ptrs(dst_s), "in_edges": i32(in_edges), "n": n_nodes, "E": E, "B": B}
+    g = {"row_ptr": ptrs(src_s), "src": i32(src_s), "dst": i32(dst_s), "attr": attr_s.contiguous(), "order": i32(order),
+         "col_ptr": None, "in_edges": None, "n": n_nodes, "E": E, "B": B}
+    if backward:
+        g["col_ptr"], g["in_edges"] = ptrs(dst_s), i32(torch.argsort(dst_s, dim=1, stable=True))
+    return g
 
 
 def train_buffers(B, n, E, device):
@@ -215,14 +222,51 @@ def train_buffers(B, n, E, device):
             "sync_ws": torch.zeros(B, dtype=torch.int32, device=device)}
 
 
+_EVAL_SCRATCH = {}
+
+
+def eval_buffers(B, n, E, device):
+    """Scratch of deepaco_gnn_forward_group: two-layer ping-pong node / edge state, the four node linears, counters."""
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+    return {"xs": f(B, 2, n, UNITS), "ws": f(B, 2, E, UNITS), "node_ws": f(B, n, 4 * UNITS),
+            "sync_ws": torch.zeros(B, dtype=torch.int32, device=device)}
+
+
 def train_args(x, graph, weights, bufs, feats, ctas, bn_eps, heu_out=None, grad_heu=None, grad_weights=None):
     """Fill a deepaco_gnn_train_args struct; returns (struct, keep-alive list)."""
     p = lambda t: None if t is None else t.data_ptr()
     a = _lib.GnnTrainArgs(graph["n"], graph["E"], feats, graph["B"], ctas, bn_eps, p(x), p(graph["row_ptr"]), p(graph["src"]),
                           p(graph["dst"]), p(graph["attr"]), p(graph["order"]), p(graph["col_ptr"]), p(graph["in_edges"]),
-                          p(weights), p(bufs["xs"]), p(bufs["ws"]), p(bufs["zv"]), p(bufs["ze"]), p(bufs["stats"]),
-                          p(bufs["node_ws"]), p(bufs["edge_ws"]), p(bufs["red"]), p(bufs["sync_ws"]), p(heu_out), p(grad_heu), p(grad_weights))
+                          p(weights), p(bufs["xs"]), p(bufs["ws"]), p(bufs.get("zv")), p(bufs.get("ze")), p(bufs.get("stats")),
+                          p(bufs["node_ws"]), p(bufs.get("edge_ws")), p(bufs.get("red")), p(bufs["sync_ws"]), p(heu_out),
+                          p(grad_heu), p(grad_weights))
     return a, [x, graph, weights, bufs, heu_out, grad_heu, grad_weights]
+
+
+def group_ctas(n_edges, n_instances):
+    """CTAs per graph for the eval-mode group forward: what the training kernels use for this graph size, halved until
+    the whole batch fits the device twice over (296 CTAs); 1 means "use the one-CTA-per-instance kernel"."""
+    ctas = default_train_ctas(n_edges)
+    while ctas > 1 and ctas * n_instances > 296:
+        ctas //= 2
+    return ctas
+
+
+def gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas):
+    """deepaco_gnn_forward_group: eval-mode Net.forward of [B, ...] graphs (identical n and E) by `ctas` CTAs per graph."""
+    import ctypes
+    B, n = x.shape[0], x.shape[1]
+    graph = train_graph(edge_index, edge_attr, n, backward=False)
+    dev = x.device
+    key = (B, n, graph["E"], dev, torch.cuda.current_stream(dev).cuda_stream)
+    if _EVAL_SCRATCH.get("key") != key:          # scratch is reused call after call on one stream (stream-ordered)
+        _EVAL_SCRATCH["key"], _EVAL_SCRATCH["bufs"] = key, eval_buffers(B, n, graph["E"], dev)
+    bufs = _EVAL_SCRATCH["bufs"]
+    heu = torch.empty((B, graph["E"]), dtype=torch.float32, device=dev)
+    a, keep = train_args(x.to(torch.float32).contiguous(), graph, weights, bufs, feats, ctas, 1e-5, heu_out=heu)
+    with torch.cuda.device(dev):
+        check(lib().deepaco_gnn_forward_group(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_forward_group")
+    return heu
 
 
 def default_train_ctas(n_edges):

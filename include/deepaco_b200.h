@@ -223,6 +223,12 @@ typedef struct deepaco_gnn_train_args {
 } deepaco_gnn_train_args;
 int deepaco_gnn_train_forward(const deepaco_gnn_train_args* args, void* stream);
 int deepaco_gnn_train_backward(const deepaco_gnn_train_args* args, void* stream);
+/* Eval-mode Net.forward (tsp/net.py:84-88, running-statistics BatchNorm) by a group of ctas_per_instance CTAs per
+ * graph: the low-latency form of deepaco_gnn_forward for one or a few instances (the reference's inference drivers
+ * process one instance at a time).  Same argument block; `weights` in the eval packing (mean / invstd slots filled),
+ * xs [B][2][n][32], ws [B][2][E][32], node_ws [B][n][128], sync_ws as above, heu_out [B][E]; zv / ze / stats / red /
+ * edge_ws / col_ptr / in_edges / grad_* are not used and may be NULL. */
+int deepaco_gnn_forward_group(const deepaco_gnn_train_args* args, void* stream);
 
 /* ---- CVRP (cvrp/aco.py:106-205, adaptive = False) ----------------------------------------------
  * Node 0 is the depot; n_nodes = customers + 1; demand fp32 [B][n_nodes] (demand[0] = 0).

@@ -43,6 +43,18 @@ int main(int argc, char** argv) {
     std::vector<uint32_t> sync_ws(B, 0);
     a.sync_ws = sync_ws.data();
     a.edge_ws = edge_ws.data(); a.red = red.data(); a.heu_out = heu.data(); a.grad_heu = g_heu.data(); a.grad_weights = grad.data();
+    {   // eval-mode group forward first (ping-pong state in the first two layers of xs / ws; positive invstd slots)
+        for (int l = 0; l < 12; ++l)
+            for (int k = 0; k < 2; ++k)
+                for (int f = 0; f < 32; ++f) {
+                    float& istd = weights[32 * F + 96 + (size_t)l * deepaco::gnnt::kLayerFloats + 5 * deepaco::gnnt::LIN + k * 128 + 96 + f];
+                    istd = std::fabs(istd) + 0.5f;
+                }
+        if (const char* err = emu_gnn_forward_group(&a, nth_f)) { printf("eval forward: %s\n", err); return 2; }
+        double es = 0;
+        for (float v : heu) es += v;
+        if (!std::isfinite(es)) { printf("non-finite eval output\n"); return 3; }
+    }
     if (const char* err = emu_gnn_train_forward(&a, nth_f)) { printf("forward: %s\n", err); return 2; }
     if (const char* err = emu_gnn_train_backward(&a, nth_b)) { printf("backward: %s\n", err); return 2; }
     double hs = 0, gs = 0;

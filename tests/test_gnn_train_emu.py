@@ -27,7 +27,7 @@ def emu():
     subprocess.run(["make", "-C", EMU_DIR, "-s"], check=True)
     h = ctypes.CDLL(out)
     from deepaco_b200._lib import GnnTrainArgs
-    for fn in (h.emu_gnn_train_forward, h.emu_gnn_train_backward):
+    for fn in (h.emu_gnn_train_forward, h.emu_gnn_train_backward, h.emu_gnn_forward_group):
         fn.restype = ctypes.c_char_p
         fn.argtypes = [ctypes.POINTER(GnnTrainArgs), ctypes.c_int]
     return h
@@ -212,3 +212,35 @@ def test_barrier_placement_under_thread_sanitizer():
     r = subprocess.run(["make", "-C", EMU_DIR, "tsan"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("tsan run ok") == 4
+
+
+@pytest.mark.parametrize("kind,fixture", CASES)
+@pytest.mark.parametrize("ctas,threads", [(1, 256), (2, 128), (8, 64), (16, 64)])
+def test_eval_mode_group_forward_on_host_matches_the_restatement(emu, golden, kind, fixture, ctas, threads):
+    """deepaco_gnn_forward_group (eval mode: running-statistics BatchNorm, two-phase layers, ping-pong state) through
+    the host build of the kernel source, against the torch restatement in eval mode with the pretrained checkpoint
+    (itself pinned to the reference's eval output by tests/test_oracle_golden.py)."""
+    from deepaco_b200 import net as N
+    from oracle import net_torch
+    g = golden(fixture)
+    net = _net(kind).eval()
+    pyg = _pyg(g)
+    with torch.no_grad():
+        want = net_torch.net_forward(net, pyg)
+    n_copies = 2
+    x = pyg.x.to(torch.float32)[None].repeat(n_copies, 1, 1).contiguous()
+    ei = pyg.edge_index[None].repeat(n_copies, 1, 1)
+    ea = pyg.edge_attr[None].repeat(n_copies, 1, 1)
+    n = x.shape[1]
+    graph = N.train_graph(ei, ea, n, backward=False)
+    bufs = N.eval_buffers(n_copies, n, graph["E"], "cpu")
+    for t in bufs.values():
+        if t.is_floating_point():
+            t.fill_(float("nan"))                      # anything read before it is written poisons the result
+    heu = torch.full((n_copies, graph["E"]), float("nan"))
+    a, keep = N.train_args(x, graph, N.pack_weights(net), bufs, net.emb_net.feats, ctas, 1e-5, heu_out=heu)
+    err = emu.emu_gnn_forward_group(ctypes.byref(a), threads)
+    assert err is None, err
+    assert torch.isfinite(heu).all()
+    assert torch.equal(heu[0], heu[1])
+    assert torch.allclose(heu[0], want, rtol=2e-4, atol=1e-7), float((heu[0] - want).abs().max())

@@ -88,3 +88,37 @@ def test_batched_front_end_equals_per_instance_path():
         with torch.no_grad():
             want = net.reshape(pyg, net(pyg)) + 1e-10
         assert torch.equal(dense[b], want)
+
+
+@pytest.mark.parametrize("kind", ["tsp", "tsp_nls", "cvrp"])
+def test_group_forward_returns_the_bits_of_the_single_cta_kernel(kind, monkeypatch):
+    """Eval-mode Net.forward of ONE instance runs on a group of CTAs (deepaco_gnn_forward_group: cluster of 8 at C2,
+    cooperative launch of 64 / 32 at C3 / C4); the one-CTA-per-instance kernel of the batched front end must give the
+    same bits, so a heuristic does not depend on which of the two produced it."""
+    from deepaco_b200 import net as N
+    if kind == "tsp":
+        from deepaco_b200.tsp.net import Net
+        from deepaco_b200.tsp.utils import gen_pyg_data
+        torch.manual_seed(1)
+        net, pyg = _load(Net, "weights_tsp100"), gen_pyg_data(torch.rand(100, 2, device=DEV), 20)[0]
+    elif kind == "tsp_nls":
+        from deepaco_b200.tsp_nls.net import Net
+        from deepaco_b200.tsp_nls.utils import gen_pyg_data
+        torch.manual_seed(2)
+        net, pyg = _load(Net, "weights_tsp_nls500"), gen_pyg_data(torch.rand(500, 2, device=DEV), 50, start_node=0)[0]
+    else:
+        from deepaco_b200.cvrp.net import Net
+        from deepaco_b200.cvrp.utils import gen_instance, gen_pyg_data
+        torch.manual_seed(3)
+        demand, dist = gen_instance(100, DEV)
+        net, pyg = _load(Net, "weights_cvrp100"), gen_pyg_data(demand, dist, DEV)
+    E = pyg.edge_index.shape[1]
+    assert N.group_ctas(E, 1) > 1
+    with torch.no_grad():
+        grouped = net(pyg)
+        monkeypatch.setenv("DEEPACO_GNN_CTAS", "1")              # group size 1 -> deepaco_gnn_forward
+        single = net(pyg)
+        monkeypatch.setenv("DEEPACO_GNN_CTAS", "4")
+        four = net(pyg)
+    assert torch.equal(grouped, single) and torch.equal(four, single)
+    assert float(grouped.min()) >= 0 and float(grouped.max()) <= 1

@@ -75,7 +75,10 @@ for kind in ("C2 tsp n=100 k=20", "C3 tsp_nls n=500 k=50", "C4 cvrp N=101 dense"
     net = Net().to(dev).eval()
     with torch.no_grad():
         t = timeit(lambda: net(pyg), 20, 3)
-    print(f"GNN eval forward {kind}: {t:8.3f} ms / instance (Python front end included)", flush=True)
+        os.environ["DEEPACO_GNN_CTAS"] = "1"
+        t1 = timeit(lambda: net(pyg), 10, 2)
+        os.environ.pop("DEEPACO_GNN_CTAS")
+    print(f"GNN eval forward {kind}: {t:8.3f} ms / instance on a CTA group, {t1:8.3f} ms on one CTA (Python front end included)", flush=True)
 from deepaco_b200.tsp.net import Net as _TspNet  # noqa: E402
 net = _TspNet().to(dev).eval()
 for B, n, k in ((256, 100, 20), (64, 200, 20)):
