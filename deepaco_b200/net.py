@@ -145,9 +145,10 @@ def _launch_gnn(weights, feats, xin, row_ptr, dst_s, attr_s, order, want_vec, de
     return out, dense
 
 
-def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None):
+def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None, graph=None):
     """deepaco_gnn_forward for one graph or a batch ([B, ...] tensors with identical n and E).
-    Returns the edge vector; with dense_eps also the dense heuristic matrix Net.reshape(...) + dense_eps."""
+    Returns the edge vector; with dense_eps also the dense heuristic matrix Net.reshape(...) + dense_eps.
+    `graph`: train_graph(...) of these edges when the caller already has it."""
     batched = x.dim() == 3
     if not batched:
         x, edge_index, edge_attr = x[None], edge_index[None], edge_attr[None]
@@ -157,7 +158,7 @@ def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None):
     if dense_eps is None:
         ctas = group_ctas(E, B)
         if ctas > 1:                          # few instances: several CTAs per graph instead of one (latency)
-            out = gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas)
+            out = gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas, graph=graph)
             return out if batched else out[0]
     rps, orders = zip(*(csr_by_source(edge_index[b], n) for b in range(B)))
     row_ptr, order = torch.stack(rps).contiguous(), torch.stack(orders).contiguous()
@@ -252,11 +253,12 @@ def group_ctas(n_edges, n_instances):
     return ctas
 
 
-def gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas):
+def gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas, graph=None):
     """deepaco_gnn_forward_group: eval-mode Net.forward of [B, ...] graphs (identical n and E) by `ctas` CTAs per graph."""
     import ctypes
     B, n = x.shape[0], x.shape[1]
-    graph = train_graph(edge_index, edge_attr, n, backward=False)
+    if graph is None:
+        graph = train_graph(edge_index, edge_attr, n, backward=False)
     dev = x.device
     key = (B, n, graph["E"], dev, torch.cuda.current_stream(dev).cuda_stream)
     if _EVAL_SCRATCH.get("key") != key:          # scratch is reused call after call on one stream (stream-ordered)
@@ -453,16 +455,28 @@ class Net(nn.Module):
         self._packed_key = None
 
     def _weights(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.state_dict().values())
+        """Eval-mode packed weights, re-packed when any tensor that goes into them was written or re-allocated.  The
+        check walks the _parameters / _buffers dicts of the modules that matter directly (state_dict() costs ~1 ms of
+        Python per call, more than the network itself)."""
+        mods = self.__dict__.get("_pack_modules")
+        if mods is None:
+            mods = [m for part in (self.emb_net, self.par_net_heu) for m in part.modules() if m._parameters or m._buffers]
+            self.__dict__["_pack_modules"] = mods
+        key = tuple((t.data_ptr(), t._version) for m in mods for d in (m._parameters, m._buffers) for t in d.values()
+                    if t is not None)
+        st = self.__dict__.get("_flat_train_state")
+        if st is not None and st.track:      # training mode updates the running statistics through the stacked buffers
+            key += (st.rm._version, st.rv._version)     # they alias (a `.data` view keeps its own version counter)
         if self._packed is None or key != self._packed_key:
             self._packed, self._packed_key = pack_weights(self), key
         return self._packed
 
     def forward(self, pyg):
         x, edge_index, edge_attr = pyg.x, pyg.edge_index, pyg.edge_attr
+        graph = _graph_of(pyg, backward=self.training) if x.dim() == 2 and x.is_cuda else None
         if self.training:
-            return gnn_train_forward(self, x, edge_index, edge_attr)
-        return gnn_forward(self._weights(), self.FEATS, x, edge_index, edge_attr)
+            return gnn_train_forward(self, x, edge_index, edge_attr, graph=graph)
+        return gnn_forward(self._weights(), self.FEATS, x, edge_index, edge_attr, graph=graph)
 
     @torch.no_grad()
     def heuristic_matrices(self, node_features, distances, k_sparse, eps=1e-10):
@@ -488,6 +502,22 @@ def load_npz_state_dict(path, device="cpu"):
     return {k.replace("__", "."): torch.from_numpy(z[k]).to(device) for k in z.files}
 
 
+def _graph_of(pyg, backward):
+    """train_graph(...) of one pyg instance, remembered on the instance when it is this package's own Data (validation
+    and training loops present the same instances every epoch; a foreign Data object is never written to)."""
+    ei, ea = pyg.edge_index, pyg.edge_attr
+    key = (ei.data_ptr(), ei._version, ea.data_ptr(), ea._version, pyg.x.shape[0])
+    own = isinstance(pyg, Data)
+    if own:
+        hit = pyg.__dict__.get("_deepaco_graph")
+        if hit is not None and hit[0] == key and (hit[1]["col_ptr"] is not None or not backward):
+            return hit[1]
+    graph = train_graph(ei[None], ea[None], pyg.x.shape[0], backward=backward)
+    if own:
+        pyg.__dict__["_deepaco_graph"] = (key, graph)
+    return graph
+
+
 class Data:
     """Attribute bag standing in for torch_geometric.data.Data: Net only reads .x, .edge_index, .edge_attr."""
 
@@ -497,6 +527,9 @@ class Data:
 
     def to(self, device):
         for k, v in list(vars(self).items()):
+            if k == "_deepaco_graph":
+                del self.__dict__[k]
+                continue
             if hasattr(v, "to"):
                 setattr(self, k, v.to(device))
         return self

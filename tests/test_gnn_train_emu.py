@@ -244,3 +244,19 @@ def test_eval_mode_group_forward_on_host_matches_the_restatement(emu, golden, ki
     assert torch.isfinite(heu).all()
     assert torch.equal(heu[0], heu[1])
     assert torch.allclose(heu[0], want, rtol=2e-4, atol=1e-7), float((heu[0] - want).abs().max())
+
+
+def test_eval_weights_follow_running_statistics_updated_in_training_mode():
+    """Net._weights() (the eval-mode packed weights, cached) must notice BatchNorm running statistics that a
+    training-mode forward updated through the stacked buffers they alias, even when no parameter changed."""
+    from deepaco_b200 import net as N
+    net = _net("tsp")
+    w0 = net.eval()._weights().clone()
+    st = N.flat_state(net)
+    assert st.track
+    stats = torch.rand(1, N.DEPTH, 6, N.UNITS) + 0.5
+    N._update_running_stats(st, stats, 40, 400)
+    w1 = net._weights()
+    assert not torch.equal(w0, w1)
+    assert torch.equal(w1, N.pack_weights(net))
+    assert net._weights() is w1                                   # unchanged state -> cached tensor
