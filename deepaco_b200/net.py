@@ -187,6 +187,35 @@ def knn_heuristic_matrices(weights, feats, node_features, distances, k_sparse, e
     return dense
 
 
+def dense_graph(distances):
+    """train_graph(...) of the complete graph the CVRP drivers build (cvrp/utils.py:24-33: edge e = i * N + j has source
+    j, destination i and attribute distances[i, j]) for a batch [B, N, N], written down directly: sorted by source the
+    edges of source s are e = i * N + s, i = 0 .. N-1."""
+    B, N = distances.shape[0], distances.shape[1]
+    dev = distances.device
+    E = N * N
+    pos = torch.arange(E, device=dev, dtype=torch.int32)
+    i32 = lambda t: t.to(torch.int32).expand(B, -1).contiguous()
+    return {"row_ptr": i32((torch.arange(N + 1, device=dev) * N)[None]), "src": i32((pos // N)[None]), "dst": i32((pos % N)[None]),
+            "attr": distances.to(torch.float32).transpose(1, 2).reshape(B, E).contiguous(),
+            "order": i32(((pos % N) * N + pos // N)[None]), "col_ptr": None, "in_edges": None, "n": N, "E": E, "B": B}
+
+
+def dense_heuristic_matrices(weights, feats, node_features, distances, eps=1e-10):
+    """Batched instance -> complete graph -> network -> heuristic matrix front end for CVRP (cvrp/utils.py:24-33 +
+    cvrp/test.py:17-19: heu_vec.reshape(N, N) + EPS) without per-instance Python: node_features [B, N, feats],
+    distances [B, N, N] -> [B, N, N]."""
+    B, N = distances.shape[0], distances.shape[1]
+    g = dense_graph(distances)
+    x = node_features.to(torch.float32).contiguous()
+    ctas = group_ctas(g["E"], B)
+    if ctas > 1:
+        vec = gnn_forward_group(weights, feats, x, None, None, ctas, graph=g)
+    else:
+        vec, _ = _launch_gnn(weights, feats, x, g["row_ptr"], g["dst"], g["attr"], g["order"], True, None)
+    return vec.view(B, N, N) + eps
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # training mode (deepaco_gnn_train_forward / _backward)
 # ---------------------------------------------------------------------------------------------------------------
@@ -482,6 +511,11 @@ class Net(nn.Module):
     def heuristic_matrices(self, node_features, distances, k_sparse, eps=1e-10):
         """[B, n, n] heuristic matrices of a batch of k-NN TSP instances in one launch (eval mode)."""
         return knn_heuristic_matrices(self._weights(), self.FEATS, node_features, distances, k_sparse, eps)
+
+    @torch.no_grad()
+    def dense_heuristic_matrices(self, node_features, distances, eps=1e-10):
+        """[B, N, N] heuristic matrices of a batch of complete-graph (CVRP) instances in one launch (eval mode)."""
+        return dense_heuristic_matrices(self._weights(), self.FEATS, node_features, distances, eps)
 
     def freeze_gnn(self):
         for p in self.emb_net.parameters():

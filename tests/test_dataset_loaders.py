@@ -54,3 +54,19 @@ def test_cvrp_loader(tmp_path, monkeypatch):
     assert demands.shape == (10,) and dist.shape == (10, 10) and float(demands[0]) == 0.0
     assert torch.equal(torch.cat((demands.unsqueeze(0), dist)), insts[2])
     assert dist[3, 3] == torch.tensor(1e-10)
+
+
+def test_complete_graph_arrays_written_directly_equal_the_sorted_edge_list():
+    """deepaco_b200.net.dense_graph (the batched CVRP front end) == train_graph of the edge list cvrp/utils.py builds."""
+    from deepaco_b200 import net as N
+    from deepaco_b200.cvrp import utils as C
+    torch.manual_seed(4)
+    insts = [C.gen_instance(8, "cpu") for _ in range(3)]
+    dist = torch.stack([d for _, d in insts])
+    got = N.dense_graph(dist)
+    for b, (demands, d) in enumerate(insts):
+        pyg = C.gen_pyg_data(demands, d, "cpu")
+        want = N.train_graph(pyg.edge_index[None], pyg.edge_attr[None], 9, backward=False)
+        for k in ("row_ptr", "src", "dst", "attr", "order"):
+            assert torch.equal(got[k][b], want[k][0]), k
+    assert got["E"] == 81 and got["n"] == 9 and got["B"] == 3

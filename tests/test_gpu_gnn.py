@@ -122,3 +122,23 @@ def test_group_forward_returns_the_bits_of_the_single_cta_kernel(kind, monkeypat
         four = net(pyg)
     assert torch.equal(grouped, single) and torch.equal(four, single)
     assert float(grouped.min()) >= 0 and float(grouped.max()) <= 1
+
+
+@pytest.mark.parametrize("customers,count", [(20, 5), (100, 3)])
+def test_dense_batched_front_end_equals_per_instance_path(customers, count):
+    """demands, distances -> complete graph -> Net -> reshape(N, N) + EPS for a whole CVRP batch in one launch == the
+    per-instance gen_pyg_data / Net.forward / reshape sequence of cvrp/test.py:14-19."""
+    from deepaco_b200.cvrp.net import Net
+    from deepaco_b200.cvrp.utils import gen_instance, gen_pyg_data
+    net = _load(Net, "weights_cvrp100")
+    torch.manual_seed(6)
+    insts = [gen_instance(customers, DEV) for _ in range(count)]
+    demands = torch.stack([d for d, _ in insts])
+    dist = torch.stack([m for _, m in insts])
+    N = customers + 1
+    dense = net.dense_heuristic_matrices(demands.unsqueeze(-1), dist)
+    assert dense.shape == (count, N, N)
+    for b, (d, m) in enumerate(insts):
+        with torch.no_grad():
+            want = net(gen_pyg_data(d, m, DEV)).reshape(N, N) + 1e-10
+        assert torch.equal(dense[b], want)
