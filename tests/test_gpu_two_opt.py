@@ -106,3 +106,54 @@ def test_device_side_run_with_local_search_matches_stepwise_composition(mode):
         ph = ref.pheromone
     assert torch.equal(aco.pheromone, ph)
     assert low == best
+
+
+def test_two_opt_and_nls_properties_at_benchmark_size():
+    """C3 (TSP-500 x 256 ants, too large for the CPU oracle in test time): size-independent properties -- the result is
+    a permutation that still starts at node 0, no tour gets longer, a converged 2-opt is a fixed point, and NLS is at
+    least as good as the plain 2-opt it starts with."""
+    from deepaco_b200 import _engine as E
+    n, A, k = 500, 256, 50
+    torch.manual_seed(0)
+    xy = torch.rand(n, 2, device=DEV)
+    dist = torch.norm(xy[:, None] - xy, dim=2, p=2)
+    dist[torch.arange(n), torch.arange(n)] = 1e9
+    _, idx = torch.topk(dist, k, dim=1, largest=False)
+    heu = torch.full_like(dist, 1e-10).scatter_(1, idx, torch.rand(n, k, device=DEV) * 0.9 + 0.05)
+    base = E.tsp_sample(torch.ones_like(dist), heu, A, start_node=0, double_norm=True, seed=3, want_paths=False, want_tours=True)[2]
+    hd = (1 / (heu / heu.max(-1, keepdim=True).values + 1e-5)).contiguous()
+
+    def costs(t):
+        return E.tsp_cost(dist, tours=t)[0]
+
+    def is_perm(t):
+        paths = E.tours_to_paths(t)                                  # int64 [n, A]
+        return bool((torch.sort(paths, dim=0).values == torch.arange(n, device=DEV)[:, None]).all()) and bool((paths[0] == 0).all())
+
+    c0 = costs(base)
+    t1, passes = E.two_opt_(dist, base.clone(), n // 4, want_passes=True)
+    c1 = costs(t1)
+    assert is_perm(t1) and bool((c1 <= c0 + 1e-4).all()) and int(passes.max()) <= n // 4
+    conv, p_conv = E.two_opt_(dist, base.clone(), 10000, want_passes=True)
+    assert is_perm(conv) and int(p_conv.max()) < 10000
+    again, p_again = E.two_opt_(dist, conv.clone(), 10000, want_passes=True)
+    assert torch.equal(again, conv) and bool((p_again == 1).all())          # one pass that finds nothing
+    t2 = E.tsp_nls_(dist, hd, base.clone(), n // 4)
+    assert is_perm(t2) and bool((costs(t2) <= c1 + 1e-4).all())
+
+
+def test_two_opt_on_tours_with_repeated_nodes_follows_the_reference_skip_rule():
+    """A tour that is not a permutation can make the reference's skip test (two_opt.py:16) fire; the kernel detects
+    such tours and runs them through the band kernel, which evaluates the test: same output as the oracle."""
+    from oracle import two_opt as T2
+    n, count = 40, 12
+    rng = np.random.default_rng(7)
+    xy = rng.random((n, 2), dtype=np.float32)
+    dist = np.sqrt(((xy[:, None] - xy[None]) ** 2).sum(-1)).astype(np.float32)
+    np.fill_diagonal(dist, 1e9)
+    tours = np.stack([np.concatenate(([0], 1 + rng.permutation(n - 1))) for _ in range(count)]).astype(np.uint16)
+    for a in range(0, count, 2):                     # every other tour: three positions repeat earlier nodes
+        pos = rng.choice(np.arange(2, n), size=3, replace=False)
+        tours[a, pos] = tours[a, pos - 2]
+    ref = T2.batched_two_opt(dist, tours, 15)
+    assert np.array_equal(_run_two_opt(dist, tours, 15), ref.astype(np.int16))
