@@ -540,15 +540,16 @@ def _graph_of(pyg, backward):
     """train_graph(...) of one pyg instance, remembered on the instance when it is this package's own Data (validation
     and training loops present the same instances every epoch; a foreign Data object is never written to)."""
     ei, ea = pyg.edge_index, pyg.edge_attr
-    key = (ei.data_ptr(), ei._version, ea.data_ptr(), ea._version, pyg.x.shape[0])
     own = isinstance(pyg, Data)
     if own:
         hit = pyg.__dict__.get("_deepaco_graph")
-        if hit is not None and hit[0] == key and (hit[1]["col_ptr"] is not None or not backward):
-            return hit[1]
+        # the entry keeps the tensors it was built from alive, so identity + version is a sound "unchanged" test
+        if (hit is not None and hit[0] is ei and hit[1] is ea and hit[2] == (ei._version, ea._version, pyg.x.shape[0])
+                and (hit[3]["col_ptr"] is not None or not backward)):
+            return hit[3]
     graph = train_graph(ei[None], ea[None], pyg.x.shape[0], backward=backward)
     if own:
-        pyg.__dict__["_deepaco_graph"] = (key, graph)
+        pyg.__dict__["_deepaco_graph"] = (ei, ea, (ei._version, ea._version, pyg.x.shape[0]), graph)
     return graph
 
 

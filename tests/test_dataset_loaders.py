@@ -70,3 +70,31 @@ def test_complete_graph_arrays_written_directly_equal_the_sorted_edge_list():
         for k in ("row_ptr", "src", "dst", "attr", "order"):
             assert torch.equal(got[k][b], want[k][0]), k
     assert got["E"] == 81 and got["n"] == 9 and got["B"] == 3
+
+
+def test_graph_cache_on_data_objects_follows_the_tensors(monkeypatch):
+    """Net.forward remembers the sorted edge arrays on this package's Data objects; the entry must be dropped when the
+    edge tensors are replaced or written, extended when the backward arrays are needed, and never put on foreign objects."""
+    from deepaco_b200 import net as N
+    from deepaco_b200.tsp import utils as T
+    torch.manual_seed(0)
+    pyg, _ = T.gen_pyg_data(torch.rand(10, 2), 3)
+    g1 = N._graph_of(pyg, backward=False)
+    assert N._graph_of(pyg, backward=False) is g1 and g1["col_ptr"] is None
+    g2 = N._graph_of(pyg, backward=True)
+    assert g2 is not g1 and g2["col_ptr"] is not None and N._graph_of(pyg, backward=False) is g2
+    pyg.edge_attr.mul_(2.0)                                  # in-place write -> version bump
+    g3 = N._graph_of(pyg, backward=False)
+    assert g3 is not g2 and torch.equal(g3["attr"], 2 * g2["attr"])
+    pyg.edge_index = pyg.edge_index.flip(1).contiguous()     # replaced tensor
+    g4 = N._graph_of(pyg, backward=False)
+    assert g4 is not g3
+    moved = pyg.to("cpu")
+    assert "_deepaco_graph" not in vars(moved)
+
+    class Foreign:
+        pass
+    f = Foreign()
+    f.x, f.edge_index, f.edge_attr = pyg.x, pyg.edge_index, pyg.edge_attr
+    N._graph_of(f, backward=False)
+    assert "_deepaco_graph" not in vars(f)
