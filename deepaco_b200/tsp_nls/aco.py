@@ -87,7 +87,7 @@ class ACO(_TspACO):
         pheromone update of every iteration are enqueued without a host round trip (the reference crosses to the CPU
         for the numba local search each iteration).  Returns lowest_cost as a Python float like the reference (:120).'''
         if self.alpha != 1 or self.beta != 1:
-            raise NotImplementedError("tsp_nls ACO.run with alpha / beta != 1: use gen_path / local_search / update_pheronome")
+            return self._run_stepwise(n_iterations, inference)     # general exponents: torch.pow supplies the powers
         if self._runner is None:
             self._runner = self._make_runner()
         r = self._runner
@@ -101,4 +101,22 @@ class ACO(_TspACO):
         self._lowest_cost = float(r.lowest_cost[0].item())
         if self.min_max:
             self.max = r.ph_max[0].clone()
+        return self._lowest_cost
+
+    def _run_stepwise(self, n_iterations, inference=False):
+        '''The same iteration composed from the per-step methods (one host read of the best cost per iteration, as the
+        reference has at tsp_nls/aco.py:120); used when alpha / beta are not 1.'''
+        for _ in range(n_iterations):
+            paths = self.local_search(self.gen_path(require_prob=False), inference)
+            costs = self.gen_path_costs(paths)
+            best = torch.argmin(costs)
+            best_cost = float(costs[best].item())
+            if best_cost < self._lowest_cost:
+                self._shortest_path, self._lowest_cost = paths[:, best], best_cost
+                if self.min_max:
+                    new_max = self.problem_size / self._lowest_cost
+                    if self.max is None:
+                        self._pheromone = self._pheromone * (new_max / self._pheromone.max())
+                    self.max = new_max
+            self.update_pheronome(paths, costs)
         return self._lowest_cost

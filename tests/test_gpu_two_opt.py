@@ -157,3 +157,29 @@ def test_two_opt_on_tours_with_repeated_nodes_follows_the_reference_skip_rule():
         tours[a, pos] = tours[a, pos - 2]
     ref = T2.batched_two_opt(dist, tours, 15)
     assert np.array_equal(_run_two_opt(dist, tours, 15), ref.astype(np.int16))
+
+
+def test_tsp_nls_run_with_general_exponents_composes_the_verified_steps():
+    """alpha / beta != 1: ACO.run of tsp_nls goes through the per-step methods (powers by torch.pow) and must equal the
+    explicit composition of those methods under the same seed."""
+    from deepaco_b200.tsp_nls.aco import ACO
+    n, A = 40, 16
+    torch.manual_seed(4)
+    xy = torch.rand(n, 2, device=DEV)
+    dist = torch.norm(xy[:, None] - xy, dim=2, p=2)
+    dist[torch.arange(n), torch.arange(n)] = 1e9
+    heu = torch.rand(n, n, device=DEV) * 0.9 + 0.05
+    kw = dict(n_ants=A, heuristic=heu, device=DEV, local_search="2opt", alpha=1.5, beta=2)
+    torch.manual_seed(21)
+    aco = ACO(dist, **kw)
+    low = aco.run(2)
+    torch.manual_seed(21)
+    ref = ACO(dist, **kw)
+    best = float("inf")
+    for _ in range(2):
+        paths = ref.local_search(ref.gen_path())
+        costs = ref.gen_path_costs(paths)
+        best = min(best, float(costs.min()))
+        ref.update_pheronome(paths, costs)
+    assert isinstance(low, float) and low == best
+    assert torch.equal(aco.pheromone, ref.pheromone)
