@@ -9,7 +9,14 @@
 //     (ATen/native/cuda/Reduce.cuh: thread_reduce_impl / input_vectorized_thread_reduce_impl /
 //     block_x_reduce), so that `p / p.sum(-1)` and `sum(dist[u,v], 1)` round identically.
 #pragma once
+#ifndef DEEPACO_CPU_EMU
 #include <cuda_runtime.h>
+// spelled through macros so that tests/cpu_emu can compile the kernel sources for the host (test infrastructure only;
+// under nvcc they expand to exactly the tokens they replace)
+#define DACO_NOINLINE __noinline__
+#define DACO_DYN_SMEM128(name) extern __shared__ __align__(128) unsigned char name[]
+#define DACO_STS_U8(addr, v) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory")
+#endif
 #include <stdint.h>
 
 namespace deepaco {
@@ -98,6 +105,7 @@ __device__ __forceinline__ uint32_t philox_word_x(uint32_t ctr_lo, uint32_t ctr_
     return __umulhi(kPhiloxM1, c2) ^ c1 ^ K.a[9];
 }
 
+#ifndef DEEPACO_CPU_EMU   // MUFU-based pieces: tests/cpu_emu supplies libm stand-ins
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -126,6 +134,8 @@ __device__ __forceinline__ float exp1_from_word(uint32_t x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
     return fmaxf(-__fmul_rn(l2, 0.693147182464599609375f), 1.1920928955078125e-07f / 2.0f);
 }
+
+#endif  // DEEPACO_CPU_EMU
 
 // ---------------------------------------------------------------------------------------------
 // ATen-ordered row sums.  The caller holds one row distributed over the 32 lanes of a warp.
@@ -210,6 +220,7 @@ __device__ __forceinline__ void aten_sum_plan_dev(int row_len, int n_rows, int* 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) used to stage matrices / rows in smem
 // ---------------------------------------------------------------------------------------------
+#ifndef DEEPACO_CPU_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -243,6 +254,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+#endif  // DEEPACO_CPU_EMU
 
 // warp arg-max over non-negative floats with lowest-index tie break (ATen ArgMaxOps semantics):
 // returns the winning index in every lane.

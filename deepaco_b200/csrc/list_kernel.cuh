@@ -52,6 +52,7 @@ struct ListParams {
     uint32_t start_increment, step_increment;
 };
 
+#ifndef DEEPACO_CPU_EMU
 __device__ __forceinline__ uint32_t lds_s8(uint32_t addr) {
     int32_t v;
     asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -71,22 +72,27 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
 
+#endif  // DEEPACO_CPU_EMU
+
 // reciprocal Exp(1) noise of element `sub` of the draw at Philox counter (ctr_lo, ctr_hi)
 __device__ __forceinline__ float noise_rcp(uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub, const PhiloxRoundKeys& K) {
     return rcp_approx(exp1_from_word(philox_word_x(ctr_lo, ctr_hi, sub, K)));
 }
 
+#ifndef DEEPACO_CPU_EMU
 // opaque register copy: stops the compiler from re-deriving a shared-memory address inside the step loop
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
     asm volatile("mov.u32 %0, %0;" : "+r"(v));
     return v;
 }
 
+#endif  // DEEPACO_CPU_EMU
+
 // GLOBAL_P: the product matrix stays in global memory (L2-resident) instead of shared memory -- colonies with more
 // than ~230 nodes; `p.ph` must then already be the product (p.heu == nullptr).
 template <int EPL, bool CVRP, bool WANT_LOGP, bool EXT_NOISE, bool GLOBAL_P = false>
 __global__ void __launch_bounds__(GLOBAL_P ? 256 : 512, GLOBAL_P ? 1 : 2) aco_list_kernel(const __grid_constant__ ListParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    DACO_DYN_SMEM128(smem);
     __shared__ uint64_t bar;
     const int n = p.n, R = p.rows;
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(GLOBAL_P ? 256 : 512, GLOBAL_P ? 1 : 2) aco_li
 // row's arg-max and the step is done.  Otherwise (about a fifth of the steps on the pretrained TSP-100
 // network) the step is evaluated densely over all unvisited nodes; near-ties go to exact_step() as before.
 // ---------------------------------------------------------------------------------------------
+#ifndef DEEPACO_CPU_EMU
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -340,8 +347,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 
+#endif  // DEEPACO_CPU_EMU
+
 // Rare tail of the fallback step: a tie or a near-tie among the approximate scores -> exact arithmetic in ATen order.
-static __device__ __noinline__ uint32_t knn_exact_tail(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t ctr_lo, uint32_t ctr_hi,
+static __device__ DACO_NOINLINE uint32_t knn_exact_tail(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t ctr_lo, uint32_t ctr_hi,
                                                        uint32_t sub_base) {
     const int lane = threadIdx.x & 31;
     uint32_t* alive_scratch = reinterpret_cast<uint32_t*>(__cvta_shared_to_generic(wbase + 256u));
@@ -360,7 +369,7 @@ static __device__ __noinline__ uint32_t knn_exact_tail(const ListParams& p, uint
 // Fallback step of the kNN kernel: evaluate every unvisited column of row `cur` (row_addr = shared address of that
 // row of P), commit the winner (alive byte, tour slot at shared address `slot`) and return it.  Everything is passed by value / as
 // 32-bit shared addresses so that the call marshals few registers.
-static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t slot, uint32_t n,
+static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t slot, uint32_t n,
                                                        uint32_t seed_lo, uint32_t seed_hi, uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub_base) {
     const uint32_t lane = threadIdx.x & 31u;
     const PhiloxRoundKeys& K = p.keys;   // the compiler clones this function for its kernel: constant-bank operands
@@ -410,7 +419,7 @@ static __device__ __noinline__ uint32_t knn_dense_step(const ListParams& p, uint
     if (nears == 0u && __popc(close) == 1) jstar = __shfl_sync(DACO_FULL, bestj, 31 - __clz(close));
     else jstar = knn_exact_tail(p, row_addr, wbase, ctr_lo, ctr_hi, sub_base);
     __syncwarp();
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
+    DACO_STS_U8(wbase + jstar, 0u);
     sts_u16(slot, jstar);
     __syncwarp();
     return jstar;
@@ -426,7 +435,7 @@ constexpr int kKnnBoundBytes = 1024;
 template <bool FUSE_COST, int MAXW>
 static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_kernel(const __grid_constant__ ListParams p) {
     constexpr int kKnnFixed = kKnnWarpBytes * MAXW;
-    extern __shared__ __align__(128) unsigned char smem[];
+    DACO_DYN_SMEM128(smem);
     __shared__ uint64_t bar;
     const int n = p.n;
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -523,7 +532,7 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
                 const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
                 // Every lane stores the same two values to the same addresses: one wavefront, no predicate to
                 // maintain, and each lane later reads what it wrote itself, so no warp-level fence between steps.
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbase + jstar), "r"(0u) : "memory");
+                DACO_STS_U8(wbase + jstar, 0u);
                 sts_u16(slot, jstar);
                 cur = (int)jstar;
             }

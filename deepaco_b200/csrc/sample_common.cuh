@@ -61,7 +61,7 @@ __device__ __forceinline__ void stage_product(float* Psm, const float* ph, const
 // lowest-index tie break).  `alive` is a 1024-bit map of unvisited nodes.  Rarely executed from the list
 // kernel (near-ties), so it is kept out of line.  Returns the chosen node in every lane; *pn_out receives
 // the normalised probability of the chosen node (valid in the lane that owns it, broadcast by caller).
-static __device__ __noinline__ uint32_t exact_step(const float* row, const uint32_t* alive, int n, int lbw, int vec,
+static __device__ DACO_NOINLINE uint32_t exact_step(const float* row, const uint32_t* alive, int n, int lbw, int vec,
                                             int double_norm, const float* nz, uint64_t seed, uint64_t off_step,
                                             uint32_t sub_base, DrawGeom g, float* pn_out) {
     const int lane = threadIdx.x & 31;

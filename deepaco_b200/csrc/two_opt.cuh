@@ -53,7 +53,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 #define DACO_2OPT_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
-#define DACO_NOINLINE __noinline__
 #endif
 
 // numpy float32 pairwise summation of one contiguous row (numpy/_core/src/umath/loops_utils.h.src
