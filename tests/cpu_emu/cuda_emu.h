@@ -22,7 +22,6 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define DACO_NOINLINE __attribute__((noinline))   /* not `__noinline__`: libstdc++ spells its own attributes that way */
 
 struct alignas(16) float4 {
     float x, y, z, w;
@@ -45,9 +44,10 @@ struct Ctx {
 };
 inline thread_local Ctx ctx;
 
-// run `kernel(params)` for n_clusters clusters of `ncta` CTAs x `nth` threads (clusters one after another)
+// run `kernel(params)` for n_clusters clusters of `ncta` CTAs x `nth` threads (clusters one after another).
+// grid_x > 0: blockIdx = (linear % grid_x, linear / grid_x) for kernels launched on a 2-D grid (ncta must be 1).
 template <class Kernel, class Params>
-void launch(Kernel kernel, const Params& params, int n_clusters, int ncta, int nth, size_t smem_bytes) {
+void launch(Kernel kernel, const Params& params, int n_clusters, int ncta, int nth, size_t smem_bytes, int grid_x = 0) {
     for (int cl = 0; cl < n_clusters; ++cl) {
         std::vector<unsigned char*> smem(ncta);
         std::vector<pthread_barrier_t> bars(ncta);
@@ -71,6 +71,7 @@ void launch(Kernel kernel, const Params& params, int n_clusters, int ncta, int n
                 threads.emplace_back([&, r, t]() {
                     ctx.tid = {(unsigned)t, 0, 0};
                     ctx.bid = {(unsigned)(cl * ncta + r), 0, 0};
+                    if (grid_x > 0) ctx.bid = {(unsigned)(cl % grid_x), (unsigned)(cl / grid_x), 0};
                     ctx.bdim = {(unsigned)nth, 1, 1};
                     ctx.rank = (unsigned)r;
                     ctx.ncta = (unsigned)ncta;
@@ -129,6 +130,52 @@ static inline int __syncthreads_or(int predicate) {
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
+static inline int atomicMax(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {}
+    return old;
+}
+// warp votes / reductions: every lane contributes through the exchange buffer, then reads all 32 slots
+template <class F>
+static inline uint32_t emu_warp_fold(uint32_t mine, F f) {
+    uint32_t* slots = emu::ctx.warp_slots + (emu::ctx.tid.x >> 5) * 32;
+    slots[emu::ctx.tid.x & 31] = mine;
+    __syncwarp();
+    uint32_t acc = slots[0];
+    for (int l = 1; l < 32; ++l) acc = f(acc, slots[l]);
+    __syncwarp();
+    return acc;
+}
+static inline uint32_t __ballot_sync(unsigned, int pred) {
+    return emu_warp_fold(pred ? (1u << (emu::ctx.tid.x & 31)) : 0u, [](uint32_t a, uint32_t b) { return a | b; });
+}
+static inline uint32_t __reduce_max_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a > b ? a : b; }); }
+static inline uint32_t __reduce_min_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a < b ? a : b; }); }
+static inline uint32_t __reduce_or_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a | b; }); }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
+static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint32_t __float_as_uint(float f) { uint32_t v; memcpy(&v, &f, 4); return v; }
+static inline float __uint_as_float(uint32_t v) { float f; memcpy(&f, &v, 4); return f; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline void* __cvta_shared_to_generic(uint32_t addr) { return emu::ctx.smem + addr; }
+#define __grid_constant__
+
+// ---- mbarrier + bulk-copy stand-in: the 64-bit barrier word is (pending tx bytes << 32 | completed phases); a copy
+// happens at issue time and completes the phase when it brings the pending bytes to zero (one issuing thread per barrier)
+static inline void emu_mbar_init(uint64_t* bar) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_RELEASE); }
+static inline void emu_mbar_expect_tx(uint64_t* bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t)bytes << 32, __ATOMIC_ACQ_REL); }
+static inline void emu_bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    memcpy(dst, src, bytes);
+    const uint64_t now = __atomic_sub_fetch(bar, (uint64_t)bytes << 32, __ATOMIC_ACQ_REL);
+    if ((now >> 32) == 0) __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_ACQ_REL);
+}
+static inline void emu_mbar_wait(uint64_t* bar, uint32_t parity) {   // done when the current phase parity != `parity`
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == parity) sched_yield();
+}
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline float __fadd_rn(float a, float b) { return a + b; }      // built with -ffp-contract=off
 static inline float __fsub_rn(float a, float b) { return a - b; }

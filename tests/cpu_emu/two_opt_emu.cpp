@@ -7,6 +7,7 @@
 using std::min;
 
 #define DACO_FULL 0xffffffffu
+#define DACO_NOINLINE __attribute__((noinline))
 #define __shared__ static            /* one CTA at a time (cluster size 1, clusters run one after another) */
 #define DACO_2OPT_SMEM(name) unsigned char* name = emu::ctx.smem
 
@@ -21,17 +22,12 @@ static inline void cp_async_4(float* dst, const float* src) { memcpy(dst, src, 4
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
-// mbarrier + TMA bulk copy: the barrier word counts completed phases; a copy completes its phase when it is issued
-static inline void mbar_init(uint64_t* bar, uint32_t) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_RELEASE); }
-static inline void mbar_expect_tx(uint64_t*, uint32_t) {}
+// mbarrier + TMA bulk copy (cuda_emu.h)
+static inline void mbar_init(uint64_t* bar, uint32_t) { emu_mbar_init(bar); }
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { emu_mbar_expect_tx(bar, bytes); }
 static inline void fence_barrier_init() {}
-static inline void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    memcpy(dst, src, bytes);
-    __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_ACQ_REL);
-}
-static inline void mbar_wait(uint64_t* bar, uint32_t parity) {       // done when the current phase parity != `parity`
-    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == parity) sched_yield();
-}
+static inline void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { emu_bulk_copy(dst, src, bytes, bar); }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) { emu_mbar_wait(bar, parity); }
 }  // namespace deepaco
 
 #include "../../deepaco_b200/csrc/two_opt.cuh"
