@@ -15,6 +15,7 @@
 // under nvcc they expand to exactly the tokens they replace)
 #define DACO_NOINLINE __noinline__
 #define DACO_DYN_SMEM128(name) extern __shared__ __align__(128) unsigned char name[]
+#define DACO_DYN_SMEM16(name) extern __shared__ __align__(16) unsigned char name[]
 #define DACO_STS_U8(addr, v) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory")
 #endif
 #include <stdint.h>

@@ -1,207 +1,8 @@
-// K2 -- tour cost and fused evaporate + deposit for TSP colonies.
-//
-// cost:   ACO.gen_path_costs (reference tsp/aco.py:120-132): sum_k dist[u_k][u_{k-1}], accumulated in
-//         the order ATen's sum kernel uses for a contiguous [n_ants][n] input, so costs are bit-equal.
-//         As a by-product each ant writes, per node u, its tour predecessor and successor.
-// update: ACO.update_pheronome (tsp/aco.py:94-118).  The reference adds 1/cost_a to cells
-//         (u, pred_a(u)) and (u, succ_a(u)) one ant at a time (index_put, non-accumulating), so every
-//         matrix cell sees its additions in ant order.  One CTA per matrix row replays exactly that
-//         order per cell from the neighbour table: deterministic, atomics-free, and every row is read
-//         and written once, coalesced, with the evaporation folded in.
-#include "common.cuh"
+// K2 -- tour cost and fused evaporate + deposit for TSP colonies: launchers and C ABI (kernels in tsp_update.cuh).
+#include "tsp_update.cuh"
 #include "host_util.h"
 
 #include <stdlib.h>
-
-namespace deepaco {
-
-struct TourView {
-    const int64_t* paths;    // [n][A] of this colony, or null
-    const uint16_t* tour;    // [n] of this ant, or null
-    int A, a;
-    __device__ __forceinline__ int at(int k) const {
-        return paths ? (int)paths[(size_t)k * A + a] : (int)tour[k];
-    }
-};
-
-__global__ void __launch_bounds__(256) tsp_cost_kernel(const float* __restrict__ dist, const int64_t* __restrict__ paths,
-                                                       const uint16_t* __restrict__ tours, int n, int A, int lbw, int vec,
-                                                       float* __restrict__ costs, uint32_t* __restrict__ nbr) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int b = blockIdx.y;
-    if (a >= A) return;
-    const float* D = dist + (size_t)b * n * n;
-    TourView tv{paths ? paths + (size_t)b * n * A : nullptr, tours ? tours + ((size_t)b * A + a) * n : nullptr, A, a};
-    auto edge = [&](int k) -> float {
-        const int u = tv.at(k);
-        const int v = tv.at(k == 0 ? n - 1 : k - 1);
-        return __ldg(D + (size_t)u * n + v);
-    };
-    if (costs) {
-        const float c = aten_row_sum_fn(edge, n, lbw, vec != 0, lane, vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
-        if (lane == 0) costs[(size_t)b * A + a] = c;
-    }
-    if (nbr) {
-        uint32_t* N = nbr + (size_t)b * n * A;
-        for (int k = lane; k < n; k += 32) {
-            const int u = tv.at(k);
-            const int pr = tv.at(k == 0 ? n - 1 : k - 1);
-            const int su = tv.at(k == n - 1 ? 0 : k + 1);
-            N[(size_t)u * A + a] = ((uint32_t)pr << 16) | (uint32_t)su;
-        }
-    }
-}
-
-// Tile version for compact tours: one CTA handles 32 consecutive ants.  Tours are staged in shared memory, each
-// ant's inverse permutation is built there, and the neighbour table is written node-major with the 32 ants of a
-// node side by side (128-byte coalesced stores) instead of one scattered 4-byte store per (ant, node).
-//   smem: tours u16 [32][n] | pos u16 [32][n]
-__global__ void __launch_bounds__(256) tsp_cost_tile_kernel(const float* __restrict__ dist, const uint16_t* __restrict__ tours,
-                                                            int n, int A, int lbw, int vec, float* __restrict__ costs,
-                                                            uint32_t* __restrict__ nbr) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint16_t* t_s = reinterpret_cast<uint16_t*>(smem);
-    uint16_t* pos_s = t_s + (size_t)32 * n;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int a0 = blockIdx.x * 32, b = blockIdx.y;
-    const int na = min(32, A - a0);
-    const uint16_t* T = tours + ((size_t)b * A + a0) * n;
-    for (int i = tid; i < na * n; i += blockDim.x) t_s[i] = T[i];
-    __syncthreads();
-    const float* D = dist + (size_t)b * n * n;
-    for (int al = warp; al < na; al += W) {
-        const uint16_t* tour = t_s + (size_t)al * n;
-        if (costs) {
-            auto edge = [&](int k) -> float { return __ldg(D + (size_t)tour[k] * n + tour[k == 0 ? n - 1 : k - 1]); };
-            const int a = a0 + al;
-            const float c = aten_row_sum_fn(edge, n, lbw, vec != 0, lane, vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
-            if (lane == 0) costs[(size_t)b * A + a] = c;
-        }
-        for (int k = lane; k < n; k += 32) pos_s[(size_t)al * n + tour[k]] = (uint16_t)k;
-    }
-    __syncthreads();
-    if (nbr) {
-        uint32_t* N = nbr + (size_t)b * n * A;
-        for (int i = tid; i < 32 * n; i += blockDim.x) {
-            const int u = i >> 5, al = i & 31;
-            if (al < na) {
-                const uint16_t* tour = t_s + (size_t)al * n;
-                const int k = pos_s[(size_t)al * n + u];
-                const uint32_t pr = tour[k == 0 ? n - 1 : k - 1], su = tour[k == n - 1 ? 0 : k + 1];
-                N[(size_t)u * A + a0 + al] = (pr << 16) | su;
-            }
-        }
-    }
-}
-
-// One warp per matrix row u.  The 2A deposit events of the row (ant a: first its predecessor cell, then its
-// successor cell -- the reference's statement order) are bucketed by cell with a stable counting sort in
-// shared memory, so each cell then adds its own few weights in ant order: work per row is O(A + n) instead
-// of O(A * n), and the row is read and written exactly once, coalesced.
-//   smem: inv[A] f32 (1 / cost, shared by the CTA's rows) | per warp: w_sorted[2A] f32 | start[n+1] i32 | cursor[n] i32
-__global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
-                                                         const float* __restrict__ costs, int n, int A, float decay,
-                                                         int elitist, int min_max, float ph_min,
-                                                         const float* __restrict__ ph_max, const float* __restrict__ scale,
-                                                         const float* __restrict__ heu, float* __restrict__ prod) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-    const int u = blockIdx.x * W + warp, b = blockIdx.y;
-    const size_t per_warp = (size_t)2 * A * 4 + (size_t)(2 * n + 1) * 4;
-    float* inv = reinterpret_cast<float*>(smem);
-    float* w_sorted = reinterpret_cast<float*>(smem + (((size_t)A * 4 + 15) & ~(size_t)15) + warp * ((per_warp + 15) & ~(size_t)15));
-    int* start = reinterpret_cast<int*>(w_sorted + 2 * A);
-    int* cursor = start + n + 1;
-    const uint32_t* N = nbr + ((size_t)b * n + u) * A;
-    const float* C = costs + (size_t)b * A;
-    for (int a = threadIdx.x; a < A; a += blockDim.x) inv[a] = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
-    __syncthreads();
-    if (u >= n) return;
-
-    int a_lo = 0, a_hi = A;
-    if (elitist) {   // costs.min(dim=0): first index of the minimum
-        float bc = INFINITY;
-        int bi = 0x7fffffff;
-        for (int a = lane; a < A; a += 32) {
-            const float c = C[a];
-            if (c < bc) { bc = c; bi = a; }
-        }
-        for (int off = 16; off > 0; off >>= 1) {
-            const float oc = __shfl_xor_sync(DACO_FULL, bc, off);
-            const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
-            if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
-        }
-        a_lo = bi;
-        a_hi = bi + 1;
-    }
-    const int E = 2 * (a_hi - a_lo);   // events, key e -> ant a_lo + e/2, statement e&1
-    for (int v = lane; v <= n; v += 32) start[v] = 0;
-    __syncwarp();
-    for (int e = lane; e < E; e += 32) {
-        const uint32_t nb = N[a_lo + (e >> 1)];
-        const int cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
-        atomicAdd(&start[cell + 1], 1);
-    }
-    __syncwarp();
-    // inclusive scan of start[1..n] (start[0] = 0) -> bucket offsets
-    int carry = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int v = base + lane;
-        int x = (v < n) ? start[v + 1] : 0;
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(DACO_FULL, x, off);
-            if (lane >= off) x += y;
-        }
-        x += carry;
-        if (v < n) { start[v + 1] = x; }
-        carry = __shfl_sync(DACO_FULL, x, 31);
-    }
-    __syncwarp();
-    for (int v = lane; v < n; v += 32) cursor[v] = start[v];
-    __syncwarp();
-    for (int e0 = 0; e0 < E; e0 += 32) {
-        const int e = e0 + lane;
-        int cell = -1 - lane;   // distinct dummies for idle lanes
-        float w = 0.f;
-        if (e < E) {
-            const int a = a_lo + (e >> 1);
-            const uint32_t nb = N[a];
-            cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
-            w = inv[a];
-        }
-        const uint32_t grp = __match_any_sync(DACO_FULL, cell);
-        const int rank = __popc(grp & ((1u << lane) - 1u));
-        if (e < E) w_sorted[cursor[cell] + rank] = w;
-        __syncwarp();
-        if (e < E && rank == 0) cursor[cell] += __popc(grp);
-        __syncwarp();
-    }
-    float* row = ph + ((size_t)b * n + u) * n;
-    const float hi = min_max ? ph_max[b] : 0.f;
-    const float sc = scale ? scale[b] : 1.0f;
-    for (int base = 0; base < n; base += 32) {      // warp-uniform loop: every lane takes part in the reductions
-        const int v = base + lane;
-        const bool valid = v < n;
-        float val = valid ? row[v] : 0.f;
-        if (scale) val = __fmul_rn(val, sc);   // MMAS rescale on the first improvement (tsp/aco.py:86-87)
-        val = __fmul_rn(val, decay);
-        if (valid)      // this cell's deposits in ant order
-            for (int i = start[v]; i < start[v + 1]; ++i) val = __fadd_rn(val, w_sorted[i]);
-        if (min_max) {
-            // ph[(ph > 1e-9) * ph < min] = min ; ph[ph > max] = max   (tsp/aco.py:117-118)
-            const float gate = __fmul_rn(val > 1e-9f ? 1.0f : 0.0f, val);
-            if (gate < ph_min) val = ph_min;
-            if (val > hi) val = hi;
-        }
-        if (valid) {
-            row[v] = val;
-            if (prod) prod[((size_t)b * n + u) * n + v] = __fmul_rn(val, heu[((size_t)b * n + u) * n + v]);
-        }
-    }
-}
-
-}  // namespace deepaco
 
 using namespace deepaco;
 

@@ -153,6 +153,21 @@ static inline uint32_t __ballot_sync(unsigned, int pred) {
 static inline uint32_t __reduce_max_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a > b ? a : b; }); }
 static inline uint32_t __reduce_min_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a < b ? a : b; }); }
 static inline uint32_t __reduce_or_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a | b; }); }
+template <class T>
+static inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {     // lanes below `delta` keep their own value
+    const int lane = (int)(emu::ctx.tid.x & 31);
+    const T got = __shfl_sync(m, v, lane >= (int)delta ? lane - (int)delta : lane);
+    return lane >= (int)delta ? got : v;
+}
+static inline uint32_t __match_any_sync(unsigned, int v) {           // mask of the lanes holding the same value
+    uint32_t* slots = emu::ctx.warp_slots + (emu::ctx.tid.x >> 5) * 32;
+    slots[emu::ctx.tid.x & 31] = (uint32_t)v;
+    __syncwarp();
+    uint32_t m = 0;
+    for (int l = 0; l < 32; ++l) m |= (slots[l] == (uint32_t)v) ? (1u << l) : 0u;
+    __syncwarp();
+    return m;
+}
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }

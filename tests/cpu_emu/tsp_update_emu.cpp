@@ -1,0 +1,60 @@
+// csrc/tsp_update.cuh (tour cost, neighbour table, fused evaporate + ordered deposit) compiled for the host (see
+// cuda_emu.h) behind entry points shaped like deepaco_tsp_cost / deepaco_tsp_update.  Test infrastructure only.
+#include "cuda_emu.h"
+
+#include <algorithm>
+#include <cmath>
+using std::min;
+
+struct uint4 {
+    uint32_t x, y, z, w;
+};
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+#define DACO_NOINLINE __attribute__((noinline))
+#define DACO_DYN_SMEM128(name) unsigned char* name = emu::ctx.smem
+#define DACO_DYN_SMEM16(name) unsigned char* name = emu::ctx.smem
+#define __shared__ static
+
+#include "../../deepaco_b200/csrc/tsp_update.cuh"
+
+using namespace deepaco;
+
+namespace {
+struct CostArgs {
+    const float* dist; const int64_t* paths; const uint16_t* tours; int n, A, lbw, vec; float* costs; uint32_t* nbr;
+};
+struct UpdArgs {
+    float* ph; const uint32_t* nbr; const float* costs; int n, A; float decay; int elitist, min_max; float ph_min;
+    const float* ph_max; const float* scale; const float* heu; float* prod;
+};
+}  // namespace
+
+// tile != 0: tsp_cost_tile_kernel (compact tours), else tsp_cost_kernel (paths or tours).  One colony per call.
+extern "C" const char* emu_tsp_cost(const float* dist, const int64_t* paths, const uint16_t* tours, int n, int A, int lbw, int vec,
+                                    float* costs, uint32_t* nbr, int tile) {
+    if (!dist || ((paths != nullptr) == (tours != nullptr)) || n < 2 || A < 1) return "bad arguments";
+    const CostArgs a{dist, paths, tours, n, A, lbw, vec, costs, nbr};
+    if (tile) {
+        if (!tours) return "the tile kernel needs compact tours";
+        emu::launch([](const CostArgs& q) { tsp_cost_tile_kernel(q.dist, q.tours, q.n, q.A, q.lbw, q.vec, q.costs, q.nbr); }, a,
+                    (A + 31) / 32, 1, 256, (size_t)32 * n * 4);
+    } else {
+        const int W = 8;
+        emu::launch([](const CostArgs& q) { tsp_cost_kernel(q.dist, q.paths, q.tours, q.n, q.A, q.lbw, q.vec, q.costs, q.nbr); }, a,
+                    (A + W - 1) / W, 1, W * 32, 16);
+    }
+    return nullptr;
+}
+
+extern "C" const char* emu_tsp_update(float* ph, const uint32_t* nbr, const float* costs, int n, int A, float decay, int elitist,
+                                      int min_max, float ph_min, const float* ph_max, const float* scale, const float* heu, float* prod) {
+    if (!ph || !nbr || !costs || n < 2 || A < 1 || (min_max && !ph_max)) return "bad arguments";
+    const int W = 4;
+    const size_t per_warp = (((size_t)2 * A * 4 + (size_t)(2 * n + 1) * 4) + 15) & ~(size_t)15;
+    const size_t smem = per_warp * W + (((size_t)A * 4 + 15) & ~(size_t)15);
+    const UpdArgs a{ph, nbr, costs, n, A, decay, elitist, min_max, ph_min, ph_max, scale, heu, prod};
+    emu::launch([](const UpdArgs& q) { tsp_update_kernel(q.ph, q.nbr, q.costs, q.n, q.A, q.decay, q.elitist, q.min_max, q.ph_min,
+                                                        q.ph_max, q.scale, q.heu, q.prod); },
+                a, (n + W - 1) / W, 1, W * 32, smem);
+    return nullptr;
+}

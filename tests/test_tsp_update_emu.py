@@ -1,0 +1,97 @@
+"""The cost / neighbour-table / evaporate + deposit kernel SOURCE (deepaco_b200/csrc/tsp_update.cuh) without a GPU:
+tests/cpu_emu compiles the same text for the host.  The ordered deposit is arithmetic whose result does not depend on
+the device -- the reference adds 1/cost per ant in ant order with unique indices per statement -- so the kernel source
+must give the oracle's pheromone matrix bit for bit (all variants: plain, elitist, min-max); tour costs follow ATen's
+CUDA summation order and are compared with the CPU sum to fp32 rounding, and the three cost kernels with each other
+exactly.  The sm_100a build of the same source is checked on the GPU by tests/test_gpu_tsp.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aco_torch as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "cpu_emu")
+vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+
+@pytest.fixture(scope="session")
+def emu_u():
+    subprocess.run(["make", "-C", EMU_DIR, "-s", "_build/libtsp_update_emu.so"], check=True)
+    h = ctypes.CDLL(os.path.join(EMU_DIR, "_build", "libtsp_update_emu.so"))
+    h.emu_tsp_cost.restype = ctypes.c_char_p
+    h.emu_tsp_cost.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp, ci]
+    h.emu_tsp_update.restype = ctypes.c_char_p
+    h.emu_tsp_update.argtypes = [vp, vp, vp, ci, ci, cf, ci, ci, cf, vp, vp, vp, vp]
+    return h
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _instance(n, A, seed):
+    torch.manual_seed(seed)
+    xy = torch.rand(n, 2)
+    dist = torch.norm(xy[:, None] - xy, dim=2, p=2)
+    dist[torch.arange(n), torch.arange(n)] = 1e9
+    paths = torch.stack([torch.randperm(n) for _ in range(A)], dim=1).contiguous()          # [n, A] int64
+    return dist.contiguous(), paths
+
+
+def _costs(emu_u, dist, paths, mode):
+    from deepaco_b200 import _engine as E
+    n, A = paths.shape
+    bw, vec, _ = E.aten_sum_plan(n, A)
+    lbw = int(np.log2(min(bw, 32)))
+    costs = torch.full((A,), float("nan"))
+    nbr = torch.full((n, A), -1, dtype=torch.int32)
+    tours = paths.T.contiguous().to(torch.int16)
+    err = emu_u.emu_tsp_cost(_ptr(dist), _ptr(paths) if mode == "paths" else None, None if mode == "paths" else _ptr(tours), n, A, lbw,
+                             int(vec), _ptr(costs), _ptr(nbr), int(mode == "tile"))
+    assert err is None, err
+    return costs, nbr
+
+
+@pytest.mark.parametrize("n,A", [(20, 8), (100, 40), (130, 33), (200, 16)])
+def test_cost_kernels_on_host(emu_u, n, A):
+    dist, paths = _instance(n, A, n)
+    want = O.tsp_path_costs(dist, paths)
+    got = {m: _costs(emu_u, dist, paths, m) for m in ("paths", "tours", "tile")}
+    for m, (c, nbr) in got.items():
+        assert torch.allclose(c, want, rtol=1e-6), m
+        assert torch.equal(c, got["paths"][0]), m                         # same summation order in all three kernels
+        assert torch.equal(nbr, got["paths"][1]), m
+    nbr = got["tile"][1].to(torch.int64) & 0xffffffff
+    prev, nxt = torch.roll(paths, 1, dims=0), torch.roll(paths, -1, dims=0)
+    cols = torch.arange(A).expand(n, A)
+    assert torch.equal(nbr[paths, cols], (prev << 16) | nxt)              # N[u][a] = pred << 16 | succ of node u in tour a
+
+
+@pytest.mark.parametrize("kw", [{}, {"elitist": True}, {"min_max": True}, {"min_max": True, "scale": 1.7}])
+@pytest.mark.parametrize("n,A", [(20, 8), (100, 48), (61, 130)])
+def test_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, n, A, kw):
+    dist, paths = _instance(n, A, 7 * n + A)
+    torch.manual_seed(1)
+    ph0 = (torch.rand(n, n) + 0.2).contiguous()
+    costs = O.tsp_path_costs(dist, paths).contiguous()
+    _, nbr = _costs(emu_u, dist, paths, "tile")
+    elitist, min_max, scale = kw.get("elitist", False), kw.get("min_max", False), kw.get("scale")
+    ph_min = 0.1
+    ph_max = torch.tensor([float(n / costs.min())])
+    ref_in = ph0 * scale if scale else ph0                                 # MMAS rescale happens before the update (tsp/aco.py:86-87)
+    want = O.tsp_update_pheromone(ref_in.clone(), paths, costs, decay=0.9, elitist=elitist, min_max=min_max, ph_min=ph_min,
+                                  ph_max=float(ph_max))
+    ph = ph0.clone()
+    heu = torch.rand(n, n).contiguous()
+    prod = torch.full((n, n), float("nan"))
+    sc = torch.tensor([scale], dtype=torch.float32) if scale else None
+    err = emu_u.emu_tsp_update(_ptr(ph), _ptr(nbr), _ptr(costs), n, A, 0.9, int(elitist), int(min_max), ph_min,
+                               _ptr(ph_max) if min_max else None, _ptr(sc), _ptr(heu), _ptr(prod))
+    assert err is None, err
+    assert torch.equal(ph, want)
+    assert torch.equal(prod, ph * heu)                                     # fused product for the next construction
