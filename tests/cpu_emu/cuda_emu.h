@@ -150,6 +150,7 @@ static inline uint32_t emu_warp_fold(uint32_t mine, F f) {
 static inline uint32_t __ballot_sync(unsigned, int pred) {
     return emu_warp_fold(pred ? (1u << (emu::ctx.tid.x & 31)) : 0u, [](uint32_t a, uint32_t b) { return a | b; });
 }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline uint32_t __reduce_max_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a > b ? a : b; }); }
 static inline uint32_t __reduce_min_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a < b ? a : b; }); }
 static inline uint32_t __reduce_or_sync(unsigned, uint32_t v) { return emu_warp_fold(v, [](uint32_t a, uint32_t b) { return a | b; }); }

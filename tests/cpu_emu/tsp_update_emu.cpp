@@ -1,5 +1,5 @@
-// csrc/tsp_update.cuh (tour cost, neighbour table, fused evaporate + ordered deposit) compiled for the host (see
-// cuda_emu.h) behind entry points shaped like deepaco_tsp_cost / deepaco_tsp_update.  Test infrastructure only.
+// csrc/tsp_update.cuh and csrc/cvrp_update.cuh (tour cost, neighbour table, fused evaporate + ordered deposit) compiled
+// for the host (see cuda_emu.h) behind entry points shaped like deepaco_{tsp,cvrp}_cost / _update.  Test infrastructure only.
 #include "cuda_emu.h"
 
 #include <algorithm>
@@ -16,6 +16,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 #define __shared__ static
 
 #include "../../deepaco_b200/csrc/tsp_update.cuh"
+#include "../../deepaco_b200/csrc/cvrp_update.cuh"
 
 using namespace deepaco;
 
@@ -56,5 +57,33 @@ extern "C" const char* emu_tsp_update(float* ph, const uint32_t* nbr, const floa
     emu::launch([](const UpdArgs& q) { tsp_update_kernel(q.ph, q.nbr, q.costs, q.n, q.A, q.decay, q.elitist, q.min_max, q.ph_min,
                                                         q.ph_max, q.scale, q.heu, q.prod); },
                 a, (n + W - 1) / W, 1, W * 32, smem);
+    return nullptr;
+}
+
+// ---- CVRP (one colony per call) ----
+namespace {
+struct CvrpCostArgs {
+    const float* dist; const int64_t* paths; const uint16_t* tours; int N, A, rows_in, T; float* costs; uint32_t* nbr;
+};
+}  // namespace
+
+extern "C" const char* emu_cvrp_cost(const float* dist, const int64_t* paths, const uint16_t* tours, int N, int A, int rows_in, int T,
+                                     float* costs, uint32_t* nbr) {
+    if (!dist || ((paths != nullptr) == (tours != nullptr)) || N < 2 || A < 1 || T < 1 || T > rows_in) return "bad arguments";
+    const CvrpCostArgs a{dist, paths, tours, N, A, rows_in, T, costs, nbr};
+    const int W = 8;
+    emu::launch([](const CvrpCostArgs& q) { cvrp_cost_kernel(q.dist, q.paths, q.tours, q.N, q.A, q.rows_in, nullptr, q.T, q.costs, q.nbr); },
+                a, (A + W - 1) / W, 1, W * 32, 16);
+    return nullptr;
+}
+
+extern "C" const char* emu_cvrp_update(float* ph, const uint32_t* nbr, const float* costs, int N, int A, float decay, int elitist,
+                                       int min_max, float ph_min, const float* ph_max, const float* scale) {
+    if (!ph || !nbr || !costs || N < 2 || A < 1 || (min_max && !ph_max)) return "bad arguments";
+    const UpdArgs a{ph, nbr, costs, N, A, decay, elitist, min_max, ph_min, ph_max, scale, nullptr, nullptr};
+    const int threads = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    emu::launch([](const UpdArgs& q) { cvrp_update_kernel(q.ph, q.nbr, q.costs, q.n, q.A, q.decay, q.elitist, q.min_max, q.ph_min,
+                                                         q.ph_max, q.scale, q.heu, q.prod); },
+                a, N, 1, threads, (size_t)A * 8);
     return nullptr;
 }

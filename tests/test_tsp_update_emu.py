@@ -95,3 +95,57 @@ def test_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, n, A
     assert err is None, err
     assert torch.equal(ph, want)
     assert torch.equal(prod, ph * heu)                                     # fused product for the next construction
+
+
+# ---- CVRP: open-path cost, one-directional deposit, repeated (0, 0) pairs count once, 1e-10 floor ------------------
+@pytest.fixture(scope="session")
+def emu_c(emu_u):
+    emu_u.emu_cvrp_cost.restype = ctypes.c_char_p
+    emu_u.emu_cvrp_cost.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
+    emu_u.emu_cvrp_update.restype = ctypes.c_char_p
+    emu_u.emu_cvrp_update.argtypes = [vp, vp, vp, ci, ci, cf, ci, ci, cf, vp, vp]
+    return emu_u
+
+
+def _cvrp_paths(customers, A, seed):
+    torch.manual_seed(seed)
+    loc = torch.cat((torch.tensor([[0.5, 0.5]]), torch.rand(customers, 2)))
+    dist = torch.norm(loc[:, None] - loc, dim=2, p=2)
+    N = customers + 1
+    dist[torch.arange(N), torch.arange(N)] = 1e-10
+    demand = torch.cat((torch.zeros(1), torch.randint(1, 10, (customers,)).float()))
+    heu = torch.rand(N, N) * 0.98 + 1e-10
+    paths = O.cvrp_gen_path(torch.ones_like(dist), heu, demand, 50, A)      # the reference's construction ops on CPU
+    return dist.contiguous(), paths.contiguous()
+
+
+@pytest.mark.parametrize("kw", [{}, {"elitist": True}, {"min_max": True}])
+@pytest.mark.parametrize("customers,A", [(12, 8), (40, 33)])
+def test_cvrp_cost_and_update_kernels_on_host(emu_c, customers, A, kw):
+    dist, paths = _cvrp_paths(customers, A, 100 + customers)
+    N, rows = customers + 1, paths.shape[0]
+    T = rows - 1
+    assert bool((paths[-1] == 0).all()) and bool(((paths[:-1] == 0) & (paths[1:] == 0)).any())   # padded (0, 0) pairs present
+    want_c = O.cvrp_path_costs(dist, paths)
+    costs = torch.full((A,), float("nan"))
+    nbr = torch.zeros((N, A), dtype=torch.int32)
+    assert emu_c.emu_cvrp_cost(_ptr(dist), _ptr(paths), None, N, A, rows, T, _ptr(costs), _ptr(nbr)) is None
+    assert torch.allclose(costs, want_c, rtol=1e-6)
+    tours = paths.T.contiguous().to(torch.int16)
+    costs2, nbr2 = torch.full((A,), float("nan")), torch.zeros((N, A), dtype=torch.int32)
+    assert emu_c.emu_cvrp_cost(_ptr(dist), None, _ptr(tours), N, A, rows, T, _ptr(costs2), _ptr(nbr2)) is None
+    assert torch.equal(costs2, costs) and torch.equal(nbr2, nbr)
+
+    elitist, min_max = kw.get("elitist", False), kw.get("min_max", False)
+    torch.manual_seed(2)
+    ph0 = (torch.rand(N, N) * 0.5 + 1e-11).contiguous()                     # some cells below the 1e-10 floor after decay
+    ph0[3, 4] = 5e-11
+    ph_min, ph_max = 0.05, torch.tensor([0.9])
+    c_in = want_c.contiguous()
+    want = O.cvrp_update_pheromone(ph0.clone(), paths, c_in, decay=0.9, elitist=elitist, min_max=min_max, ph_min=ph_min,
+                                   ph_max=float(ph_max))
+    ph = ph0.clone()
+    err = emu_c.emu_cvrp_update(_ptr(ph), _ptr(nbr), _ptr(c_in), N, A, 0.9, int(elitist), int(min_max), ph_min,
+                                _ptr(ph_max) if min_max else None, None)
+    assert err is None, err
+    assert torch.equal(ph, want)
