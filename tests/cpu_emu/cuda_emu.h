@@ -130,6 +130,16 @@ static inline int __syncthreads_or(int predicate) {
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+static inline float atomicAdd(float* p, float v) {
+    uint32_t old = __atomic_load_n(reinterpret_cast<uint32_t*>(p), __ATOMIC_ACQUIRE), want;
+    float f;
+    do {
+        memcpy(&f, &old, 4);
+        f += v;
+        memcpy(&want, &f, 4);
+    } while (!__atomic_compare_exchange_n(reinterpret_cast<uint32_t*>(p), &old, want, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE));
+    return f - v;
+}
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_ACQ_REL); }
 static inline int atomicMax(int* p, int v) {
     int old = __atomic_load_n(p, __ATOMIC_ACQUIRE);

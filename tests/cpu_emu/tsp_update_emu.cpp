@@ -17,6 +17,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 #include "../../deepaco_b200/csrc/tsp_update.cuh"
 #include "../../deepaco_b200/csrc/cvrp_update.cuh"
+#include "../../deepaco_b200/csrc/backward.cuh"
 
 using namespace deepaco;
 
@@ -85,5 +86,14 @@ extern "C" const char* emu_cvrp_update(float* ph, const uint32_t* nbr, const flo
     emu::launch([](const UpdArgs& q) { cvrp_update_kernel(q.ph, q.nbr, q.costs, q.n, q.A, q.decay, q.elitist, q.min_max, q.ph_min,
                                                          q.ph_max, q.scale, q.heu, q.prod); },
                 a, N, 1, threads, (size_t)A * 8);
+    return nullptr;
+}
+
+// ---- analytic backward of the log-probabilities (deepaco_logp_backward) ----
+extern "C" const char* emu_logp_backward(const float* ph, const float* heu, const int64_t* paths, const float* glogp, int n, int A,
+                                         int rows, const float* demand, float capacity, float* g_heu, float* g_ph) {
+    if (!ph || !heu || !paths || !glogp || !g_heu || n < 2 || A < 1 || rows < 2) return "bad arguments";
+    const BackwardParams p{ph, heu, paths, glogp, g_heu, g_ph, demand, capacity, n, A, rows};
+    emu::launch(logp_backward_kernel, p, (A + 7) / 8, 1, 256, 16);
     return nullptr;
 }

@@ -149,3 +149,33 @@ def test_cvrp_cost_and_update_kernels_on_host(emu_c, customers, A, kw):
                                 _ptr(ph_max) if min_max else None, None)
     assert err is None, err
     assert torch.equal(ph, want)
+
+
+# ---- analytic gradient of the sampled log-probabilities (REINFORCE) vs autograd through the reference's ops ----------
+@pytest.mark.parametrize("problem", ["tsp", "cvrp"])
+def test_logp_backward_kernel_on_host_matches_autograd_through_the_reference_ops(emu_u, problem):
+    emu_u.emu_logp_backward.restype = ctypes.c_char_p
+    emu_u.emu_logp_backward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, cf, vp, vp]
+    torch.manual_seed(5)
+    n, A = 30, 16
+    ph = (torch.rand(n, n) + 0.5).requires_grad_(True)
+    heu0 = torch.rand(n, n) * 0.9 + 0.05
+    heu0[torch.rand(n, n) < 0.3] = 1e-10                   # the clamp region (p < eps) passes no gradient
+    heu = heu0.clone().requires_grad_(True)
+    demand = None
+    torch.manual_seed(9)
+    if problem == "tsp":
+        paths, logp = O.tsp_gen_path(ph, heu, A, require_prob=True)
+    else:
+        demand = torch.cat((torch.zeros(1), torch.randint(1, 10, (n - 1,)).float())).contiguous()
+        paths, logp = O.cvrp_gen_path(ph, heu, demand, 30, A, require_prob=True)
+    g = torch.randn_like(logp)
+    (logp * g).sum().backward()
+    g_heu, g_ph = torch.zeros(n, n), torch.zeros(n, n)
+    paths_c, g_c = paths.contiguous(), g.contiguous()
+    err = emu_u.emu_logp_backward(_ptr(ph.detach().contiguous()), _ptr(heu.detach().contiguous()), _ptr(paths_c), _ptr(g_c), n, A,
+                                  paths.shape[0], _ptr(demand), 30.0, _ptr(g_heu), _ptr(g_ph))
+    assert err is None, err
+    scale = float(heu.grad.abs().max())
+    assert torch.allclose(g_heu, heu.grad, rtol=1e-4, atol=1e-6 * scale)
+    assert torch.allclose(g_ph, ph.grad, rtol=1e-4, atol=1e-6 * float(ph.grad.abs().max()))
