@@ -129,6 +129,8 @@ static inline int __syncthreads_or(int predicate) {
 }
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+template <class T>
+static inline T __ldcg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 static inline float atomicAdd(float* p, float v) {
     uint32_t old = __atomic_load_n(reinterpret_cast<uint32_t*>(p), __ATOMIC_ACQUIRE), want;

@@ -260,3 +260,49 @@ def test_eval_weights_follow_running_statistics_updated_in_training_mode():
     assert not torch.equal(w0, w1)
     assert torch.equal(w1, N.pack_weights(net))
     assert net._weights() is w1                                   # unchanged state -> cached tensor
+
+
+@pytest.fixture(scope="session")
+def emu_g():
+    out = os.path.join(EMU_DIR, "_build", "libgnn_emu.so")
+    subprocess.run(["make", "-C", EMU_DIR, "-s", "_build/libgnn_emu.so"], check=True)
+    h = ctypes.CDLL(out)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    h.emu_gnn_forward.restype = ctypes.c_char_p
+    h.emu_gnn_forward.argtypes = [vp] * 6 + [ci] * 4 + [vp] * 4 + [ctypes.c_float, ci]
+    return h
+
+
+@pytest.mark.parametrize("kind,fixture", CASES)
+def test_one_cta_eval_kernel_on_host_matches_the_restatement_and_the_group_kernel_bit_for_bit(emu, emu_g, golden, kind, fixture):
+    """deepaco_gnn_forward (csrc/gnn.cuh: one CTA per instance, TMA double-buffered weights, fused reshape + EPS) through
+    its host build: equal to the eval-mode torch restatement to fp32 rounding, equal to deepaco_gnn_forward_group's host
+    build BIT FOR BIT (the two kernels are interchangeable), and the dense output is Net.reshape(...) + EPS."""
+    from deepaco_b200 import net as N
+    from oracle import net_torch
+    g = golden(fixture)
+    net = _net(kind).eval()
+    pyg = _pyg(g)
+    with torch.no_grad():
+        want = net_torch.net_forward(net, pyg)
+    n = pyg.x.shape[0]
+    graph = N.train_graph(pyg.edge_index[None], pyg.edge_attr[None], n, backward=False)
+    E = graph["E"]
+    w = N.pack_weights(net)
+    x = pyg.x.to(torch.float32)[None].contiguous()
+    node_ws = torch.full((1, n, 6 * N.UNITS), float("nan"))
+    edge_ws = torch.full((1, E, N.UNITS), float("nan"))
+    heu = torch.full((1, E), float("nan"))
+    dense = torch.full((1, n, n), float("nan"))
+    err = emu_g.emu_gnn_forward(x.data_ptr(), graph["row_ptr"].data_ptr(), graph["dst"].data_ptr(), graph["attr"].data_ptr(),
+                                graph["order"].data_ptr(), w.data_ptr(), n, E, net.emb_net.feats, 1, node_ws.data_ptr(),
+                                edge_ws.data_ptr(), heu.data_ptr(), dense.data_ptr(), 1e-10, 256)
+    assert err is None, err
+    assert torch.allclose(heu[0], want, rtol=2e-4, atol=1e-7)
+    assert torch.equal(dense[0], N.Net.reshape(pyg, heu[0]) + 1e-10)
+    # group kernel, 4 CTAs per graph
+    bufs = N.eval_buffers(1, n, E, "cpu")
+    heu_g = torch.full((1, E), float("nan"))
+    a, keep = N.train_args(x, graph, w, bufs, net.emb_net.feats, 4, 1e-5, heu_out=heu_g)
+    assert emu.emu_gnn_forward_group(ctypes.byref(a), 128) is None
+    assert torch.equal(heu_g, heu)
