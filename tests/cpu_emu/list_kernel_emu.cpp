@@ -54,18 +54,23 @@ static inline uint32_t pin_u32(uint32_t v) { return v; }
 using namespace deepaco;
 
 namespace {
-template <int E, bool CVRP>
+template <int E, bool CVRP, bool GLOBAL = false>
 void run_list(const ListParams& p, int W, bool logp, bool ext) {
-    const size_t sm = list_kernel_smem(p.n, p.rows, W, CVRP);
+    const size_t sm = list_kernel_smem(p.n, p.rows, W, CVRP, GLOBAL);
     const int gx = (p.A + W - 1) / W;
     auto go = [&](auto kernel) { emu::launch(kernel, p, gx * p.B, 1, W * 32, sm, gx); };
-    if (ext) { if (logp) go(aco_list_kernel<E, CVRP, true, true>); else go(aco_list_kernel<E, CVRP, false, true>); }
-    else { if (logp) go(aco_list_kernel<E, CVRP, true, false>); else go(aco_list_kernel<E, CVRP, false, false>); }
+    if (ext) { if (logp) go(aco_list_kernel<E, CVRP, true, true, GLOBAL>); else go(aco_list_kernel<E, CVRP, false, true, GLOBAL>); }
+    else { if (logp) go(aco_list_kernel<E, CVRP, true, false, GLOBAL>); else go(aco_list_kernel<E, CVRP, false, false, GLOBAL>); }
 }
 template <bool CVRP>
 const char* dispatch_list(const ListParams& p, int W) {
     const int epl = CVRP ? (p.n + 31) / 32 : (p.n - 1 + 31) / 32;
     const bool logp = p.logp != nullptr, ext = p.noise != nullptr;
+    if (p.heu == nullptr && p.n > 256) {       // product matrix in global memory (colonies too large for shared memory)
+        if (epl <= 16) run_list<16, CVRP, true>(p, W, logp, ext);
+        else return "n too large for the host harness (n <= 512)";
+        return nullptr;
+    }
     if (epl <= 1) run_list<1, CVRP>(p, W, logp, ext);
     else if (epl <= 2) run_list<2, CVRP>(p, W, logp, ext);
     else if (epl <= 4) run_list<4, CVRP>(p, W, logp, ext);
