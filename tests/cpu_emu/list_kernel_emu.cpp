@@ -50,6 +50,7 @@ static inline uint32_t pin_u32(uint32_t v) { return v; }
 }  // namespace deepaco
 
 #include "../../deepaco_b200/csrc/list_kernel.cuh"
+#include "../../deepaco_b200/csrc/pick_move.cuh"
 
 using namespace deepaco;
 
@@ -125,4 +126,17 @@ extern "C" const char* emu_cvrp_sample(const float* ph, const float* heu, const 
     p.paths = paths; p.logp = logp; p.tours = tours; p.lens = lens; p.tmax = tmax;
     for (int b = 0; b < B; ++b) tmax[b] = 0;
     return dispatch_list<true>(p, W);
+}
+
+// ACO.pick_move (deepaco_pick_move): one step for caller-held masks, Philox noise with the given draw geometry
+extern "C" const char* emu_pick_move(const float* php, const float* heup, const int64_t* prev, const float* mask, const float* mask2,
+                                     int n, int A, uint64_t seed, uint64_t offset, int64_t* actions, float* logp, int* bad_prev,
+                                     int lbw, int vec, uint32_t g_threads, uint32_t g_single) {
+    if (!php || !prev || !mask || !actions || !bad_prev || n < 1 || A < 1) return "bad arguments";
+    PickMoveParams p{};
+    p.php = php; p.heup = heup; p.prev = prev; p.mask = mask; p.mask2 = mask2; p.n = n; p.A = A; p.lbw = lbw; p.vec = vec;
+    p.seed = seed; p.offset = offset; p.g = {g_threads, g_single}; p.actions = actions; p.logp = logp; p.bad_prev = bad_prev;
+    const int W = 8;
+    emu::launch(pick_move_kernel, p, (A + W - 1) / W, 1, W * 32, 16);
+    return nullptr;
 }
