@@ -14,6 +14,11 @@ its own B colonies, no data-path collective).  Prints ONE JSON line on rank 0.
              CUDA-event duration, against the measured HBM copy bandwidth of MEASURED_PEAKS.json
   cpu_baseline / --impl reference
              the reference's PyTorch-CPU path (oracle port, op for op) on the host cores of this box
+  configs    the other BASELINE.json configs (tools/bench_legs.py): c2_dense, c3, c4 on rank 0's GPU; c5 = 64 x TSP-200 x
+             256 ants split over the N ranks with the result gather inside the timed region (strong scaling)
+  ant_sharded  one TSP-200 colony of 8192 ants with its ants split over the N ranks (deepaco_tsp_run_shard: fused
+             NVLink peer stores + flag barrier, no host sync), timed against the same colony on one GPU, bits compared
+  reference_cuda  the reference op sequence with device='cuda' on this GPU
 """
 import argparse
 import json
@@ -253,9 +258,19 @@ def main():
     mat = B * N_NODES * N_NODES * 4
     h2d, d2h = 3 * mat, mat + B * 4 + B * N_NODES * 8
 
+    # ---- multi-GPU data-path legs (every rank takes part): C5 colony-sharded with the result gather in the timed
+    #      region, and one big colony with its ANTS sharded (deepaco_tsp_run_shard)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_legs as L
+    del runner, r1, r2, flush
+    torch.cuda.empty_cache()
+    leg_steps = max(3, min(K, 20))
+    c5 = L.guarded("c5", L.leg_c5, dev, leg_steps)
+    ant = L.guarded("ant_sharded", L.leg_ant_sharded, dev, leg_steps)
+
     if rank != 0:
         if world > 1:
-            dist_pg.barrier()          # rank 0 enters this barrier after its CPU-baseline leg
+            dist_pg.barrier()          # rank 0 enters this barrier after its single-rank legs and the CPU baseline
             dist_pg.destroy_process_group()
         return
 
@@ -289,6 +304,12 @@ def main():
         "single_colony": {"value": N_ANTS / (single_ms * 1e-3), "unit": "ant-tours/s", "ms_per_iteration": single_ms,
                           "note": "one colony of 512 ants, K back-to-back iterations in one deepaco_tsp_run call (rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks,
+        # the other BASELINE.json configs on this GPU (C2 with the dense 1/dist heuristic, C3, C4) and C5 over all ranks
+        "configs": {"c2_dense": L.guarded("c2_dense", L.leg_c2_dense, dev, leg_steps),
+                    "c3": L.guarded("c3", L.leg_c3, dev, leg_steps),
+                    "c4": L.guarded("c4", L.leg_c4, dev, leg_steps),
+                    "c5": c5},
+        "ant_sharded": ant,
     }
     # best-cost gap vs the reference on this GPU: same torch seed, one colony of the workload, oracle = the
     # reference's op sequence run with device='cuda' (outside every timed region)
@@ -308,6 +329,7 @@ def main():
     except Exception as exc:      # the oracle is test infrastructure; its absence must not break the bench
         line["parity"] = {"error": str(exc)[:200]}
     if not args.no_cpu_baseline:
+        line["reference_cuda"] = L.guarded("reference_cuda", L.leg_reference_cuda, dev)
         cb, _, _ = cpu_reference_throughput(100, 2)
         line["cpu_baseline"] = cb
     print(json.dumps(line))

@@ -242,6 +242,25 @@ class TspRunner:
             self.product_valid = True
         return self.lowest_cost
 
+    def run_shard(self, n_iterations, seed, peer, ant_base, n_ants_local, epoch, status, timeout_ms=2000, *, offset=0,
+                  offsets=None, sample_events=None):
+        """deepaco_tsp_run_shard: this rank builds ants [ant_base, ant_base + n_ants_local) of every colony; `peer`
+        (dist.PeerMemory) names every rank's tour buffers / flag words.  No host sync."""
+        from .dist import shard_tables
+        offs = _offsets(offsets, self.B, self.dev)
+        a = self._args(seed, offset, offs, sample_events)
+        tours_tab, flags_tab = shard_tables(peer)
+        t_arr = (C.c_uint64 * len(tours_tab))(*tours_tab)
+        f_arr = (C.c_uint64 * len(flags_tab))(*flags_tab)
+        sh = _lib.ShardArgs(peer.rank, peer.world, int(ant_base), int(n_ants_local), C.cast(t_arr, C.c_void_p),
+                            C.cast(f_arr, C.c_void_p), int(epoch) & 0xffffffff, int(timeout_ms), ptr(status))
+        with torch.cuda.device(self.dev):
+            check(lib().deepaco_tsp_run_shard(C.byref(a), C.byref(sh), int(n_iterations), stream_ptr(self.dev)),
+                  "deepaco_tsp_run_shard")
+        if n_iterations > 0:
+            self.product_valid = True
+        return self.lowest_cost
+
     def run_host(self, n_iterations, seed, distances_h, heuristic_h, pheromone_h, lowest_h, shortest_h, offset=0,
                  offsets=None, copy_back_pheromone=True):
         """deepaco_tsp_run_host: pinned HOST tensors in/out (pheromone_h is updated in place when

@@ -60,6 +60,12 @@ class TspRunArgs(C.Structure):
                 ("T_nls", _i32), ("T_p", _i32), ("heuristic_dist", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
 
 
+class ShardArgs(C.Structure):
+    """deepaco_shard_args (include/deepaco_b200.h)."""
+    _fields_ = [("rank", _i32), ("world", _i32), ("ant_base", _i32), ("n_ants_local", _i32), ("peer_tours_host", _vp),
+                ("peer_flags_host", _vp), ("epoch", C.c_uint32), ("timeout_ms", C.c_uint32), ("status", _vp)]
+
+
 class CvrpRunArgs(C.Structure):
     """deepaco_cvrp_run_args (include/deepaco_b200.h)."""
     _fields_ = [("n_nodes", _i32), ("n_ants", _i32), ("n_colonies", _i32), ("capacity", _f32), ("decay", _f32),
@@ -83,6 +89,7 @@ _SIGNATURES["deepaco_gnn_train_backward"] = (_i32, [C.POINTER(GnnTrainArgs), _vp
 _SIGNATURES["deepaco_gnn_forward_group"] = (_i32, [C.POINTER(GnnTrainArgs), _vp])
 _SIGNATURES["deepaco_cvrp_run"] = (_i32, [C.POINTER(CvrpRunArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp])
+_SIGNATURES["deepaco_tsp_run_shard"] = (_i32, [C.POINTER(TspRunArgs), C.POINTER(ShardArgs), _i32, _vp])
 _SIGNATURES["deepaco_tsp_run_host"] = (_i32, [C.POINTER(TspRunArgs), _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp])
 
 _lib = None

@@ -66,22 +66,16 @@ extern "C" int deepaco_cvrp_sample(const float* pheromone, const float* heuristi
     const size_t cap = (size_t)di->max_smem_optin - 1024;
     const bool global_p = !(n_nodes <= 256 && list_kernel_smem(n_nodes, path_rows, W, true) <= cap);
     DACO_CHECK_ARG(n_nodes <= 1024, "deepaco_cvrp_sample: n_nodes=%d exceeds the supported maximum of 1024", n_nodes);
-    static float* cvrp_prod_ws = nullptr;
-    static size_t cvrp_prod_ws_bytes = 0;
+    StreamScratch prod_ws;   // stream-ordered scratch, private to this call (freed behind the kernel on return)
     if (global_p) {
         W = 4;
         if (heuristic) {   // product once per call into a scratch matrix; rows are then gathered from L2
-            const size_t need_b = (size_t)n_colonies * n_nodes * n_nodes * sizeof(float);
-            if (need_b > cvrp_prod_ws_bytes) {
-                if (cvrp_prod_ws) cudaFree(cvrp_prod_ws);
-                cvrp_prod_ws = nullptr; cvrp_prod_ws_bytes = 0;
-                DACO_CHECK_CUDA(cudaMalloc(&cvrp_prod_ws, need_b));
-                cvrp_prod_ws_bytes = need_b;
-            }
             const size_t cnt = (size_t)n_colonies * n_nodes * n_nodes;
-            hadamard3_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, cvrp_prod_ws, cnt);
+            DACO_CHECK_CUDA(prod_ws.alloc(cnt * sizeof(float), st));
+            float* ws = static_cast<float*>(prod_ws.ptr);
+            hadamard3_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, ws, cnt);
             DACO_CHECK_LAUNCH();
-            p.ph = cvrp_prod_ws; p.heu = nullptr;
+            p.ph = ws; p.heu = nullptr;
         }
     }
     auto need = [&](int w) { return list_kernel_smem(n_nodes, path_rows, w, true, global_p); };

@@ -42,6 +42,31 @@ const DeviceInfo* device_info() {
     return &cache[dev];
 }
 
+cudaError_t StreamScratch::alloc(size_t bytes, cudaStream_t stream) {
+    static bool tuned[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!tuned[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            tuned[dev] = true;
+        }
+    }
+    st = stream;
+    return cudaMallocAsync(&ptr, bytes, stream);
+}
+
+StreamScratch::~StreamScratch() {
+    if (ptr) cudaFreeAsync(ptr, st);
+}
+
 static int last_pow2(int64_t v) {
     int p = 1;
     while ((int64_t)p * 2 <= v) p *= 2;

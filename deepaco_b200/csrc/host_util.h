@@ -35,6 +35,19 @@ struct DrawPlan {
 };
 DrawPlan torch_draw_plan(int64_t numel, const DeviceInfo& di);
 
+// Stream-ordered scratch memory (cudaMallocAsync on the current device's default pool; the pool's release threshold is
+// raised once per device so freed blocks stay cached).  The free is queued on the same stream behind the consumer, so
+// the buffer is private to (device, stream, call): no process-global workspace.
+struct StreamScratch {
+    void* ptr = nullptr;
+    cudaStream_t st = nullptr;
+    StreamScratch() = default;
+    StreamScratch(const StreamScratch&) = delete;
+    StreamScratch& operator=(const StreamScratch&) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream);
+    ~StreamScratch();
+};
+
 void count_launch();   // every kernel launch of the library passes through DACO_CHECK_LAUNCH
 
 // (count_launch is declared before the macros that use it)

@@ -79,6 +79,53 @@ __device__ __forceinline__ float noise_rcp(uint32_t ctr_lo, uint32_t ctr_hi, uin
     return rcp_approx(exp1_from_word(philox_word_x(ctr_lo, ctr_hi, sub, K)));
 }
 
+// Component COMP (0..3 = .x .. .w) of the Philox4x32-10 block at (counter, subsequence): torch's draw kernels hand
+// component (li / threads) % 4 of call (li / threads) / 4 to element li once a tensor has more elements than the launch
+// has threads (DistributionTemplates.h:65-89).  COMP = 0 compiles to the same instructions as philox_word_x.
+template <int COMP>
+__device__ __forceinline__ uint32_t philox_word_comp(uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub, const PhiloxRoundKeys& K) {
+    if (COMP == 0) return philox_word_x(ctr_lo, ctr_hi, sub, K);
+    uint32_t c0 = ctr_lo, c1 = ctr_hi, c2 = sub, c3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(kPhiloxM0, c0), l0 = kPhiloxM0 * c0;
+        const uint32_t h1 = __umulhi(kPhiloxM1, c2), l1 = kPhiloxM1 * c2;
+        c0 = h1 ^ c1 ^ K.a[r];
+        c2 = h0 ^ c3 ^ K.b[r];
+        c1 = l1;
+        c3 = l0;
+    }
+    return COMP == 1 ? c1 : (COMP == 2 ? c2 : c3);
+}
+template <int COMP>
+__device__ __forceinline__ float noise_rcp_comp(uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub, const PhiloxRoundKeys& K) {
+    return rcp_approx(exp1_from_word(philox_word_comp<COMP>(ctr_lo, ctr_hi, sub, K)));
+}
+// Any geometry, run-time: element li = q0 * threads + r0 + j of a draw whose call 0 has counter (ctr_lo, ctr_hi).
+// An ant's n consecutive elements cross a multiple of `threads` at most once, so no division is needed per column.
+__device__ __forceinline__ float noise_rcp_general(uint32_t ctr_lo, uint32_t ctr_hi, uint32_t q0, uint32_t r0, uint32_t j,
+                                                   uint32_t threads, const PhiloxRoundKeys& K) {
+    uint32_t sub = r0 + j, q = q0;
+    if (sub >= threads) {
+        sub -= threads;
+        q += 1u;
+    }
+    const uint32_t call = q >> 2, comp = q & 3u;
+    const uint32_t lo = ctr_lo + call, hi = ctr_hi + (lo < ctr_lo ? 1u : 0u);
+    uint32_t c0 = lo, c1 = hi, c2 = sub, c3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(kPhiloxM0, c0), l0 = kPhiloxM0 * c0;
+        const uint32_t h1 = __umulhi(kPhiloxM1, c2), l1 = kPhiloxM1 * c2;
+        c0 = h1 ^ c1 ^ K.a[r];
+        c2 = h0 ^ c3 ^ K.b[r];
+        c1 = l1;
+        c3 = l0;
+    }
+    const uint32_t w = comp == 0u ? c0 : (comp == 1u ? c1 : (comp == 2u ? c2 : c3));
+    return rcp_approx(exp1_from_word(w));
+}
+
 #ifndef DEEPACO_CPU_EMU
 // opaque register copy: stops the compiler from re-deriving a shared-memory address inside the step loop
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
@@ -324,6 +371,10 @@ __global__ void __launch_bounds__(GLOBAL_P ? 256 : 512, GLOBAL_P ? 1 : 2) aco_li
         uint16_t* out = p.tours + ((size_t)b * p.A + a0) * R;
         for (int i = tid; i < R * wvalid; i += nthreads) out[i] = tour_all[i];
     }
+    for (int r = 0; r < p.n_peers; ++r) {   // fused exchange (ant sharding): this CTA's tours go to every GPU's buffer
+        uint16_t* out = p.peer_tours[r] + ((size_t)b * p.A_total + p.ant_base + a0) * R;
+        for (int i = tid; i < R * wvalid; i += nthreads) out[i] = tour_all[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,8 +401,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 #endif  // DEEPACO_CPU_EMU
 
 // Rare tail of the fallback step: a tie or a near-tie among the approximate scores -> exact arithmetic in ATen order.
+// (ctr_lo, ctr_hi) = Philox counter of call 0 of this step's draw; li0 = linear element index of the ant's column 0.
 static __device__ DACO_NOINLINE uint32_t knn_exact_tail(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t ctr_lo, uint32_t ctr_hi,
-                                                       uint32_t sub_base) {
+                                                       uint32_t li0) {
     const int lane = threadIdx.x & 31;
     uint32_t* alive_scratch = reinterpret_cast<uint32_t*>(__cvta_shared_to_generic(wbase + 256u));
     for (int w = 0; w < 8; ++w) {       // alive bitmap for exact_step from the alive byte map
@@ -363,17 +415,18 @@ static __device__ DACO_NOINLINE uint32_t knn_exact_tail(const ListParams& p, uin
     float pn;
     const uint64_t off_step = (((uint64_t)ctr_hi << 32) | ctr_lo) << 2;
     return exact_step(reinterpret_cast<const float*>(__cvta_shared_to_generic(row_addr)), alive_scratch, p.n, p.lbw, p.vec, p.double_norm, nullptr,
-                      p.seed, off_step, sub_base, p.g_noise, &pn);
+                      p.seed, off_step, li0, p.g_noise, &pn);
 }
 
 // Fallback step of the kNN kernel: evaluate every unvisited column of row `cur` (row_addr = shared address of that
 // row of P), commit the winner (alive byte, tour slot at shared address `slot`) and return it.  Everything is passed by value / as
-// 32-bit shared addresses so that the call marshals few registers.
+// 32-bit shared addresses so that the call marshals few registers.  GEN: any torch draw geometry (element li = q0 *
+// threads + r0 + j); otherwise the single-launch geometry (q0 = 0, every element is component .x of call 0).
+template <bool GEN>
 static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uint32_t row_addr, uint32_t wbase, uint32_t slot, uint32_t n,
-                                                       uint32_t seed_lo, uint32_t seed_hi, uint32_t ctr_lo, uint32_t ctr_hi, uint32_t sub_base) {
+                                                       uint32_t ctr_lo, uint32_t ctr_hi, uint32_t q0, uint32_t r0) {
     const uint32_t lane = threadIdx.x & 31u;
     const PhiloxRoundKeys& K = p.keys;   // the compiler clones this function for its kernel: constant-bank operands
-    (void)seed_lo; (void)seed_hi;
     // Compact the unvisited columns first (ids = the not-yet-written tail of this ant's tour buffer, one slot per
     // unvisited node by construction): the Philox work shrinks from ceil(n/32) rounds to ceil(alive/32).
     // Lane l looks at columns 128r + 4l .. 4l+3 (one 32-bit load of the alive bytes: 0xff = unvisited; bytes >= n are 0);
@@ -399,7 +452,8 @@ static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uin
         const uint32_t i = base + lane;
         const bool on = i < cnt;
         const uint32_t j = on ? lds_u16(ids_addr + 2u * i) : 0u;
-        float A = __fmul_rn(lds_f32(row_addr + 4u * j), noise_rcp(ctr_lo, ctr_hi, sub_base + j, K));
+        const float rq = GEN ? noise_rcp_general(ctr_lo, ctr_hi, q0, r0, j, p.g_noise.threads, K) : noise_rcp(ctr_lo, ctr_hi, r0 + j, K);
+        float A = __fmul_rn(lds_f32(row_addr + 4u * j), rq);
         A = on ? A : 0.f;
         if (A > bestA) {
             second = bestA;
@@ -417,12 +471,41 @@ static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uin
     const uint32_t nears = __ballot_sync(DACO_FULL, second >= thr);
     uint32_t jstar;
     if (nears == 0u && __popc(close) == 1) jstar = __shfl_sync(DACO_FULL, bestj, 31 - __clz(close));
-    else jstar = knn_exact_tail(p, row_addr, wbase, ctr_lo, ctr_hi, sub_base);
+    else jstar = knn_exact_tail(p, row_addr, wbase, ctr_lo, ctr_hi, GEN ? q0 * p.g_noise.threads + r0 : r0);
     __syncwarp();
     DACO_STS_U8(wbase + jstar, 0u);
     sts_u16(slot, jstar);
     __syncwarp();
     return jstar;
+}
+
+// Fast steps of one tour: lane l evaluates column knn[cur][l] only.  Runs until the tour is complete or a step needs
+// the dense / exact treatment (returns with `slot` at that step).  COMP = Philox output word of this ant's elements.
+template <int COMP>
+__device__ __forceinline__ void knn_fast_steps(uint32_t& slot, uint32_t& ctr_lo, int& cur, const uint32_t slot_end, const uint32_t ctr_step,
+                                               const uint32_t ctr_hi, const uint32_t sub0, const uint32_t knn_lane, const uint32_t wbase,
+                                               const uint32_t T_addr, const uint32_t P_addr, const uint32_t n, const PhiloxRoundKeys& K) {
+#pragma unroll 1
+    for (; slot < slot_end; slot += 2u, ctr_lo += ctr_step) {
+        const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
+        const uint32_t alive = lds_s8(wbase + j);     // sign-extended: all ones while column j is unvisited
+        const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
+        const float x = __uint_as_float(__float_as_uint(lds_f32(P_addr + ((uint32_t)cur * n + j) * 4u)) & alive);
+        const float A = __fmul_rn(x, noise_rcp_comp<COMP>(ctr_lo, ctr_hi, sub0 + j, K));
+        const uint32_t mybits = __float_as_uint(A);
+        const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
+        const float top = __uint_as_float(topbits);
+        // lanes within 2^-18 (relative) of the top score, the top lane included: the step is decided here
+        // only when that is exactly one lane and no unlisted column can beat it
+        const uint32_t close = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f));
+        if (!(__popc(close) == 1 && T < top)) break;
+        const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
+        // Every lane stores the same two values to the same addresses: one wavefront, no predicate to
+        // maintain, and each lane later reads what it wrote itself, so no warp-level fence between steps.
+        DACO_STS_U8(wbase + jstar, 0u);
+        sts_u16(slot, jstar);
+        cur = (int)jstar;
+    }
 }
 
 // TSP only, 32 < n <= 256, no log-probs, Philox noise, compact tours out.
@@ -432,7 +515,10 @@ static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uin
 constexpr int kKnnWarpBytes = 256 + 128 + 512;
 constexpr int kKnnBoundBytes = 1024;
 
-template <bool FUSE_COST, int MAXW>
+// GEN = false: single-launch draw geometry (n_ants * n <= torch's grid * 256 threads: every element is word .x of call 0).
+// GEN = true : any geometry (big colonies): an ant's elements share one (call, word) pair unless its n consecutive
+//              elements straddle a multiple of `threads` -- those few ants take every step through the fallback.
+template <bool FUSE_COST, int MAXW, bool GEN = false>
 static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_kernel(const __grid_constant__ ListParams p) {
     constexpr int kKnnFixed = kKnnWarpBytes * MAXW;
     DACO_DYN_SMEM128(smem);
@@ -480,14 +566,22 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     const uint32_t sub_base = (uint32_t)(a + p.ant_base) * (uint32_t)n;
 
     int cur;
-    uint64_t ctr = offset0 >> 2;                                          // Philox counter of the first noise draw
+    uint64_t ctr = offset0 >> 2;                                          // Philox counter of the first noise draw (call 0)
     if (p.start_node >= 0) {
         cur = p.start_node;
     } else {
         cur = (int)(torch_philox_word(p.seed, offset0, (uint64_t)(a + p.ant_base), p.g_start) % (uint32_t)n);
-        ctr += 1;
+        ctr += p.start_increment >> 2;
     }
-    constexpr uint32_t ctr_step = 1;   // single-launch draw geometry (host-checked): every draw advances the offset by 4
+    // every draw advances the generator offset by step_increment (4 for the single-launch geometry, host-checked)
+    const uint32_t ctr_step = GEN ? (p.step_increment >> 2) : 1u;
+    uint32_t q0 = 0u, r0 = sub_base;                                      // element li = q0 * threads + r0 + j
+    bool slow = false;
+    if (GEN) {
+        q0 = sub_base / p.g_noise.threads;
+        r0 = sub_base - q0 * p.g_noise.threads;
+        slow = r0 + (uint32_t)n > p.g_noise.threads;                      // this ant's row straddles two Philox blocks
+    }
     for (int k = lane; k < 64; k += 32) {          // alive bytes: 0xff = unvisited, 0 = visited or column >= n
         const int j0 = 4 * k;
         uint32_t v = 0u;
@@ -509,39 +603,29 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     // tour: such a warp (one in ~2^32/n) takes every step through the fallback, which gets the carried high word.
     uint32_t slot = wbase + 384u + 2u;
     const uint32_t slot_end = wbase + 384u + 2u * (uint32_t)n;
-    const uint32_t ctr_lo0 = (uint32_t)ctr, ctr_hi0 = (uint32_t)(ctr >> 32);
-    const bool wraps = ctr_lo0 > 0xffffffffu - (uint32_t)n;
+    const uint64_t ctr_fast = ctr + (q0 >> 2);                            // fast loop: counter of this ant's own call
+    const uint32_t ctr_lo0 = (uint32_t)ctr_fast, ctr_hi0 = (uint32_t)(ctr_fast >> 32);
+    slow = slow || ctr_lo0 > 0xffffffffu - ((uint32_t)n * ctr_step + 8u);
     uint32_t ctr_lo = ctr_lo0;
 #pragma unroll 1
     while (slot < slot_end) {
-        if (!wraps) {
-#pragma unroll 1
-            for (; slot < slot_end; slot += 2u, ++ctr_lo) {
-                const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
-                const uint32_t alive = lds_s8(wbase + j);     // sign-extended: all ones while column j is unvisited
-                const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
-                const float x = __uint_as_float(__float_as_uint(lds_f32(P_addr + ((uint32_t)cur * (uint32_t)n + j) * 4u)) & alive);
-                const float A = __fmul_rn(x, noise_rcp(ctr_lo, ctr_hi0, sub_base + j, K));
-                const uint32_t mybits = __float_as_uint(A);
-                const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
-                const float top = __uint_as_float(topbits);
-                // lanes within 2^-18 (relative) of the top score, the top lane included: the step is decided here
-                // only when that is exactly one lane and no unlisted column can beat it
-                const uint32_t close = __ballot_sync(DACO_FULL, A >= __fmul_rn(top, 1.0f - 3.814697265625e-06f));
-                if (!(__popc(close) == 1 && T < top)) break;
-                const uint32_t jstar = __shfl_sync(DACO_FULL, j, 31 - __clz(close));
-                // Every lane stores the same two values to the same addresses: one wavefront, no predicate to
-                // maintain, and each lane later reads what it wrote itself, so no warp-level fence between steps.
-                DACO_STS_U8(wbase + jstar, 0u);
-                sts_u16(slot, jstar);
-                cur = (int)jstar;
-            }
+        if (!slow) {
+            if (!GEN || (q0 & 3u) == 0u)
+                knn_fast_steps<0>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K);
+            else if ((q0 & 3u) == 1u)
+                knn_fast_steps<1>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K);
+            else if ((q0 & 3u) == 2u)
+                knn_fast_steps<2>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K);
+            else
+                knn_fast_steps<3>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K);
         }
         if (slot < slot_end) {
-            cur = (int)knn_dense_step(p, P_addr + (uint32_t)cur * (uint32_t)n * 4u, wbase, slot, (uint32_t)n, (uint32_t)p.seed,
-                                      (uint32_t)(p.seed >> 32), ctr_lo, ctr_hi0 + (ctr_lo < ctr_lo0 ? 1u : 0u), sub_base);
+            // counter of call 0 of this step's draw (the fallback derives call / word per column itself)
+            const uint64_t c = ctr + (uint64_t)((slot - (wbase + 384u + 2u)) >> 1) * ctr_step;
+            cur = (int)knn_dense_step<GEN>(p, P_addr + (uint32_t)cur * (uint32_t)n * 4u, wbase, slot, (uint32_t)n, (uint32_t)c,
+                                           (uint32_t)(c >> 32), q0, r0);
             slot += 2u;
-            ++ctr_lo;
+            ctr_lo += ctr_step;
         }
     }
     __syncwarp();

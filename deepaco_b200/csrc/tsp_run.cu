@@ -11,6 +11,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace deepaco {
 
 int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants, int n_colonies,
@@ -25,6 +27,12 @@ int tsp_sample_fused(const float* product, int n, int n_ants, int n_colonies, in
 __global__ void hadamard2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         o[i] = __fmul_rn(a[i], b[i]);
+}
+
+int hadamard_launch(const float* a, const float* b, float* o, size_t n, cudaStream_t st) {
+    hadamard2_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(a, b, o, n);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
 }
 
 // one CTA per colony: iteration best -> running best, MMAS bookkeeping

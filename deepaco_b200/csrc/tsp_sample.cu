@@ -24,6 +24,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace deepaco {
 
 struct TspSampleParams {
@@ -44,6 +46,8 @@ struct TspSampleParams {
     DrawGeom g_noise, g_start;
     uint32_t start_increment, step_increment;
     int ant_base;
+    uint16_t* peer_tours[8];   // fused exchange (ant sharding): [B][A_total][n] tour buffer of each of the n_peers GPUs
+    int n_peers, A_total;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +177,32 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
         uint16_t* out = p.tours + ((size_t)b * p.A + a0) * n;
         for (int i = tid; i < n * wvalid; i += nthreads) out[i] = tour_all[i];
     }
+    for (int r = 0; r < p.n_peers; ++r) {
+        uint16_t* out = p.peer_tours[r] + ((size_t)b * p.A_total + p.ant_base + a0) * n;
+        for (int i = tid; i < n * wvalid; i += nthreads) out[i] = tour_all[i];
+    }
+}
+
+// Warps per CTA for the kNN kernel.  A tour is a chain of n-1 dependent steps of ~900 cycles each; an SM sustains about one
+// warp-step per 45 cycles once enough warps are resident (issue bound, profiles/).  Estimated time = waves x
+// max(step latency, resident warps x issue cost); ties go to the larger CTA (the per-CTA staging is shared by more ants).
+// Returns 0 when no size fits shared memory.
+static int knn_pick_warps(int n, int n_ants, int n_colonies, int sm_count, size_t cap) {
+    int best_w = 0;
+    double best_t = 0.0;
+    for (int w = 4; w <= 32; w *= 2) {
+        const size_t sm = knn_kernel_smem(n, w);
+        if (sm > cap) continue;
+        long cps = (long)(cap / sm);                       // CTAs per SM: shared memory, then registers (64 / thread -> 32 warps)
+        cps = std::max<long>(std::min<long>(cps, 32 / w), 1);
+        const long ctas = (long)((n_ants + w - 1) / w) * n_colonies;
+        const long slots = (long)sm_count * cps;
+        const long waves = (ctas + slots - 1) / slots;
+        const long resident = std::min<long>(cps, (ctas + sm_count - 1) / sm_count) * w;
+        const double t = (double)waves * std::max(900.0, 45.0 * (double)resident);
+        if (best_w == 0 || t <= best_t) { best_w = w; best_t = t; }
+    }
+    return best_w;
 }
 
 template <typename KFn, typename P>
@@ -190,9 +220,6 @@ __global__ void hadamard_kernel(const float* __restrict__ a, const float* __rest
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         o[i] = __fmul_rn(a[i], b[i]);
 }
-
-static float* g_prod_ws = nullptr;
-static size_t g_prod_ws_bytes = 0;
 
 }  // namespace deepaco
 
@@ -222,6 +249,7 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
     DACO_CHECK_ARG(ant_base >= 0 && n_ants_total >= ant_base + n_ants, "deepaco_tsp_sample: ant shard [%d, %d) outside the colony's %d ants",
                    ant_base, ant_base + n_ants, n_ants_total);
     cudaStream_t st = (cudaStream_t)stream;
+    StreamScratch prod_ws;   // product matrix for colonies too large for shared memory; freed (stream-ordered) on return
 
     TspSampleParams p{};
     p.ph = pheromone; p.heu = heuristic;
@@ -257,7 +285,9 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
     auto list_smem = [&](int w) { return list_kernel_smem(n, n, w, false); };
     const size_t cap = (size_t)di->max_smem_optin - 1024;
     const bool force_dense = getenv("DEEPACO_TSP_DENSE") != nullptr;
-    if (!force_dense && dn.single && (uint64_t)n_ants_total * n < (1ull << 32) && n <= 256 && list_smem(W) <= cap) {
+    const bool knn_ok = knn && !noise && !log_probs && !paths && !start && (tours || n_peers) && n > 32 && n <= 256 &&
+                        (uint64_t)n_ants_total * n < (1ull << 32) && ds.single && !getenv("DEEPACO_TSP_NO_KNN");
+    if (!force_dense && (dn.single || knn_ok) && (uint64_t)n_ants_total * n < (1ull << 32) && n <= 256 && (list_smem(W) <= cap || knn_ok)) {
         // keep >= 32 resident warps per SM when shared memory allows only few CTAs
         if (total_ants > (long)di->sm_count * 4)
             while (W < 16 && (cap / list_smem(W)) * W < 32 && list_smem(W * 2) <= cap) W *= 2;
@@ -272,18 +302,16 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         q.noise = noise; q.start = start; q.paths = paths; q.logp = log_probs; q.tours = tours;
         q.lbw = p.lbw; q.vec = p.vec; q.g_noise = p.g_noise; q.g_start = p.g_start;
         q.start_increment = p.start_increment; q.step_increment = p.step_increment;
-        if (knn && !noise && !log_probs && !paths && !start && (tours || n_peers) && n > 32 && n <= 256 && dn.increment == 4 &&
-            ds.increment == 4 && !getenv("DEEPACO_TSP_NO_KNN")) {
+        if (knn_ok) {
             // sparse product: one candidate per lane (kNN kernel)
             // 4 warps while the job is tiny, 16 when many CTAs queue per SM (the per-CTA staging is shared by more ants)
-            int Wk = total_ants <= (long)di->sm_count * 4 ? 4 : (total_ants >= (long)di->sm_count * 128 && n_ants % 16 == 0 ? 16 : 8);
+            int Wk = knn_pick_warps(n, n_ants, n_colonies, di->sm_count, cap);
             if (const char* e = getenv("DEEPACO_TSP_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= 32) Wk = w; }
-            if (knn_kernel_smem(n, Wk) <= cap) {
-                if (total_ants > (long)di->sm_count * 4)
-                    while (Wk < 32 && (cap / knn_kernel_smem(n, Wk)) * Wk < 32 && knn_kernel_smem(n, Wk * 2) <= cap) Wk *= 2;   // n ~ 200: one 32-warp CTA per SM
+            if (Wk > 0 && knn_kernel_smem(n, Wk) <= cap) {
                 q.knn = knn;
                 // small jobs are launch-latency bound: fold cost + neighbour table into the construction kernel's epilogue
-                const bool fuse = fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants &&
+                const bool gen = !dn.single;   // more elements than torch's draw launch has threads: general Philox geometry
+                const bool fuse = !gen && fuse_dist && fuse_costs && fuse_nbr && ant_base == 0 && n_ants_total == n_ants &&
                                   (getenv("DEEPACO_TSP_FUSE_COST") || total_ants <= (long)di->sm_count * 16);
                 if (fuse) {
                     q.dist = fuse_dist; q.costs = fuse_costs; q.nbr = fuse_nbr;
@@ -291,20 +319,22 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
                 }
                 dim3 grid((n_ants + Wk - 1) / Wk, n_colonies);
                 const size_t ksm = knn_kernel_smem(n, Wk);
-#define DACO_KNN(F, M)                                                                                                          \
+#define DACO_KNN(F, M, G)                                                                                                       \
     do {                                                                                                                        \
-        DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));     \
-        DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel<F, M>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel<F, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));  \
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(aco_knn_kernel<F, M, G>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
                                              cudaSharedmemCarveoutMaxShared));                                                  \
-        aco_knn_kernel<F, M><<<grid, Wk * 32, ksm, st>>>(q);                                                                    \
+        aco_knn_kernel<F, M, G><<<grid, Wk * 32, ksm, st>>>(q);                                                                 \
     } while (0)
-                if (fuse) { if (Wk <= 8) DACO_KNN(true, 8); else if (Wk <= 16) DACO_KNN(true, 16); else DACO_KNN(true, 32); }
-                else { if (Wk <= 8) DACO_KNN(false, 8); else if (Wk <= 16) DACO_KNN(false, 16); else DACO_KNN(false, 32); }
+                if (gen) { if (Wk <= 8) DACO_KNN(false, 8, true); else if (Wk <= 16) DACO_KNN(false, 16, true); else DACO_KNN(false, 32, true); }
+                else if (fuse) { if (Wk <= 8) DACO_KNN(true, 8, false); else if (Wk <= 16) DACO_KNN(true, 16, false); else DACO_KNN(true, 32, false); }
+                else { if (Wk <= 8) DACO_KNN(false, 8, false); else if (Wk <= 16) DACO_KNN(false, 16, false); else DACO_KNN(false, 32, false); }
 #undef DACO_KNN
                 DACO_CHECK_LAUNCH();
                 return DEEPACO_OK;
             }
         }
+        if (dn.single && list_smem(W) <= cap) {
         const int epl = (n - 1 + 31) / 32;
         const size_t sm = list_smem(W);
 #define DACO_LIST(E)                                                                                        \
@@ -321,23 +351,19 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
         if (epl <= 4) DACO_LIST(4);
         DACO_LIST(8);
 #undef DACO_LIST
+        }
     }
 
     // ---- list kernel with the product in global memory (n too large for shared memory)
     if (!force_dense && dn.single && (uint64_t)n_ants_total * n < (1ull << 32) && n - 1 <= 32 * 32) {
         const float* prod = pheromone;
         if (heuristic) {   // product once per call into a scratch matrix, rows then come from L2
-            const size_t need = (size_t)n_colonies * n * n * sizeof(float);
-            if (need > g_prod_ws_bytes) {
-                if (g_prod_ws) cudaFree(g_prod_ws);
-                g_prod_ws = nullptr; g_prod_ws_bytes = 0;
-                DACO_CHECK_CUDA(cudaMalloc(&g_prod_ws, need));
-                g_prod_ws_bytes = need;
-            }
             const size_t cnt = (size_t)n_colonies * n * n;
-            hadamard_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, g_prod_ws, cnt);
+            DACO_CHECK_CUDA(prod_ws.alloc(cnt * sizeof(float), st));   // stream-ordered: private to this call
+            float* ws = static_cast<float*>(prod_ws.ptr);
+            hadamard_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, ws, cnt);
             DACO_CHECK_LAUNCH();
-            prod = g_prod_ws;
+            prod = ws;
         }
         ListParams q{};
         q.ph = prod; q.heu = nullptr; q.n = n; q.A = n_ants; q.B = n_colonies; q.rows = n;
@@ -369,6 +395,8 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
     }
 
     // ---- dense exact kernel
+    p.n_peers = n_peers; p.A_total = n_ants_total;
+    for (int r = 0; r < n_peers && r < 8; ++r) p.peer_tours[r] = reinterpret_cast<uint16_t*>(peer_tours[r]);
     int epl_needed = vec ? 4 * ((n + 127) / 128) : (n + bw - 1) / bw;
     int epl = vec ? 8 : 1;
     while (epl < epl_needed) epl *= 2;
@@ -378,17 +406,12 @@ static int tsp_sample_impl(const float* pheromone, const float* heuristic, int n
     if (!smemp) {
         smem = (size_t)W * n * 2;
         if (heuristic) {   // product once per call into a scratch matrix, rows then come from L2
-            const size_t need = (size_t)n_colonies * n * n * sizeof(float);
-            if (need > g_prod_ws_bytes) {
-                if (g_prod_ws) cudaFree(g_prod_ws);
-                g_prod_ws = nullptr; g_prod_ws_bytes = 0;
-                DACO_CHECK_CUDA(cudaMalloc(&g_prod_ws, need));
-                g_prod_ws_bytes = need;
-            }
             const size_t cnt = (size_t)n_colonies * n * n;
-            hadamard_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, g_prod_ws, cnt);
+            DACO_CHECK_CUDA(prod_ws.alloc(cnt * sizeof(float), st));   // stream-ordered: private to this call
+            float* ws = static_cast<float*>(prod_ws.ptr);
+            hadamard_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(pheromone, heuristic, ws, cnt);
             DACO_CHECK_LAUNCH();
-            p.ph = g_prod_ws; p.heu = nullptr;
+            p.ph = ws; p.heu = nullptr;
         }
     }
 
@@ -435,6 +458,14 @@ int tsp_sample_fused(const float* product, int n, int n_ants, int n_colonies, in
     return tsp_sample_impl(product, nullptr, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr, nullptr,
                            nullptr, nullptr, tours, knn, 0, n_ants, st, dist, costs, nbr, fused);
 }
+// internal: ant-sharded sampling from a ready product matrix with the fused peer store (deepaco_tsp_run_shard)
+int tsp_sample_peers(const float* product, int n, int n_ants_local, int n_colonies, int start_node, int double_norm, uint64_t seed,
+                     uint64_t offset, const uint64_t* offsets, const uint8_t* knn, int ant_base, int n_ants_total,
+                     const uint64_t* peer_tours_host, int n_peers, cudaStream_t st) {
+    return tsp_sample_impl(product, nullptr, n, n_ants_local, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr,
+                           nullptr, nullptr, nullptr, nullptr, knn, ant_base, n_ants_total, st, nullptr, nullptr, nullptr, nullptr,
+                           peer_tours_host, n_peers);
+}
 }  // namespace deepaco
 
 // Ant-sharded construction with the exchange fused into the kernel: each finished tour is written by the building
@@ -446,7 +477,6 @@ extern "C" int deepaco_tsp_sample_shard_p2p(const float* pheromone, const float*
                                             const uint64_t* offsets, const uint8_t* knn, int ant_base, int n_ants_total,
                                             const uint64_t* peer_tours_host, int n_peers, void* stream) {
     DACO_CHECK_ARG(peer_tours_host && n_peers >= 1 && n_peers <= 8, "deepaco_tsp_sample_shard_p2p: need 1..8 peer buffers");
-    DACO_CHECK_ARG(n <= 256, "deepaco_tsp_sample_shard_p2p: n <= 256 (shared-memory kernels only)");
     return tsp_sample_impl(pheromone, heuristic, n, n_ants, n_colonies, start_node, double_norm, seed, offset, offsets, nullptr,
                            nullptr, nullptr, nullptr, nullptr, knn, ant_base, n_ants_total, stream, nullptr, nullptr, nullptr,
                            nullptr, peer_tours_host, n_peers);

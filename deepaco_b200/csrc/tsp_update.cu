@@ -34,9 +34,11 @@ extern "C" int deepaco_tsp_cost(const float* distances, const int64_t* paths, co
 static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants,
                              int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
                              const float* scale, const float* heuristic, float* product, cudaStream_t st) {
-    const int W = 4;
+    int W = 4;   // rows (warps) per CTA; fewer when a row's 2 * n_ants deposit events need more shared memory
     const size_t per_warp = (((size_t)2 * n_ants * 4 + (size_t)(2 * n + 1) * 4) + 15) & ~(size_t)15;
-    const size_t smem = per_warp * W + (((size_t)n_ants * 4 + 15) & ~(size_t)15);
+    const size_t inv_bytes = ((size_t)n_ants * 4 + 15) & ~(size_t)15;
+    while (W > 1 && per_warp * W + inv_bytes > 200 * 1024) W >>= 1;
+    const size_t smem = per_warp * W + inv_bytes;
     DACO_CHECK_ARG(smem <= 200 * 1024, "deepaco_tsp_update: n_ants=%d / n=%d too large for one pass", n_ants, n);
     DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + W - 1) / W, n_colonies);

@@ -12,8 +12,11 @@ Two independent ways to shard:
   it every later tour -- is bit-identical to the single-GPU run whatever the world size.  (An all-reduce of
   pheromone deltas would need less replicated work but changes the floating-point summation order.)
 
-The compute backend is injectable so that the protocol can be exercised with `gloo` on CPU in the test-suite;
-the product backend is the CUDA engine.
+`DeviceShardedColony` is the product path for ant sharding: all T iterations are enqueued by ONE C call per rank
+(`deepaco_tsp_run_shard`): the sampling kernel stores finished tours into every rank's peer-mapped buffer, a one-CTA
+flag barrier replaces the collective, and there is no host sync and no Python between iterations.
+`AntShardedColony` is the same protocol driven from Python with an injectable compute backend, so that it can be
+exercised with `gloo` on CPU in the test-suite (and with NCCL all-gathers where peer mapping is unavailable).
 """
 from __future__ import annotations
 
@@ -50,6 +53,29 @@ def gather_colony_results(lowest_cost: torch.Tensor, shortest_path: torch.Tensor
     dist.all_gather(sps, sp, group=group)
     return (torch.cat([lcs[r][:counts[r]] for r in range(world)]),
             torch.cat([sps[r][:counts[r]] for r in range(world)]))
+
+
+def gather_colony_results_packed(lowest_cost: torch.Tensor, shortest_path: torch.Tensor, counts, group=None):
+    """Same result as `gather_colony_results` with ONE collective: best cost (fp32 bits) and best tour (int64) of every
+    colony travel in one int64 [count, 1 + n] block per rank (`all_gather_into_tensor`; ragged shards are padded)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n = shortest_path.shape[-1]
+    mx = max(counts)
+    block = torch.zeros((mx, n + 1), dtype=torch.int64, device=shortest_path.device)
+    b = lowest_cost.shape[0]
+    block[:b, 0] = lowest_cost.contiguous().view(torch.int32).to(torch.int64)
+    block[:b, 1:] = shortest_path
+    if world == 1:
+        allb = block[None]
+    else:
+        allb = torch.empty((world * mx, n + 1), dtype=torch.int64, device=block.device)   # rank-major concatenation
+        dist.all_gather_into_tensor(allb, block, group=group)
+        allb = allb.view(world, mx, n + 1)
+    if all(c == mx for c in counts):
+        flat = allb.reshape(world * mx, n + 1)
+    else:
+        flat = torch.cat([allb[r, :counts[r]] for r in range(world)])
+    return flat[:, 0].to(torch.int32).view(torch.float32), flat[:, 1:]
 
 
 class CudaTspBackend:
@@ -152,3 +178,90 @@ class AntShardedColony:
         for t in range(n_iterations):
             self.iterate(seed, offset + t * inc)
         return self.lowest_cost
+
+
+# ---- device-side ant-sharded run (deepaco_tsp_run_shard) ------------------------------------------------------------
+TOUR_BUFFERS = 2          # double buffered by iteration parity (see csrc/tsp_shard.cu)
+FLAG_BYTES = 128          # uint32 [8] flag words, padded to a cache line
+
+
+class PeerMemory:
+    """Tour buffers + flag words of every rank as addresses valid on THIS rank's device.
+    tour_ptrs[r][k]: rank r's tour buffer k (uint16 [B, A, n]); flag_ptrs[r]: rank r's flag words (uint32 [8])."""
+
+    def __init__(self, rank, world, tour_ptrs, flag_ptrs, keep_alive, barrier=None):
+        self.rank, self.world = int(rank), int(world)
+        self.tour_ptrs, self.flag_ptrs = tour_ptrs, flag_ptrs
+        self._keep, self._barrier = keep_alive, barrier
+
+    def host_barrier(self):
+        if self._barrier is not None:
+            self._barrier()
+
+
+def _peer_layout(B, A, n):
+    tour_bytes = (B * A * n * 2 + 255) // 256 * 256
+    return tour_bytes, TOUR_BUFFERS * tour_bytes + FLAG_BYTES
+
+
+def symmetric_peer_memory(B, A, n, device, group=None) -> PeerMemory:
+    """One symmetric-memory allocation per rank (`torch.distributed._symmetric_memory`): [tours 0 | tours 1 | flags],
+    peer-mapped on all ranks of `group` over NVLink / NVSwitch."""
+    import torch.distributed._symmetric_memory as symm_mem
+    group = group if group is not None else dist.group.WORLD
+    tour_bytes, total = _peer_layout(B, A, n)
+    buf = symm_mem.empty((total,), dtype=torch.uint8, device=device)
+    buf.zero_()
+    handle = symm_mem.rendezvous(buf, group)
+    torch.cuda.synchronize(device)
+    handle.barrier(channel=0)               # every rank's flag words are zero before anyone signals
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    base = [int(p) for p in handle.buffer_ptrs]
+    return PeerMemory(rank, world, [[base[r] + k * tour_bytes for k in range(TOUR_BUFFERS)] for r in range(world)],
+                      [base[r] + TOUR_BUFFERS * tour_bytes for r in range(world)], (buf, handle),
+                      barrier=lambda: handle.barrier(channel=0))
+
+
+def local_peer_memory(B, A, n, device, world):
+    """`world` virtual ranks on ONE device (plain device pointers are their own peer mapping): exercises the complete
+    device-side protocol -- fused peer stores, flag barrier, double buffering -- on a single GPU, each virtual rank on its
+    own stream.  -> list of PeerMemory, one per virtual rank."""
+    tour_bytes, total = _peer_layout(B, A, n)
+    bufs = [torch.zeros((total,), dtype=torch.uint8, device=device) for _ in range(world)]
+    base = [b.data_ptr() for b in bufs]
+    tour_ptrs = [[base[r] + k * tour_bytes for k in range(TOUR_BUFFERS)] for r in range(world)]
+    flag_ptrs = [base[r] + TOUR_BUFFERS * tour_bytes for r in range(world)]
+    return [PeerMemory(r, world, tour_ptrs, flag_ptrs, bufs) for r in range(world)]
+
+
+def shard_tables(peer: PeerMemory):
+    """Flattened host tables of deepaco_shard_args: (peer_tours_host [world * 2], peer_flags_host [world])."""
+    return [p for r in range(peer.world) for p in peer.tour_ptrs[r]], list(peer.flag_ptrs)
+
+
+class DeviceShardedColony:
+    """TSP colonies whose ants are split over the ranks of `peer` (deepaco_tsp_run_shard).  State (pheromone,
+    lowest_cost, shortest_path) lives in `runner` (an `_engine.TspRunner` with the FULL ant count) and ends up identical
+    on every rank -- and identical to the single-GPU `TspRunner.run`."""
+
+    def __init__(self, runner, peer: PeerMemory, timeout_ms=2000):
+        self.runner, self.peer = runner, peer
+        self.a0, self.count = shard_range(runner.n_ants, peer.world, peer.rank)
+        self.epoch = 0
+        self.timeout_ms = int(timeout_ms)
+        self.status = torch.zeros(1, dtype=torch.int32, device=runner.dev)
+        self.collectives = 0                 # NCCL collectives issued on the data path: none
+
+    def run(self, n_iterations, seed, offset=0, offsets=None, sample_events=None):
+        """Enqueue n_iterations on the current stream (no host sync).  Call `check()` after synchronising."""
+        self.runner.run_shard(n_iterations, seed, self.peer, self.a0, self.count, self.epoch, self.status, self.timeout_ms,
+                              offset=offset, offsets=offsets, sample_events=sample_events)
+        self.epoch += int(n_iterations)
+        return self.runner.lowest_cost
+
+    def check(self):
+        """Host-side check (synchronises): raises if a peer never arrived at a barrier."""
+        s = int(self.status.item())
+        if s:
+            from ._lib import DeepAcoError
+            raise DeepAcoError(f"ant-sharded run: rank {self.peer.rank} timed out waiting for rank {s - 1}")

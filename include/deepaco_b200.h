@@ -146,6 +146,31 @@ int deepaco_tsp_run_host(const deepaco_tsp_run_args* args, int n_iterations, con
                          const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
                          int64_t* shortest_path_host, int copy_back_pheromone, void* stream);
 
+/* ---- ACO.run with the ANTS of every colony split over the GPUs of one box (no reference counterpart: the reference is
+ * single-device; semantics reproduced: tsp/aco.py:74-92, bit-identical to deepaco_tsp_run on one GPU for any world size).
+ * One process per GPU calls this with the same `args` values (its own device buffers) and its own shard description.
+ * Per iteration: this rank builds ants [ant_base, ant_base + n_ants_local) of args->n_ants and the sampling kernel stores
+ * each finished tour into the tour buffer of EVERY rank over NVLink (peer-mapped addresses); a one-CTA flag barrier
+ * (release / acquire at system scope, no host sync, no NCCL) follows; then every rank replays cost, best tracking and the
+ * ordered deposit on all tours.  args->tours is not used: the tour buffers are the peer-mapped ones below.
+ *   peer_tours_host [world][2]  host array: address (valid on THIS device) of rank r's tour buffer k, uint16
+ *                               [n_colonies][n_ants][n] each; iteration e uses buffer (epoch + e) & 1;
+ *   peer_flags_host [world]     host array: address of rank r's flag words, uint32 [8], zero before the first call;
+ *   epoch                       iterations already run on these flags (0 for the first call, then += n_iterations);
+ *   status                      device int32, zero at entry; non-zero afterwards = a peer did not arrive within
+ *                               timeout_ms (default 2000) and the results are invalid;
+ * With world = 1 the call degenerates to deepaco_tsp_run on the supplied buffer. */
+typedef struct {
+    int rank, world;
+    int ant_base, n_ants_local;
+    const uint64_t* peer_tours_host;
+    const uint64_t* peer_flags_host;
+    uint32_t epoch;
+    uint32_t timeout_ms;
+    int32_t* status;
+} deepaco_shard_args;
+int deepaco_tsp_run_shard(const deepaco_tsp_run_args* args, const deepaco_shard_args* shard, int n_iterations, void* stream);
+
 /* ---- local search (tsp_nls/two_opt.py:6-49, tsp_nls/aco.py:234-258) ---------------------------------
  * In place on compact tours (u16 [B][A][n]); one CTA per tour, bit-exact with the reference's numba code
  * (first strict minimum in (i,j) scan order, fp32 left-to-right delta, threshold -1e-6).

@@ -102,17 +102,30 @@ extern "C" const char* emu_tsp_sample(const float* ph, const float* heu, int n, 
     fill_common(p, ph, heu, n, A, B, seed, offset, noise, lbw, vec, g_threads, g_single, increment);
     p.rows = n; p.start_node = start_node; p.double_norm = double_norm; p.start = start;
     p.paths = paths; p.logp = logp; p.tours = tours;
-    if (kernel == 1) {
-        if (!knn || noise || logp || paths || start || !tours || n <= 32 || n > 256 || !g_single || increment != 4)
+    if (kernel == 1 || kernel == 2) {   // 2 = the general-geometry instantiation (any g_threads / increment)
+        if (!knn || noise || logp || paths || start || !tours || n <= 32 || n > 256 || (kernel == 1 && (!g_single || increment != 4)))
             return "the kNN kernel needs candidate lists, Philox noise, tours out, 32 < n <= 256";
         p.knn = knn;
         const int gx = (A + W - 1) / W;
         const size_t sm = knn_kernel_smem(n, W);
-        if (W <= 8) emu::launch(aco_knn_kernel<false, 8>, p, gx * B, 1, W * 32, sm, gx);
-        else emu::launch(aco_knn_kernel<false, 16>, p, gx * B, 1, W * 32, sm, gx);
+        if (kernel == 2) {
+            if (W <= 8) emu::launch(aco_knn_kernel<false, 8, true>, p, gx * B, 1, W * 32, sm, gx);
+            else emu::launch(aco_knn_kernel<false, 16, true>, p, gx * B, 1, W * 32, sm, gx);
+        } else {
+            if (W <= 8) emu::launch(aco_knn_kernel<false, 8>, p, gx * B, 1, W * 32, sm, gx);
+            else emu::launch(aco_knn_kernel<false, 16>, p, gx * B, 1, W * 32, sm, gx);
+        }
         return nullptr;
     }
     return dispatch_list<false>(p, W);
+}
+
+// Exp(1) variates of a torch `exponential_` draw of `numel` elements at (seed, offset) for an arbitrary launch geometry,
+// element by element through torch_philox_word (the literal layout rule): the independent reference for the
+// general-geometry kNN kernel.
+extern "C" void emu_exponential_general(uint64_t seed, uint64_t offset, int64_t numel, uint32_t g_threads, uint32_t g_single, float* out) {
+    const DrawGeom g{g_threads, g_single};
+    for (int64_t li = 0; li < numel; ++li) out[li] = exp1_from_word(torch_philox_word(seed, offset, (uint64_t)li, g));
 }
 
 extern "C" const char* emu_cvrp_sample(const float* ph, const float* heu, const float* demand, float capacity, int n, int A, int B,

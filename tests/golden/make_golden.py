@@ -43,7 +43,9 @@ def npy(t):
 
 
 def save(name, **arrays):
-    path = os.path.join(HERE, name + ".npz")
+    # converted checkpoints are package data (deepaco_b200/data); everything else is a test fixture
+    where = os.path.join(os.path.dirname(os.path.dirname(HERE)), "deepaco_b200", "data") if name.startswith("weights_") else HERE
+    path = os.path.join(where, name + ".npz")
     np.savez_compressed(path, **{k: npy(v) for k, v in arrays.items()})
     print(f"{name}.npz  {os.path.getsize(path)/1024:.1f} KiB")
 

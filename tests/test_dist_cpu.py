@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from deepaco_b200.dist import AntShardedColony, colony_offsets, gather_colony_results, shard_range
+from deepaco_b200.dist import (AntShardedColony, DeviceShardedColony, PeerMemory, colony_offsets, gather_colony_results,
+                               gather_colony_results_packed, shard_range, shard_tables)
 
 
 def test_shard_range_covers_everything():
@@ -82,6 +83,8 @@ def _worker(rank, world, port, ret):
         sp = torch.arange(s, s + c)[:, None].repeat(1, 4)
         counts = [shard_range(5, world, r)[1] for r in range(world)]
         glc, gsp = gather_colony_results(lc, sp, counts)
+        plc, psp = gather_colony_results_packed(lc + 0.25, sp, counts)      # one collective, same result
+        assert torch.equal(plc, glc + 0.25) and torch.equal(psp, gsp)
         ret[rank] = (col.pheromone.numpy().copy(), float(low), col.shortest_path.numpy().copy(), col.collectives,
                      glc.numpy().copy(), gsp.numpy().copy())
     finally:
@@ -109,3 +112,28 @@ def test_ant_sharding_is_independent_of_world_size():
         assert np.array_equal(glc, np.arange(5, dtype=np.float32))
         assert np.array_equal(gsp[:, 0], np.arange(5))
     assert np.array_equal(two[0][0], two[1][0])
+
+
+class _FakeRunner:
+    """Records what DeviceShardedColony hands to the C entry (host logic only: shard, epoch, tables)."""
+
+    def __init__(self, n_ants):
+        self.n_ants, self.dev, self.calls, self.lowest_cost, self.increment = n_ants, "cpu", [], torch.tensor([1.0]), 400
+
+    def run_shard(self, T, seed, peer, a0, count, epoch, status, timeout_ms, **kw):
+        self.calls.append((T, seed, a0, count, epoch, shard_tables(peer), kw["offset"]))
+
+
+def test_device_sharded_colony_host_logic():
+    world = 3
+    tour_ptrs = [[1000 * r + 10 * k for k in range(2)] for r in range(world)]
+    flag_ptrs = [9000 + r for r in range(world)]
+    for rank in range(world):
+        fr = _FakeRunner(500)
+        col = DeviceShardedColony(fr, PeerMemory(rank, world, tour_ptrs, flag_ptrs, None))
+        assert (col.a0, col.count) == shard_range(500, world, rank)
+        col.run(4, seed=9, offset=0)
+        col.run(3, seed=9, offset=4 * fr.increment)
+        (T0, _, a0, cnt, e0, tabs, off0), (T1, _, _, _, e1, _, off1) = fr.calls
+        assert (T0, e0, off0) == (4, 0, 0) and (T1, e1, off1) == (3, 4, 1600) and col.epoch == 7
+        assert tabs == ([0, 10, 1000, 1010, 2000, 2010], [9000, 9001, 9002]) and (a0, cnt) == (col.a0, col.count)

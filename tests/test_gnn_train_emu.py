@@ -42,7 +42,7 @@ def _net(kind):
         from deepaco_b200.cvrp.net import Net
         weights = "weights_cvrp100"
     net = Net()
-    r = net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "tests", "golden", weights + ".npz")))
+    r = net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "deepaco_b200", "data", weights + ".npz")))
     assert not r.missing_keys and not r.unexpected_keys
     return net.train()
 

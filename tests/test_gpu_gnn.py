@@ -12,7 +12,8 @@ def _load(net_cls, weights):
     import os
     from deepaco_b200.net import load_npz_state_dict
     net = net_cls().to(DEV)
-    path = os.path.join(os.path.dirname(__file__), "golden", weights + ".npz")
+    from deepaco_b200.heuristics import weights_path
+    path = weights_path(weights)
     missing = net.load_state_dict(load_npz_state_dict(path, DEV))
     assert not missing.missing_keys and not missing.unexpected_keys
     return net.eval()

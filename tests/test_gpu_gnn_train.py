@@ -29,7 +29,7 @@ def _net(kind, weights=None):
         from deepaco_b200.cvrp.net import Net
         weights = weights or "weights_cvrp100"
     net = Net().to(DEV)
-    r = net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "tests", "golden", weights + ".npz"), DEV))
+    r = net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "deepaco_b200", "data", weights + ".npz"), DEV))
     assert not r.missing_keys and not r.unexpected_keys
     return net.train()
 

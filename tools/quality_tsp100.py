@@ -24,7 +24,7 @@ EPS = 1e-10
 torch.manual_seed(1234)                                    # tsp/train.ipynb cell 0
 coords = torch.from_numpy(np.load(os.path.join(ROOT, "tests/golden/val_tsp100_coords.npz"))["coords"]).to(dev)
 net = Net().to(dev)
-net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "tests/golden/weights_tsp100.npz"), dev))
+net.load_state_dict(load_npz_state_dict(os.path.join(ROOT, "deepaco_b200/data/weights_tsp100.npz"), dev))
 net.eval()
 tot = np.zeros(3)
 for inst in coords:
