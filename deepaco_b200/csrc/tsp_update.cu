@@ -4,7 +4,11 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 using namespace deepaco;
+
+static const int kRowKernelMinAnts = 2048;   // from here on a row's 2A events are worth a whole CTA
 
 extern "C" int deepaco_tsp_cost(const float* distances, const int64_t* paths, const uint16_t* tours, int n, int n_ants,
                                 int n_colonies, float* costs, uint32_t* neighbours, void* stream) {
@@ -34,6 +38,17 @@ extern "C" int deepaco_tsp_cost(const float* distances, const int64_t* paths, co
 static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants,
                              int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
                              const float* scale, const float* heuristic, float* product, cudaStream_t st) {
+    if (!elitist && n_ants >= kRowKernelMinAnts && n <= 4096 && !getenv("DEEPACO_UPDATE_WARP_ROWS")) {
+        // many ants per colony: one CTA per matrix row, ants in chunks (tsp_update_row_kernel)
+        const int Wr = 8, CH = std::min(n_ants, 8192);
+        const size_t smem = (size_t)n * 4 + (size_t)(n + 1) * 4 + (size_t)Wr * n * 4 + (size_t)2 * CH * 4;
+        DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(n, n_colonies);
+        tsp_update_row_kernel<<<grid, Wr * 32, smem, st>>>(pheromone, neighbours, costs, n, n_ants, CH, decay, min_max, ph_min,
+                                                          ph_max, scale, heuristic, product);
+        DACO_CHECK_LAUNCH();
+        return DEEPACO_OK;
+    }
     int W = 4;   // rows (warps) per CTA; fewer when a row's 2 * n_ants deposit events need more shared memory
     const size_t per_warp = (((size_t)2 * n_ants * 4 + (size_t)(2 * n + 1) * 4) + 15) & ~(size_t)15;
     const size_t inv_bytes = ((size_t)n_ants * 4 + 15) & ~(size_t)15;

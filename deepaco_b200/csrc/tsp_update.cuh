@@ -202,4 +202,113 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
     }
 }
 
+// Same update for colonies with MANY ants (thousands: the ant-sharded path), where a row's 2A deposit events are too
+// many for one warp: one CTA per matrix row.  Ants are processed in chunks of `CH` (ant order, so the per-cell add order
+// is kept across chunks); inside a chunk warp w owns a contiguous ant range and buckets its events by cell into its own
+// sub-bucket -- buckets are laid out cell-major, warp-minor, so reading a cell's bucket front to back is ant order again.
+//   smem: val f32 [n] | cellstart i32 [n+1] | cnt i32 [W][n] (counts, then cursors) | w_sorted f32 [2*CH]
+__global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
+                                                             const float* __restrict__ costs, int n, int A, int CH, float decay,
+                                                             int min_max, float ph_min, const float* __restrict__ ph_max,
+                                                             const float* __restrict__ scale, const float* __restrict__ heu,
+                                                             float* __restrict__ prod) {
+    DACO_DYN_SMEM16(smem);
+    const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5, lane = tid & 31, W = nthreads >> 5;
+    const int u = blockIdx.x, b = blockIdx.y;
+    float* val = reinterpret_cast<float*>(smem);
+    int* cellstart = reinterpret_cast<int*>(val + n);
+    int* cnt = cellstart + n + 1;
+    float* w_sorted = reinterpret_cast<float*>(cnt + (size_t)W * n);
+    const uint32_t* N = nbr + ((size_t)b * n + u) * A;
+    const float* C = costs + (size_t)b * A;
+    float* row = ph + ((size_t)b * n + u) * n;
+    const float sc = scale ? scale[b] : 1.0f;
+    for (int v = tid; v < n; v += nthreads) {
+        float x = row[v];
+        if (scale) x = __fmul_rn(x, sc);   // MMAS rescale on the first improvement (tsp/aco.py:86-87)
+        val[v] = __fmul_rn(x, decay);
+    }
+    int* mycnt = cnt + (size_t)warp * n;
+    for (int a0 = 0; a0 < A; a0 += CH) {
+        const int ca = min(CH, A - a0);
+        const int per = (ca + W - 1) / W;
+        const int wa0 = min(ca, warp * per), wa1 = min(ca, wa0 + per);
+        const int e_lo = 2 * wa0, e_hi = 2 * wa1;          // this warp's events of the chunk: e -> ant a0 + e/2, statement e&1
+        for (int i = tid; i < W * n; i += nthreads) cnt[i] = 0;
+        if (tid == 0) cellstart[0] = 0;
+        __syncthreads();
+        for (int e = e_lo + lane; e < e_hi; e += 32) {
+            const uint32_t nb = N[a0 + (e >> 1)];
+            atomicAdd(&mycnt[(e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16)], 1);
+        }
+        __syncthreads();
+        for (int v = tid; v < n; v += nthreads) {
+            int tot = 0;
+            for (int w = 0; w < W; ++w) tot += cnt[(size_t)w * n + v];
+            cellstart[v + 1] = tot;
+        }
+        __syncthreads();
+        if (warp == 0) {   // inclusive scan of cellstart[1..n]
+            int carry = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int v = base + lane;
+                int x = (v < n) ? cellstart[v + 1] : 0;
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int y = __shfl_up_sync(DACO_FULL, x, off);
+                    if (lane >= off) x += y;
+                }
+                x += carry;
+                if (v < n) cellstart[v + 1] = x;
+                carry = __shfl_sync(DACO_FULL, x, 31);
+            }
+        }
+        __syncthreads();
+        for (int v = tid; v < n; v += nthreads) {   // counts -> cursors (cell-major, warp-minor)
+            int run = cellstart[v];
+            for (int w = 0; w < W; ++w) {
+                const int t = cnt[(size_t)w * n + v];
+                cnt[(size_t)w * n + v] = run;
+                run += t;
+            }
+        }
+        __syncthreads();
+        for (int e0 = e_lo; e0 < e_hi; e0 += 32) {   // stable placement of this warp's events
+            const int e = e0 + lane;
+            int cell = -1 - lane;   // distinct dummies for idle lanes
+            float w = 0.f;
+            if (e < e_hi) {
+                const int a = a0 + (e >> 1);
+                const uint32_t nb = N[a];
+                cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
+                w = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+            }
+            const uint32_t grp = __match_any_sync(DACO_FULL, cell);
+            const int rank = __popc(grp & ((1u << lane) - 1u));
+            if (e < e_hi) w_sorted[mycnt[cell] + rank] = w;
+            __syncwarp();
+            if (e < e_hi && rank == 0) mycnt[cell] += __popc(grp);
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int v = tid; v < n; v += nthreads) {   // this cell's deposits of the chunk, in ant order
+            float x = val[v];
+            for (int i = cellstart[v]; i < cellstart[v + 1]; ++i) x = __fadd_rn(x, w_sorted[i]);
+            val[v] = x;
+        }
+        __syncthreads();
+    }
+    const float hi = min_max ? ph_max[b] : 0.f;
+    for (int v = tid; v < n; v += nthreads) {
+        float x = val[v];
+        if (min_max) {
+            // ph[(ph > 1e-9) * ph < min] = min ; ph[ph > max] = max   (tsp/aco.py:117-118)
+            const float gate = __fmul_rn(x > 1e-9f ? 1.0f : 0.0f, x);
+            if (gate < ph_min) x = ph_min;
+            if (x > hi) x = hi;
+        }
+        row[v] = x;
+        if (prod) prod[((size_t)b * n + u) * n + v] = __fmul_rn(x, heu[((size_t)b * n + u) * n + v]);
+    }
+}
+
 }  // namespace deepaco

@@ -204,6 +204,15 @@ def _peer_layout(B, A, n):
     return tour_bytes, TOUR_BUFFERS * tour_bytes + FLAG_BYTES
 
 
+def _init_peer_block(buf, B, A, n, tour_bytes):
+    """Flag words zero; tour buffers hold identity tours, so that a rank whose peer never arrives (barrier time-out,
+    reported through `status`) still replays valid permutations instead of indexing with garbage."""
+    buf.zero_()
+    ident = torch.arange(n, dtype=torch.int32, device=buf.device).to(torch.uint16).view(torch.uint8).repeat(B * A)
+    for k in range(TOUR_BUFFERS):
+        buf[k * tour_bytes:k * tour_bytes + ident.numel()] = ident
+
+
 def symmetric_peer_memory(B, A, n, device, group=None) -> PeerMemory:
     """One symmetric-memory allocation per rank (`torch.distributed._symmetric_memory`): [tours 0 | tours 1 | flags],
     peer-mapped on all ranks of `group` over NVLink / NVSwitch."""
@@ -211,7 +220,7 @@ def symmetric_peer_memory(B, A, n, device, group=None) -> PeerMemory:
     group = group if group is not None else dist.group.WORLD
     tour_bytes, total = _peer_layout(B, A, n)
     buf = symm_mem.empty((total,), dtype=torch.uint8, device=device)
-    buf.zero_()
+    _init_peer_block(buf, B, A, n, tour_bytes)
     handle = symm_mem.rendezvous(buf, group)
     torch.cuda.synchronize(device)
     handle.barrier(channel=0)               # every rank's flag words are zero before anyone signals
@@ -227,7 +236,9 @@ def local_peer_memory(B, A, n, device, world):
     device-side protocol -- fused peer stores, flag barrier, double buffering -- on a single GPU, each virtual rank on its
     own stream.  -> list of PeerMemory, one per virtual rank."""
     tour_bytes, total = _peer_layout(B, A, n)
-    bufs = [torch.zeros((total,), dtype=torch.uint8, device=device) for _ in range(world)]
+    bufs = [torch.empty((total,), dtype=torch.uint8, device=device) for _ in range(world)]
+    for b in bufs:
+        _init_peer_block(b, B, A, n, tour_bytes)
     base = [b.data_ptr() for b in bufs]
     tour_ptrs = [[base[r] + k * tour_bytes for k in range(TOUR_BUFFERS)] for r in range(world)]
     flag_ptrs = [base[r] + TOUR_BUFFERS * tour_bytes for r in range(world)]

@@ -61,6 +61,22 @@ extern "C" const char* emu_tsp_update(float* ph, const uint32_t* nbr, const floa
     return nullptr;
 }
 
+// tsp_update_row_kernel (one CTA per row, ants in chunks of CH, W warps): the many-ants form of the same update
+extern "C" const char* emu_tsp_update_rows(float* ph, const uint32_t* nbr, const float* costs, int n, int A, int CH, int W, float decay,
+                                           int min_max, float ph_min, const float* ph_max, const float* scale, const float* heu,
+                                           float* prod) {
+    if (!ph || !nbr || !costs || n < 2 || A < 1 || CH < 1 || W < 1 || W > 8 || (min_max && !ph_max)) return "bad arguments";
+    struct RowArgs {
+        UpdArgs u; int CH;
+    };
+    const RowArgs a{{ph, nbr, costs, n, A, decay, 0, min_max, ph_min, ph_max, scale, heu, prod}, CH};
+    const size_t smem = (size_t)n * 4 + (size_t)(n + 1) * 4 + (size_t)W * n * 4 + (size_t)2 * CH * 4;
+    emu::launch([](const RowArgs& r) { const UpdArgs& q = r.u; tsp_update_row_kernel(q.ph, q.nbr, q.costs, q.n, q.A, r.CH, q.decay, q.min_max,
+                                                                                 q.ph_min, q.ph_max, q.scale, q.heu, q.prod); },
+                a, n, 1, W * 32, smem);
+    return nullptr;
+}
+
 // ---- CVRP (one colony per call) ----
 namespace {
 struct CvrpCostArgs {

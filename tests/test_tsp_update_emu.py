@@ -97,6 +97,34 @@ def test_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, n, A
     assert torch.equal(prod, ph * heu)                                     # fused product for the next construction
 
 
+@pytest.mark.parametrize("kw", [{}, {"min_max": True}, {"min_max": True, "scale": 1.7}])
+@pytest.mark.parametrize("n,A,CH,W", [(20, 8, 8, 2), (61, 130, 48, 8), (40, 300, 64, 3), (100, 257, 8192, 8)])
+def test_row_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, n, A, CH, W, kw):
+    """tsp_update_row_kernel (many ants: one CTA per row, ants in chunks of CH split over W warps): same bits as the
+    reference's sequential per-ant deposit, incl. ragged chunk / warp splits."""
+    emu_u.emu_tsp_update_rows.restype = ctypes.c_char_p
+    emu_u.emu_tsp_update_rows.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, ci, cf, vp, vp, vp, vp]
+    dist, paths = _instance(n, A, 3 * n + A)
+    torch.manual_seed(2)
+    ph0 = (torch.rand(n, n) + 0.2).contiguous()
+    costs = O.tsp_path_costs(dist, paths).contiguous()
+    _, nbr = _costs(emu_u, dist, paths, "tile")
+    min_max, scale = kw.get("min_max", False), kw.get("scale")
+    ph_max = torch.tensor([float(n / costs.min())])
+    ref_in = ph0 * scale if scale else ph0
+    want = O.tsp_update_pheromone(ref_in.clone(), paths, costs, decay=0.9, elitist=False, min_max=min_max, ph_min=0.1,
+                                  ph_max=float(ph_max))
+    ph = ph0.clone()
+    heu = torch.rand(n, n).contiguous()
+    prod = torch.full((n, n), float("nan"))
+    sc = torch.tensor([scale], dtype=torch.float32) if scale else None
+    err = emu_u.emu_tsp_update_rows(_ptr(ph), _ptr(nbr), _ptr(costs), n, A, CH, W, 0.9, int(min_max), 0.1,
+                                    _ptr(ph_max) if min_max else None, _ptr(sc), _ptr(heu), _ptr(prod))
+    assert err is None, err
+    assert torch.equal(ph, want)
+    assert torch.equal(prod, ph * heu)
+
+
 # ---- CVRP: open-path cost, one-directional deposit, repeated (0, 0) pairs count once, 1e-10 floor ------------------
 @pytest.fixture(scope="session")
 def emu_c(emu_u):
