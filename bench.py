@@ -16,7 +16,7 @@ its own B colonies, no data-path collective).  Prints ONE JSON line on rank 0.
              the reference's PyTorch-CPU path (oracle port, op for op) on the host cores of this box
   configs    the other BASELINE.json configs (tools/bench_legs.py): c2_dense, c3, c4 on rank 0's GPU; c5 = 64 x TSP-200 x
              256 ants split over the N ranks with the result gather inside the timed region (strong scaling)
-  ant_sharded  one TSP-200 colony of 8192 ants with its ants split over the N ranks (deepaco_tsp_run_shard: fused
+  ant_sharded  one TSP-200 colony of 16384 ants with its ants split over the N ranks (deepaco_tsp_run_shard: fused
              NVLink peer stores + flag barrier, no host sync), timed against the same colony on one GPU, bits compared
   reference_cuda  the reference op sequence with device='cuda' on this GPU
 """

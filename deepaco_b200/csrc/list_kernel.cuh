@@ -447,14 +447,14 @@ static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uin
     __syncwarp();
     float bestA = 0.f, second = 0.f;
     uint32_t bestj = 0xffffffffu;
-#pragma unroll 1
-    for (uint32_t base = 0; base < cnt; base += 32) {     // warp-uniform rounds (no divergent remainder loop)
-        const uint32_t i = base + lane;
+    auto score = [&](uint32_t i, uint32_t& j) -> float {
         const bool on = i < cnt;
-        const uint32_t j = on ? lds_u16(ids_addr + 2u * i) : 0u;
+        j = on ? lds_u16(ids_addr + 2u * i) : 0u;
         const float rq = GEN ? noise_rcp_general(ctr_lo, ctr_hi, q0, r0, j, p.g_noise.threads, K) : noise_rcp(ctr_lo, ctr_hi, r0 + j, K);
-        float A = __fmul_rn(lds_f32(row_addr + 4u * j), rq);
-        A = on ? A : 0.f;
+        const float A = __fmul_rn(lds_f32(row_addr + 4u * j), rq);
+        return on ? A : 0.f;
+    };
+    auto keep = [&](float A, uint32_t j) {
         if (A > bestA) {
             second = bestA;
             bestA = A;
@@ -462,6 +462,20 @@ static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uin
         } else if (A > second) {
             second = A;
         }
+    };
+    uint32_t base = 0;
+#pragma unroll 1
+    for (; base + 32u < cnt; base += 64u) {   // two independent Philox chains per lane in flight (the step is latency bound)
+        uint32_t ja, jb;
+        const float Aa = score(base + lane, ja);
+        const float Ab = score(base + 32u + lane, jb);
+        keep(Aa, ja);
+        keep(Ab, jb);
+    }
+    if (base < cnt) {                         // warp-uniform remainder round
+        uint32_t ja;
+        const float Aa = score(base + lane, ja);
+        keep(Aa, ja);
     }
     const uint32_t mybits = __float_as_uint(bestA);
     const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
@@ -481,17 +495,20 @@ static __device__ DACO_NOINLINE uint32_t knn_dense_step(const ListParams& p, uin
 
 // Fast steps of one tour: lane l evaluates column knn[cur][l] only.  Runs until the tour is complete or a step needs
 // the dense / exact treatment (returns with `slot` at that step).  COMP = Philox output word of this ant's elements.
+// COMP = 4: the ant's elements straddle two Philox blocks -- word / call chosen per column at run time (q0, threads).
 template <int COMP>
 __device__ __forceinline__ void knn_fast_steps(uint32_t& slot, uint32_t& ctr_lo, int& cur, const uint32_t slot_end, const uint32_t ctr_step,
                                                const uint32_t ctr_hi, const uint32_t sub0, const uint32_t knn_lane, const uint32_t wbase,
-                                               const uint32_t T_addr, const uint32_t P_addr, const uint32_t n, const PhiloxRoundKeys& K) {
+                                               const uint32_t T_addr, const uint32_t P_addr, const uint32_t n, const PhiloxRoundKeys& K,
+                                               const uint32_t q0 = 0u, const uint32_t threads = 0u) {
 #pragma unroll 1
     for (; slot < slot_end; slot += 2u, ctr_lo += ctr_step) {
         const uint32_t j = lds_u8(knn_lane + (uint32_t)cur * 32u);
         const uint32_t alive = lds_s8(wbase + j);     // sign-extended: all ones while column j is unvisited
         const float T = lds_f32(T_addr + 4u * (uint32_t)cur);
         const float x = __uint_as_float(__float_as_uint(lds_f32(P_addr + ((uint32_t)cur * n + j) * 4u)) & alive);
-        const float A = __fmul_rn(x, noise_rcp_comp<COMP>(ctr_lo, ctr_hi, sub0 + j, K));
+        const float A = __fmul_rn(x, COMP == 4 ? noise_rcp_general(ctr_lo, ctr_hi, q0, sub0, j, threads, K)
+                                               : noise_rcp_comp<(COMP & 3)>(ctr_lo, ctr_hi, sub0 + j, K));
         const uint32_t mybits = __float_as_uint(A);
         const uint32_t topbits = __reduce_max_sync(DACO_FULL, mybits);
         const float top = __uint_as_float(topbits);
@@ -576,11 +593,11 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     // every draw advances the generator offset by step_increment (4 for the single-launch geometry, host-checked)
     const uint32_t ctr_step = GEN ? (p.step_increment >> 2) : 1u;
     uint32_t q0 = 0u, r0 = sub_base;                                      // element li = q0 * threads + r0 + j
-    bool slow = false;
+    bool straddle = false;
     if (GEN) {
         q0 = sub_base / p.g_noise.threads;
         r0 = sub_base - q0 * p.g_noise.threads;
-        slow = r0 + (uint32_t)n > p.g_noise.threads;                      // this ant's row straddles two Philox blocks
+        straddle = r0 + (uint32_t)n > p.g_noise.threads;                  // this ant's row straddles two Philox blocks
     }
     for (int k = lane; k < 64; k += 32) {          // alive bytes: 0xff = unvisited, 0 = visited or column >= n
         const int j0 = 4 * k;
@@ -603,14 +620,18 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
     // tour: such a warp (one in ~2^32/n) takes every step through the fallback, which gets the carried high word.
     uint32_t slot = wbase + 384u + 2u;
     const uint32_t slot_end = wbase + 384u + 2u * (uint32_t)n;
-    const uint64_t ctr_fast = ctr + (q0 >> 2);                            // fast loop: counter of this ant's own call
+    // fast loop: counter of this ant's own call (of call 0 for a straddling ant, which picks call / word per column)
+    const uint64_t ctr_fast = straddle ? ctr : ctr + (q0 >> 2);
     const uint32_t ctr_lo0 = (uint32_t)ctr_fast, ctr_hi0 = (uint32_t)(ctr_fast >> 32);
-    slow = slow || ctr_lo0 > 0xffffffffu - ((uint32_t)n * ctr_step + 8u);
+    const bool slow = ctr_lo0 > 0xffffffffu - ((uint32_t)n * ctr_step + 8u + (q0 >> 2));
     uint32_t ctr_lo = ctr_lo0;
 #pragma unroll 1
     while (slot < slot_end) {
         if (!slow) {
-            if (!GEN || (q0 & 3u) == 0u)
+            if (GEN && straddle)
+                knn_fast_steps<4>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K, q0,
+                                  p.g_noise.threads);
+            else if (!GEN || (q0 & 3u) == 0u)
                 knn_fast_steps<0>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K);
             else if ((q0 & 3u) == 1u)
                 knn_fast_steps<1>(slot, ctr_lo, cur, slot_end, ctr_step, ctr_hi0, r0, knn_lane, wbase, T_addr, P_addr, (uint32_t)n, K);

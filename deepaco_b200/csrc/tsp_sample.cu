@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(512) tsp_sample_dense_kernel(const TspSamplePa
     }
 }
 
-// Warps per CTA for the kNN kernel.  A tour is a chain of n-1 dependent steps of ~900 cycles each; an SM sustains about one
-// warp-step per 45 cycles once enough warps are resident (issue bound, profiles/).  Estimated time = waves x
-// max(step latency, resident warps x issue cost); ties go to the larger CTA (the per-CTA staging is shared by more ants).
+// Warps per CTA for the kNN kernel.  A tour is a chain of n-1 dependent steps; measured (profiles/r02_k1_*): a step takes
+// about 700 + 30 x (resident warps per SM) cycles -- latency of the dependent chain plus issue contention, ~1180 cycles
+// at 16 warps, ~1660 at 32.  Estimated time = waves x that; ties go to the larger CTA (per-CTA staging shared by more ants).
 // Returns 0 when no size fits shared memory.
 static int knn_pick_warps(int n, int n_ants, int n_colonies, int sm_count, size_t cap) {
     int best_w = 0;
@@ -199,7 +199,7 @@ static int knn_pick_warps(int n, int n_ants, int n_colonies, int sm_count, size_
         const long slots = (long)sm_count * cps;
         const long waves = (ctas + slots - 1) / slots;
         const long resident = std::min<long>(cps, (ctas + sm_count - 1) / sm_count) * w;
-        const double t = (double)waves * std::max(900.0, 45.0 * (double)resident);
+        const double t = (double)waves * (700.0 + 30.0 * (double)resident);
         if (best_w == 0 || t <= best_t) { best_w = w; best_t = t; }
     }
     return best_w;

@@ -40,8 +40,8 @@ static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const
                              const float* scale, const float* heuristic, float* product, cudaStream_t st) {
     if (!elitist && n_ants >= kRowKernelMinAnts && n <= 4096 && !getenv("DEEPACO_UPDATE_WARP_ROWS")) {
         // many ants per colony: one CTA per matrix row, ants in chunks (tsp_update_row_kernel)
-        const int Wr = 8, CH = std::min(n_ants, 8192);
-        const size_t smem = (size_t)n * 4 + (size_t)(n + 1) * 4 + (size_t)Wr * n * 4 + (size_t)2 * CH * 4;
+        const int Wr = 8, CH = std::min(n_ants, 4096);
+        const size_t smem = (size_t)n * 4 + (size_t)(n + 1) * 4 + (size_t)Wr * n * 4 + (size_t)4 * CH * 4;
         DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(n, n_colonies);
         tsp_update_row_kernel<<<grid, Wr * 32, smem, st>>>(pheromone, neighbours, costs, n, n_ants, CH, decay, min_max, ph_min,

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
 // many for one warp: one CTA per matrix row.  Ants are processed in chunks of `CH` (ant order, so the per-cell add order
 // is kept across chunks); inside a chunk warp w owns a contiguous ant range and buckets its events by cell into its own
 // sub-bucket -- buckets are laid out cell-major, warp-minor, so reading a cell's bucket front to back is ant order again.
-//   smem: val f32 [n] | cellstart i32 [n+1] | cnt i32 [W][n] (counts, then cursors) | w_sorted f32 [2*CH]
+//   smem: val f32 [n] | cellstart i32 [n+1] | cnt i32 [W][n] (counts, then cursors) | w_sorted f32 [2*CH] |
+//         nb u32 [CH] | inv f32 [CH]  (the chunk's neighbour words and 1 / cost, staged by the whole CTA)
 __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__ ph, const uint32_t* __restrict__ nbr,
                                                              const float* __restrict__ costs, int n, int A, int CH, float decay,
                                                              int min_max, float ph_min, const float* __restrict__ ph_max,
@@ -219,6 +220,8 @@ __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__
     int* cellstart = reinterpret_cast<int*>(val + n);
     int* cnt = cellstart + n + 1;
     float* w_sorted = reinterpret_cast<float*>(cnt + (size_t)W * n);
+    uint32_t* nb_s = reinterpret_cast<uint32_t*>(w_sorted + (size_t)2 * CH);
+    float* inv_s = reinterpret_cast<float*>(nb_s + CH);
     const uint32_t* N = nbr + ((size_t)b * n + u) * A;
     const float* C = costs + (size_t)b * A;
     float* row = ph + ((size_t)b * n + u) * n;
@@ -236,10 +239,21 @@ __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__
         const int e_lo = 2 * wa0, e_hi = 2 * wa1;          // this warp's events of the chunk: e -> ant a0 + e/2, statement e&1
         for (int i = tid; i < W * n; i += nthreads) cnt[i] = 0;
         if (tid == 0) cellstart[0] = 0;
+        for (int i = tid; i < ca; i += nthreads) {   // coalesced, all loads in flight at once
+            nb_s[i] = N[a0 + i];
+            inv_s[i] = __fdiv_rn(1.0f, C[a0 + i]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+        }
         __syncthreads();
-        for (int e = e_lo + lane; e < e_hi; e += 32) {
-            const uint32_t nb = N[a0 + (e >> 1)];
-            atomicAdd(&mycnt[(e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16)], 1);
+        for (int e0 = e_lo; e0 < e_hi; e0 += 32) {   // most ants share a few cells: count per group, not per lane
+            const int e = e0 + lane;
+            int cell = -1 - lane;
+            if (e < e_hi) {
+                const uint32_t nb = nb_s[e >> 1];
+                cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
+            }
+            const uint32_t grp = __match_any_sync(DACO_FULL, cell);
+            if (e < e_hi && (grp & ((1u << lane) - 1u)) == 0u) mycnt[cell] += __popc(grp);
+            __syncwarp();
         }
         __syncthreads();
         for (int v = tid; v < n; v += nthreads) {
@@ -277,10 +291,9 @@ __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__
             int cell = -1 - lane;   // distinct dummies for idle lanes
             float w = 0.f;
             if (e < e_hi) {
-                const int a = a0 + (e >> 1);
-                const uint32_t nb = N[a];
+                const uint32_t nb = nb_s[e >> 1];
                 cell = (e & 1) ? (int)(nb & 0xffffu) : (int)(nb >> 16);
-                w = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+                w = inv_s[e >> 1];
             }
             const uint32_t grp = __match_any_sync(DACO_FULL, cell);
             const int rank = __popc(grp & ((1u << lane) - 1u));
@@ -292,7 +305,27 @@ __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__
         __syncthreads();
         for (int v = tid; v < n; v += nthreads) {   // this cell's deposits of the chunk, in ant order
             float x = val[v];
-            for (int i = cellstart[v]; i < cellstart[v + 1]; ++i) x = __fadd_rn(x, w_sorted[i]);
+            int i = cellstart[v];
+            const int end = cellstart[v + 1];
+            // the add chain is sequential by definition (fp32, ant order); keep the loads of the next eight ahead of it
+            if (i + 8 <= end) {
+                float c[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c[k] = w_sorted[i + k];
+                i += 8;
+                for (; i + 8 <= end; i += 8) {
+                    float nx[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) nx[k] = w_sorted[i + k];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x = __fadd_rn(x, c[k]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) c[k] = nx[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x = __fadd_rn(x, c[k]);
+            }
+            for (; i < end; ++i) x = __fadd_rn(x, w_sorted[i]);
             val[v] = x;
         }
         __syncthreads();

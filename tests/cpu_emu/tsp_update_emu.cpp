@@ -70,7 +70,7 @@ extern "C" const char* emu_tsp_update_rows(float* ph, const uint32_t* nbr, const
         UpdArgs u; int CH;
     };
     const RowArgs a{{ph, nbr, costs, n, A, decay, 0, min_max, ph_min, ph_max, scale, heu, prod}, CH};
-    const size_t smem = (size_t)n * 4 + (size_t)(n + 1) * 4 + (size_t)W * n * 4 + (size_t)2 * CH * 4;
+    const size_t smem = (size_t)n * 4 + (size_t)(n + 1) * 4 + (size_t)W * n * 4 + (size_t)4 * CH * 4;
     emu::launch([](const RowArgs& r) { const UpdArgs& q = r.u; tsp_update_row_kernel(q.ph, q.nbr, q.costs, q.n, q.A, r.CH, q.decay, q.min_max,
                                                                                  q.ph_min, q.ph_max, q.scale, q.heu, q.prod); },
                 a, n, 1, W * 32, smem);

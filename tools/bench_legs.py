@@ -236,8 +236,8 @@ def leg_c5(dev, steps, T=10):
             "mean_best_cost": float(low.mean().item())}
 
 
-def leg_ant_sharded(dev, steps, T=10, n=200, A=8192, k=20):
-    """One colony too big for one GPU's latency budget (TSP-200 x 8192 ants), ants split over the ranks:
+def leg_ant_sharded(dev, steps, T=10, n=200, A=16384, k=20):
+    """One colony with enough ants to fill one GPU several times over (TSP-200 x 16384 ants), ants split over the ranks:
     deepaco_tsp_run_shard (fused peer stores over NVLink + flag barrier, no NCCL on the data path, no host sync), against
     the same colony on ONE GPU (rank 0, deepaco_tsp_run) -- time and bits."""
     rank, world = _world()
