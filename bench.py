@@ -234,7 +234,7 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI entry (pinned matrices in, results out)
     dist_h, heu_h = dist.cpu().pin_memory(), heu.cpu().pin_memory()
-    ph_h = torch.ones_like(dist_h).pin_memory()
+    ph_h = runner.pheromone.cpu().pin_memory()          # continue the colonies where the device-resident steps left them
     low_h = torch.empty(B, dtype=torch.float32).pin_memory()
     sp_h = torch.empty((B, N_NODES), dtype=torch.int64).pin_memory()
     r2 = E.TspRunner(dist, heu, ph0, N_ANTS)
@@ -300,7 +300,9 @@ def main():
                      "kernel_share_of_step": samp_mean / (total_ms / K),
                      "note": "matrices are L2/SMEM resident: a throughput-normalised figure, not DRAM utilisation"},
         "e2e": {"value": e2e_value, "unit": "ant-tours/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "deepaco_tsp_run_host (C ABI, pinned host buffers)", "ms_per_step": float(e2e_ms) / K},
+                "api": "deepaco_tsp_run_host (C ABI): pinned host distances + heuristic + pheromone in, pheromone + best cost + "
+                       "best tour out, every step; chunked upload / compute / download pipeline over four streams",
+                "ms_per_step": float(e2e_ms) / K},
         "single_colony": {"value": N_ANTS / (single_ms * 1e-3), "unit": "ant-tours/s", "ms_per_iteration": single_ms,
                           "note": "one colony of 512 ants, K back-to-back iterations in one deepaco_tsp_run call (rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks,

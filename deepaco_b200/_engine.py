@@ -264,8 +264,11 @@ class TspRunner:
     def run_host(self, n_iterations, seed, distances_h, heuristic_h, pheromone_h, lowest_h, shortest_h, offset=0,
                  offsets=None, copy_back_pheromone=True):
         """deepaco_tsp_run_host: pinned HOST tensors in/out (pheromone_h is updated in place when
-        copy_back_pheromone); synchronous."""
+        copy_back_pheromone; pheromone_h = None: start from ones like ACO.__init__); synchronous."""
         for t, nm in ((distances_h, "distances"), (heuristic_h, "heuristic"), (pheromone_h, "pheromone")):
+            if t is None and nm == "pheromone":
+                copy_back_pheromone = False      # pheromone starts as ACO.__init__ creates it (ones), nothing to upload
+                continue
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.B * self.n * self.n:
                 raise _lib.DeepAcoError(f"run_host: `{nm}` must be a contiguous fp32 host tensor [B, n, n]")
         offs = _offsets(offsets, self.B, self.dev)

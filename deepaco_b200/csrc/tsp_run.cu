@@ -167,43 +167,69 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
     return DEEPACO_OK;
 }
 
-// Host-buffer entry point (what a CPU-side caller of the reference's ACO.run would bind): copies the three
-// matrices of every colony to the device buffers named in `a`, runs, copies the results back, synchronises.
-// Colonies are independent, so the batch is cut into up to four chunks that alternate between the caller's stream
-// and an internal one: the H2D / D2H copies of one chunk overlap the kernels of the other.
+// Host-buffer entry point (what a CPU-side caller of the reference's `ACO(distances, heuristic=...).run(T)` would bind):
+// copies the matrices of every colony to the device buffers named in `a`, runs, copies the results back, synchronises.
+// Colonies are independent, so the batch is cut into chunks and pipelined over four streams:
+//   upload stream    H2D of chunk after chunk, back to back (PCIe never idles, no two uploads compete);
+//   caller's stream + one internal compute stream, alternating: chunk c starts as soon as its upload has landed, and the
+//                    tail of one chunk's launches overlaps the head of the next;
+//   download stream  D2H of a chunk's results while later chunks still compute.
+// The first and last chunks are small (only their upload / download is exposed), the middle ones large.
 struct AuxStream {   // one per device ordinal, created on first use
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
+    cudaEvent_t fork = nullptr, comp_done = nullptr, down_done = nullptr;
+    cudaEvent_t ready[8] = {}, done[8] = {};
 };
 static AuxStream g_aux[64];
+
+__global__ void fill_kernel(float* __restrict__ o, float v, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = v;
+}
 
 extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterations, const float* distances_host,
                                     const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
                                     int64_t* shortest_path_host, int copy_back_pheromone, void* stream) {
-    DACO_CHECK_ARG(a && distances_host && heuristic_host && pheromone_host && lowest_cost_host && shortest_path_host,
+    DACO_CHECK_ARG(a && distances_host && heuristic_host && lowest_cost_host && shortest_path_host,
                    "deepaco_tsp_run_host: NULL argument");
+    DACO_CHECK_ARG(pheromone_host || !copy_back_pheromone, "deepaco_tsp_run_host: copy_back_pheromone needs pheromone_host");
     cudaStream_t st = (cudaStream_t)stream;
     const DeviceInfo* di = device_info();
     if (!di) return DEEPACO_ENODEV;
     AuxStream& aux = g_aux[di->device];
-    if (!aux.stream) {
-        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking));
-        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming));
-        DACO_CHECK_CUDA(cudaEventCreateWithFlags(&aux.join, cudaEventDisableTiming));
+    if (!aux.up) {
+        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&aux.up, cudaStreamNonBlocking));
+        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&aux.comp, cudaStreamNonBlocking));
+        DACO_CHECK_CUDA(cudaStreamCreateWithFlags(&aux.down, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&aux.fork, &aux.comp_done, &aux.down_done}) DACO_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (auto& e : aux.ready) DACO_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : aux.done) DACO_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    cudaStream_t g_aux_stream = aux.stream;
-    cudaEvent_t g_ev_fork = aux.fork, g_ev_join = aux.join;
     const int B = a->n_colonies, n = a->n, A = a->n_ants;
-    int chunks = B >= 16 ? 2 : 1;   // measured: 2 chunks 39.3 M tours/s, 4: 39.1, 8: 37.4, 16: 36.0 (256 colonies)
-    if (const char* e = getenv("DEEPACO_HOST_CHUNKS")) { const int c = atoi(e); if (c >= 1 && c <= B) chunks = c; }
+    // chunk boundaries: 1/8 | 3/8 | 3/8 | 1/8 of a large batch, halves of a medium one
+    int cuts[9] = {0, B, 0, 0, 0, 0, 0, 0, 0};
+    int chunks = 1;
+    if (B >= 64) { chunks = 4; cuts[1] = B / 8; cuts[2] = B / 2; cuts[3] = B - B / 8; cuts[4] = B; }
+    else if (B >= 8) { chunks = 2; cuts[1] = B / 2; cuts[2] = B; }
+    if (const char* e = getenv("DEEPACO_HOST_CHUNKS")) {   // equal chunks, for experiments
+        const int c = atoi(e);
+        if (c >= 1 && c <= 8 && c <= B) { chunks = c; for (int k = 0; k <= c; ++k) cuts[k] = (int)((long)B * k / c); }
+    }
     const size_t mat1 = (size_t)n * n;
-    if (chunks > 1) {   // the internal stream starts after everything already queued on the caller's stream
-        DACO_CHECK_CUDA(cudaEventRecord(g_ev_fork, st));
-        DACO_CHECK_CUDA(cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0));
+    // the internal streams start after everything already queued on the caller's stream (the buffers may be in use)
+    DACO_CHECK_CUDA(cudaEventRecord(aux.fork, st));
+    for (cudaStream_t s : {aux.up, aux.comp, aux.down}) DACO_CHECK_CUDA(cudaStreamWaitEvent(s, aux.fork, 0));
+    for (int c = 0; c < chunks; ++c) {
+        const int b0 = cuts[c], nb = cuts[c + 1] - cuts[c];
+        const size_t bytes = (size_t)nb * mat1 * sizeof(float);
+        DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->distances) + b0 * mat1, distances_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, aux.up));
+        DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(a->heuristic) + b0 * mat1, heuristic_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, aux.up));
+        if (pheromone_host)
+            DACO_CHECK_CUDA(cudaMemcpyAsync(a->pheromone + b0 * mat1, pheromone_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, aux.up));
+        DACO_CHECK_CUDA(cudaEventRecord(aux.ready[c], aux.up));
     }
     for (int c = 0; c < chunks; ++c) {
-        const int b0 = (int)((long)B * c / chunks), b1 = (int)((long)B * (c + 1) / chunks), nb = b1 - b0;
-        cudaStream_t s = (c & 1) ? g_aux_stream : st;
+        const int b0 = cuts[c], nb = cuts[c + 1] - cuts[c];
+        cudaStream_t cs = (c & 1) ? aux.comp : st;
         deepaco_tsp_run_args b = *a;
         b.n_colonies = nb;
         b.product_valid = 0;
@@ -222,22 +248,27 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
         b.knn = a->knn ? a->knn + (size_t)b0 * n * 32 : nullptr;
         b.heuristic_dist = a->heuristic_dist ? a->heuristic_dist + b0 * mat1 : nullptr;
         b.ev_sample_begin = b.ev_sample_end = nullptr;
-        const size_t bytes = (size_t)nb * mat1 * sizeof(float);
-        DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(b.distances), distances_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));
-        DACO_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(b.heuristic), heuristic_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));
-        DACO_CHECK_CUDA(cudaMemcpyAsync(b.pheromone, pheromone_host + b0 * mat1, bytes, cudaMemcpyHostToDevice, s));
-        const int rc = deepaco_tsp_run(&b, n_iterations, s);
+        const size_t cnt = (size_t)nb * mat1;
+        if (!pheromone_host) {   // ACO.__init__ (tsp/aco.py:37-40): pheromone = ones (* min under min_max)
+            fill_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, cs>>>(b.pheromone, a->min_max ? a->ph_min : 1.0f, cnt);
+            DACO_CHECK_LAUNCH();
+        }
+        DACO_CHECK_CUDA(cudaStreamWaitEvent(cs, aux.ready[c], 0));
+        const int rc = deepaco_tsp_run(&b, n_iterations, cs);
         if (rc) return rc;
+        DACO_CHECK_CUDA(cudaEventRecord(aux.done[c], cs));
+        DACO_CHECK_CUDA(cudaStreamWaitEvent(aux.down, aux.done[c], 0));
         if (copy_back_pheromone)
-            DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host + b0 * mat1, b.pheromone, bytes, cudaMemcpyDeviceToHost, s));
-        DACO_CHECK_CUDA(cudaMemcpyAsync(lowest_cost_host + b0, b.lowest_cost, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
+            DACO_CHECK_CUDA(cudaMemcpyAsync(pheromone_host + b0 * mat1, b.pheromone, cnt * sizeof(float), cudaMemcpyDeviceToHost, aux.down));
+        DACO_CHECK_CUDA(cudaMemcpyAsync(lowest_cost_host + b0, b.lowest_cost, sizeof(float) * nb, cudaMemcpyDeviceToHost, aux.down));
         DACO_CHECK_CUDA(cudaMemcpyAsync(shortest_path_host + (size_t)b0 * n, b.shortest_path, sizeof(int64_t) * nb * n,
-                                        cudaMemcpyDeviceToHost, s));
+                                        cudaMemcpyDeviceToHost, aux.down));
     }
-    if (chunks > 1) {
-        DACO_CHECK_CUDA(cudaEventRecord(g_ev_join, g_aux_stream));
-        DACO_CHECK_CUDA(cudaStreamWaitEvent(st, g_ev_join, 0));
-    }
+    // join: the caller's stream continues after the internal compute stream and the downloads
+    DACO_CHECK_CUDA(cudaEventRecord(aux.comp_done, aux.comp));
+    DACO_CHECK_CUDA(cudaEventRecord(aux.down_done, aux.down));
+    DACO_CHECK_CUDA(cudaStreamWaitEvent(st, aux.comp_done, 0));
+    DACO_CHECK_CUDA(cudaStreamWaitEvent(st, aux.down_done, 0));
     DACO_CHECK_CUDA(cudaStreamSynchronize(st));
     return DEEPACO_OK;
 }

@@ -138,10 +138,13 @@ typedef struct {
     void* ev_sample_end;
 } deepaco_tsp_run_args;
 int deepaco_tsp_run(const deepaco_tsp_run_args* args, int n_iterations, void* stream);
-/* Same with HOST matrices ([B][n][n] fp32 each): H2D of distances, heuristic, pheromone into the device
- * buffers of `args`, n_iterations, D2H of lowest_cost [B], shortest_path [B][n] and, if copy_back_pheromone,
- * the pheromone; synchronises `stream` before returning.
- * Bytes moved: 3 * B*n*n*4 in; B*4 + B*n*8 (+ B*n*n*4) out. */
+/* Same with HOST matrices ([B][n][n] fp32 each) -- `ACO(distances, heuristic=...).run(T)` for a caller whose data lives
+ * on the host: H2D of distances, heuristic and pheromone into the device buffers of `args`, n_iterations, D2H of
+ * lowest_cost [B], shortest_path [B][n] and, if copy_back_pheromone, the pheromone; synchronises `stream` before
+ * returning.  pheromone_host may be NULL: the pheromone then starts as ACO.__init__ creates it (ones, times ph_min under
+ * min_max; tsp/aco.py:37-40) and is not uploaded.  Uploads run on an internal copy stream, chunk after chunk, while the
+ * caller's stream computes the chunks that have landed.
+ * Bytes moved: (2 or 3) * B*n*n*4 in; B*4 + B*n*8 (+ B*n*n*4) out. */
 int deepaco_tsp_run_host(const deepaco_tsp_run_args* args, int n_iterations, const float* distances_host,
                          const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
                          int64_t* shortest_path_host, int copy_back_pheromone, void* stream);
