@@ -310,6 +310,7 @@ def main():
         "configs": {"c2_dense": L.guarded("c2_dense", L.leg_c2_dense, dev, leg_steps),
                     "c3": L.guarded("c3", L.leg_c3, dev, leg_steps),
                     "c4": L.guarded("c4", L.leg_c4, dev, leg_steps),
+                    "gnn_front_end": L.guarded("gnn_front_end", L.leg_gnn_front_end, dev, leg_steps),
                     "c5": c5},
         "ant_sharded": ant,
     }

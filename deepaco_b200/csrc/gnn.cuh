@@ -6,24 +6,40 @@
 //             w <- w + silu(BN_e(w1 + x3[src] + x4[dst])) }
 //   ParNet (net.py:48-75):  heu = sigmoid(Lin(silu(Lin(silu(Lin(w))))))  -> one value per edge
 //
-// Edge-parallel gather / scatter-free formulation: edges arrive sorted by source node (CSR), so the mean
-// aggregation is a fixed-order segmented sum (deterministic, no atomics -- the reference's torch_scatter path
-// uses atomics).  One CTA per instance runs all 12 layers: the per-layer weight block (22 KB) is double
-// buffered in shared memory by TMA bulk copies, node-side intermediates live in a small global scratch
-// (L2-resident), the edge state w[E][32] streams through L2 once per layer, and the 32x32 linears are fp32
-// FMAs with the weight row broadcast from shared memory (M is tiny; a tensor-core tile would be mostly padding).
-// BatchNorm runs in eval mode (running statistics), as in the reference's test drivers.
+// One CTA per instance runs all 12 layers (batches: one instance per CTA, two CTAs per SM).  Edges arrive sorted by
+// source node (CSR), so the mean aggregation is a fixed-order segmented sum (deterministic, no atomics -- the
+// reference's torch_scatter path uses atomics).  The edge state w[E][32] streams through L2 once per layer.
 //
-// Kernel source only (the C ABI is in gnn.cu); apart from the TMA / mbarrier helpers of common.cuh it is plain CUDA
-// C++, so tests/cpu_emu compiles the same text for the host.
+// The [rows, 32] x [32, 32] linears (edge linear: E rows per layer; the four node linears; the two head linears) run on
+// the TENSOR CORES: a warp owns a tile of 16 rows staged in shared memory and issues mma.sync.m16n8k8 TF32 on operands
+// split into tf32-exact parts (a = a1 + a2 + a3, w = w1 + w2 + w3, 11 significant bits each: the three parts carry all 24
+// bits of an fp32 value); the six products a_i * w_j with i + j <= 4 are accumulated in fp32, smallest first, so a
+// product is accurate to ~2^-33 and the result is as good as an fp32 FMA chain (the classic two-part 3xTF32 scheme,
+// ~2^-21 per product, measured 2.8x the reference's own distance from an fp64 evaluation after 12 layers; this one
+// is on par with it -- tests/test_gpu_gnn.py).  A 16 x 32 x 32 tile costs 96 MMA + 80 conversions instead of 512 FMA + their
+// shared-memory weight reads per warp.  BatchNorm (eval mode: running statistics), SiLU, the residual and
+// the x3[src] + x4[dst] gathers are the tile's register epilogue in the accumulator layout.  tcgen05 is deliberately not
+// used: N = K = 32 tiles of a 12-layer dependent chain per instance are epilogue- and latency-bound, not MMA-bound, and a
+// TMEM round trip per tile would only add to that.
+//
+// Kernel source only (the C ABI is in gnn.cu).  tests/cpu_emu compiles the same text for the host with a plain-loop
+// stand-in for tile_linear (same fragment layout).
 #pragma once
 #include "common.cuh"
 
 namespace deepaco {
 
 constexpr int U = 32;                                            // units
-constexpr int kLayerFloats = 4 * (U * U + U) + (U * U + U) + 8 * U;   // 5536
+constexpr int LINF = U * U + U;                                  // one packed linear: W[out][in] then b[out]
+constexpr int kLayerFloats = 5 * LINF + 8 * U;                   // 5536
 constexpr int kDepth = 12;
+constexpr int TS = 36;                                           // row stride of staged tiles / split weights (conflict-free fragments)
+constexpr int kTileRows = 16;
+#ifndef DACO_GNN_SPLIT_PARTS
+#define DACO_GNN_SPLIT_PARTS 2                                   // 2: classic 3xTF32 (error ~2^-21 per product); 3: six-term split (~2^-33)
+#endif
+constexpr int kParts = DACO_GNN_SPLIT_PARTS;
+constexpr int kSplitFloats = kParts * U * TS;                    // one linear as tf32 parts (big | mid | small), padded rows
 
 struct GnnParams {
     const float* x_in;      // [B][n][feats]
@@ -38,32 +54,162 @@ struct GnnParams {
     float* dense_out;       // [B][n][n] or null: Net.reshape(pyg, heu) + eps  (zero-padded matrix, tsp/net.py:95-102)
     float dense_eps;
     int n, E, feats;
+    const int32_t* src;     // [B][E] source of the sorted edge, or null (then found by binary search in row_ptr)
 };
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+#ifndef DEEPACO_CPU_EMU
+// exp(-v) as 2^(-v * log2 e) on the MUFU (ex2.approx, 2 ulp) with the rounding of the product compensated by an FMA
+// residual, and the division as rcp.approx (1 ulp): ~8 instructions instead of ~40 for expf + an IEEE division, at a
+// relative error of ~3e-7 -- what remains is measured against fp64 by tests/test_gpu_gnn.py.
+__device__ __forceinline__ float exp_neg(float v) {
+    const float kL2E = 1.4426950216293335f, kL2E_lo = 1.9259629911266175e-8f;
+    const float t = __fmul_rn(-v, kL2E);
+    const float r = fmaf(-v, kL2E_lo, fmaf(-v, kL2E, -t));          // (-v * log2 e) - t, to first order
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e < 3.0e38f ? fmaf(e, __fmul_rn(r, 0.6931471824645996f), e) : e;   // 2^(t + r) = 2^t * (1 + r ln 2 + ...)
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float silu_f(float v) { return __fmul_rn(v, rcp_fast(1.0f + exp_neg(v))); }
+__device__ __forceinline__ float sigmoid_f(float v) { return rcp_fast(1.0f + exp_neg(v)); }
+#else
+static inline float silu_f(float v) { return v / (1.0f + expf(-v)); }
+static inline float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+#endif
 
-// out[o] = b[o] + sum_k W[o][k] * in[k]   (W, b in shared memory: broadcast reads)
-__device__ __forceinline__ void linear32(const float* __restrict__ Wb, const float (&in)[U], float (&out)[U]) {
+#ifndef DEEPACO_CPU_EMU
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// v = part[0] + part[1] (+ part[2]) with every part exactly representable in tf32 (11 significant bits each: two parts
+// carry 22 of fp32's 24 bits, three carry all of them)
+__device__ __forceinline__ void split_tf32(float v, float (&part)[kParts]) {
+    float r = v;
 #pragma unroll
-    for (int o = 0; o < U; ++o) {
-        float acc = Wb[U * U + o];
-#pragma unroll
-        for (int k = 0; k < U; ++k) acc = fmaf(Wb[o * U + k], in[k], acc);
-        out[o] = acc;
+    for (int i = 0; i < kParts; ++i) {
+        part[i] = __uint_as_float(to_tf32(r));
+        r -= part[i];
     }
 }
 
-__global__ void __launch_bounds__(512) gnn_forward_kernel(const GnnParams p) {
+// d[nt][.] = rows (g, g+8) x columns (8 nt + 2t, 8 nt + 2t + 1) of  As[16][32] * W^T,  g = lane / 4, t = lane % 4
+// (the m16n8 accumulator layout).  As: staged tile, row stride TS.  Ws: split weights of one linear, kParts planes of
+// W[out][in] with row stride TS.  Products a_i * w_j are kept for i + j <= kParts - 1 and accumulated smallest first.
+__device__ __forceinline__ void tile_linear(const float* __restrict__ As, const float* __restrict__ Ws, float (&d)[4][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // The tensor core's fp32 accumulate truncates instead of rounding to nearest (a one-sided 2^-24 error per MMA): the
+    // correction terms (2^-11 and below) therefore go to their own accumulator, where that error is negligible, and only
+    // the four big-part MMAs of a dot product touch the main one.
+    float ds[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[nt][i] = ds[nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const float av[4] = {As[g * TS + ks * 8 + t], As[(g + 8) * TS + ks * 8 + t], As[g * TS + ks * 8 + t + 4],
+                             As[(g + 8) * TS + ks * 8 + t + 4]};
+        uint32_t a[kParts][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float part[kParts];
+            split_tf32(av[i], part);
+#pragma unroll
+            for (int q = 0; q < kParts; ++q) a[q][i] = __float_as_uint(part[q]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int o = (nt * 8 + g) * TS + ks * 8 + t;      // B[k][n] = W[n][k]
+            uint32_t b[kParts][2];
+#pragma unroll
+            for (int q = 0; q < kParts; ++q) {
+                b[q][0] = __float_as_uint(Ws[q * U * TS + o]);
+                b[q][1] = __float_as_uint(Ws[q * U * TS + o + 4]);
+            }
+#pragma unroll
+            for (int order = kParts - 1; order >= 1; --order)   // smallest terms first
+#pragma unroll
+                for (int i = order; i >= 0; --i) mma_tf32(ds[nt], a[i], b[order - i][0], b[order - i][1]);
+            mma_tf32(d[nt], a[0], b[0][0], b[0][1]);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[nt][i] += ds[nt][i];
+}
+#else   // host build (tests/cpu_emu): same fragment layout, plain fp32 loops instead of the MMA
+static inline void split_tf32(float v, float (&part)[kParts]) {
+    part[0] = v;
+    for (int i = 1; i < kParts; ++i) part[i] = 0.f;
+}
+static inline void tile_linear(const float* As, const float* Ws, float (&d)[4][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int nt = 0; nt < 4; ++nt)
+        for (int i = 0; i < 4; ++i) {
+            const int row = g + 8 * (i >> 1), col = nt * 8 + 2 * t + (i & 1);
+            float acc = 0.f;
+            for (int k = 0; k < U; ++k) {
+                float w = 0.f;
+                for (int q = kParts - 1; q >= 0; --q) w += Ws[q * U * TS + col * TS + k];
+                acc = fmaf(As[row * TS + k], w, acc);
+            }
+            d[nt][i] = acc;
+        }
+}
+#endif  // DEEPACO_CPU_EMU
+
+// stage rows [r0, r0 + 16) of a row-major [rows][32] matrix into the warp's tile (zero rows past `rows`)
+__device__ __forceinline__ void stage_tile(float* __restrict__ As, const float* __restrict__ src, int r0, int rows) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i, r = idx >> 3, c4 = idx & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < rows) v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * U + c4 * 4));
+        *reinterpret_cast<float4*>(As + r * TS + c4 * 4) = v;
+    }
+    __syncwarp();
+}
+
+// all threads: packed linear `lin_g` (W[32][32], b[32]) -> split weights (hi | lo, padded rows) + bias
+__device__ __forceinline__ void prep_linear(float* __restrict__ Ws, float* __restrict__ bias, const float* __restrict__ lin_g) {
+    for (int i = threadIdx.x; i < U * U; i += blockDim.x) {
+        float part[kParts];
+        split_tf32(__ldg(lin_g + i), part);
+        const int o = i >> 5, k = i & 31;
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) Ws[q * U * TS + o * TS + k] = part[q];
+    }
+    for (int i = threadIdx.x; i < U; i += blockDim.x) bias[i] = __ldg(lin_g + U * U + i);
+}
+
+__global__ void __launch_bounds__(512, 2) gnn_forward_kernel(const GnnParams p) {
     DACO_DYN_SMEM128(smem);
-    __shared__ uint64_t bars[2];
-    float* wbuf = reinterpret_cast<float*>(smem);                 // [2][kLayerFloats]
-    float* head = wbuf + 2 * kLayerFloats;                        // 2*(U*U+U) + U + 1
-    float* w0s = head + 2 * (U * U + U) + U + 1;                  // v_lin0 [U][feats] + b[U], e_lin0 [U] + b[U]
-    const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
+    float* wsplit = reinterpret_cast<float*>(smem);               // [5][kSplitFloats]: node linears 1..4, edge linear (head: 0, 1)
+    float* bias = wsplit + 5 * kSplitFloats;                      // [5][32]
+    float* bn = bias + 5 * U;                                     // v: gamma beta mean invstd | e: gamma beta mean invstd
+    float* h2 = bn + 8 * U;                                       // head lin2: W[32], b
+    float* w0s = h2 + U + 4;                                      // v_lin0 [U][feats] + b[U], e_lin0 [U] + b[U]
+    const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
     const int n = p.n, E = p.E, F = p.feats;
+    float* tiles = w0s + ((U * F + 3 * U + 3) & ~3);              // [nwarp][16][TS]
+    float* As = tiles + (size_t)warp * kTileRows * TS;
+    const int g = lane >> 2, t = lane & 3;
     const int32_t* rp = p.row_ptr + (size_t)b * (n + 1);
     const int32_t* dst = p.dst + (size_t)b * E;
+    const int32_t* srcs = p.src ? p.src + (size_t)b * E : nullptr;
     float* NW = p.node_ws + (size_t)b * n * 6 * U;
     float* X = NW, *X1 = NW + (size_t)n * U, *X3 = NW + (size_t)2 * n * U, *AG = NW + (size_t)3 * n * U;
     float* X2 = NW + (size_t)4 * n * U, *X4 = NW + (size_t)5 * n * U;
@@ -72,148 +218,184 @@ __global__ void __launch_bounds__(512) gnn_forward_kernel(const GnnParams p) {
     const int off_layers = U * F + U + U + U;                     // after v_lin0 and e_lin0
     const float* layers_g = Wg + off_layers;
     const float* head_g = layers_g + (size_t)kDepth * kLayerFloats;
+    auto src_of = [&](int e) -> int {
+        if (srcs) return srcs[e];
+        int lo = 0, hi = n;                                       // binary search in row_ptr
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (rp[mid] <= e) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
 
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_barrier_init();
-    }
     for (int i = tid; i < off_layers; i += nth) w0s[i] = Wg[i];
-    for (int i = tid; i < 2 * (U * U + U) + U + 1; i += nth) head[i] = head_g[i];
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], kLayerFloats * 4);
-        tma_bulk_g2s(wbuf, layers_g, kLayerFloats * 4, &bars[0]);
-    }
     // ---- input embeddings
-    for (int t = tid; t < n * U; t += nth) {
-        const int i = t / U, o = t % U;
+    for (int i = tid; i < n * U; i += nth) {
+        const int node = i / U, o = i % U;
         float acc = w0s[U * F + o];
-        for (int k = 0; k < F; ++k) acc = fmaf(w0s[o * F + k], p.x_in[((size_t)b * n + i) * F + k], acc);
-        X[t] = silu_f(acc);
+        for (int k = 0; k < F; ++k) acc = fmaf(w0s[o * F + k], p.x_in[((size_t)b * n + node) * F + k], acc);
+        X[i] = silu_f(acc);
     }
     {
         const float* We0 = w0s + U * F + U;
         const float* attr = p.attr + (size_t)b * E;
-        for (int t = tid; t < E * U; t += nth) {
-            const int e = t / U, o = t % U;
-            Wst[t] = silu_f(fmaf(We0[o], attr[e], We0[U + o]));
+        for (int i = tid; i < E * U; i += nth) {
+            const int e = i / U, o = i % U;
+            Wst[i] = silu_f(fmaf(We0[o], attr[e], We0[U + o]));
+        }
+    }
+
+    const int node_tiles = (n + kTileRows - 1) / kTileRows, edge_tiles = (E + kTileRows - 1) / kTileRows;
+    for (int l = 0; l < kDepth; ++l) {
+        const float* Lg = layers_g + (size_t)l * kLayerFloats;
+        __syncthreads();                                          // previous layer done with wsplit / bn; X, Wst complete
+        for (int q = 0; q < 5; ++q) prep_linear(wsplit + q * kSplitFloats, bias + q * U, Lg + q * LINF);
+        for (int i = tid; i < 8 * U; i += nth) bn[i] = __ldg(Lg + 5 * LINF + i);
+        __syncthreads();
+        const float* bnv = bn;                                    // gamma, beta, mean, invstd
+        const float* bne = bn + 4 * U;
+
+        // ---- node linears on the tensor cores: task = (node tile, which linear)
+        for (int task = warp; task < node_tiles * 4; task += nwarp) {
+            const int tile = task >> 2, q = task & 3;
+            stage_tile(As, X, tile * kTileRows, n);
+            float d[4][4];
+            tile_linear(As, wsplit + q * kSplitFloats, d);
+            float* outp = q == 0 ? X1 : q == 1 ? X2 : q == 2 ? X3 : X4;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = tile * kTileRows + g + 8 * h;
+                if (r < n)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int c = nt * 8 + 2 * t;
+                        *reinterpret_cast<float2*>(outp + (size_t)r * U + c) =
+                            make_float2(d[nt][2 * h] + bias[q * U + c], d[nt][2 * h + 1] + bias[q * U + c + 1]);
+                    }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- aggregation: a warp per node, lanes = features; fixed edge order within the node's CSR segment
+        for (int i = warp; i < n; i += nwarp) {
+            const int e0 = rp[i], e1 = rp[i + 1];
+            float s = 0.f;
+            for (int eb = e0; eb < e1; eb += 32) {             // destinations of up to 32 edges with one coalesced load
+                const int cnt = min(32, e1 - eb);
+                const int dl = lane < cnt ? dst[eb + lane] : 0;
+                for (int j0 = 0; j0 < cnt; j0 += 8) {          // eight edges' rows in flight (same summation order)
+                    float wv[8], xv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int d = __shfl_sync(DACO_FULL, dl, (j0 + j) & 31);
+                        const bool on = j0 + j < cnt;
+                        wv[j] = on ? __ldcg(Wst + (size_t)(eb + j0 + j) * U + lane) : 0.f;
+                        xv[j] = on ? X2[(size_t)d * U + lane] : 0.f;   // node arrays: written and read by this CTA only (L1)
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j0 + j < cnt) s += sigmoid_f(wv[j]) * xv[j];
+                }
+            }
+            const int deg = e1 - e0;
+            AG[i * U + lane] = s / (float)(deg > 0 ? deg : 1);
+        }
+        __syncthreads();
+        // ---- edge update on the tensor cores: task = tile of 16 edges
+        for (int tile = warp; tile < edge_tiles; tile += nwarp) {
+            int se[2], de[2];                                      // endpoints of this lane's two rows: loads in flight during the MMA
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = min(tile * kTileRows + g + 8 * h, E - 1);
+                se[h] = src_of(e);
+                de[h] = dst[e];
+            }
+            stage_tile(As, Wst, tile * kTileRows, E);
+            float d[4][4];
+            tile_linear(As, wsplit + 4 * kSplitFloats, d);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = tile * kTileRows + g + 8 * h;
+                if (e < E) {
+                    const float* x3 = X3 + (size_t)se[h] * U;
+                    const float* x4 = X4 + (size_t)de[h] * U;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int c = nt * 8 + 2 * t;
+                        const float2 a3 = *reinterpret_cast<const float2*>(x3 + c);
+                        const float2 a4 = *reinterpret_cast<const float2*>(x4 + c);
+                        const float z0 = d[nt][2 * h] + bias[4 * U + c] + a3.x + a4.x;
+                        const float z1 = d[nt][2 * h + 1] + bias[4 * U + c + 1] + a3.y + a4.y;
+                        const float y0 = (z0 - bne[2 * U + c]) * bne[3 * U + c] * bne[c] + bne[U + c];
+                        const float y1 = (z1 - bne[2 * U + c + 1]) * bne[3 * U + c + 1] * bne[c + 1] + bne[U + c + 1];
+                        const float2 in = *reinterpret_cast<const float2*>(As + (g + 8 * h) * TS + c);
+                        *reinterpret_cast<float2*>(Wst + (size_t)e * U + c) = make_float2(in.x + silu_f(y0), in.y + silu_f(y1));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- node update: task = (node, feature)
+        for (int i = tid; i < n * U; i += nth) {
+            const int f = i % U;
+            const float z = __ldcg(X1 + i) + __ldcg(AG + i);
+            const float y = (z - bnv[2 * U + f]) * bnv[3 * U + f] * bnv[f] + bnv[U + f];
+            X[i] = __ldcg(X + i) + silu_f(y);
         }
     }
     __syncthreads();
-
-    for (int l = 0; l < kDepth; ++l) {
-        const float* Wl = wbuf + (size_t)(l & 1) * kLayerFloats;
-        if (tid == 0 && l + 1 < kDepth) {      // prefetch next layer's weights into the other buffer
-            mbar_expect_tx(&bars[(l + 1) & 1], kLayerFloats * 4);
-            tma_bulk_g2s(wbuf + (size_t)((l + 1) & 1) * kLayerFloats, layers_g + (size_t)(l + 1) * kLayerFloats,
-                         kLayerFloats * 4, &bars[(l + 1) & 1]);
-        }
-        mbar_wait(&bars[l & 1], (l >> 1) & 1);
-        const float* Wv = Wl;                                   // 4 x (W[32][32], b[32])
-        const float* We = Wl + 4 * (U * U + U);
-        const float* bnv = We + (U * U + U);                    // gamma, beta, mean, invstd
-        const float* bne = bnv + 4 * U;
-
-        // ---- node linears: task = (node, which linear)
-        for (int t = tid; t < n * 4; t += nth) {
-            const int i = t >> 2, q = t & 3;
-            float in[U], out[U];
-#pragma unroll
-            for (int k = 0; k < U; k += 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(X + (size_t)i * U + k));
-                in[k] = v.x; in[k + 1] = v.y; in[k + 2] = v.z; in[k + 3] = v.w;
-            }
-            linear32(Wv + q * (U * U + U), in, out);
-            float* dstp = (q == 0 ? X1 : q == 1 ? X2 : q == 2 ? X3 : X4) + (size_t)i * U;
-#pragma unroll
-            for (int k = 0; k < U; k += 4) *reinterpret_cast<float4*>(dstp + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
-        }
-        __syncthreads();
-        // ---- aggregation: task = (node, feature); fixed edge order within the node's CSR segment
-        for (int t = tid; t < n * U; t += nth) {
-            const int i = t / U, f = t % U;
-            const int e0 = rp[i], e1 = rp[i + 1];
-            float s = 0.f;
-            for (int e = e0; e < e1; ++e)
-                s += sigmoid_f(__ldcg(Wst + (size_t)e * U + f)) * __ldcg(X2 + (size_t)dst[e] * U + f);
-            const int deg = e1 - e0;
-            AG[t] = s / (float)(deg > 0 ? deg : 1);
-        }
-        __syncthreads();
-        // ---- edge update: task = edge
-        for (int e = tid; e < E; e += nth) {
-            // source node of sorted edge e: binary search in row_ptr
-            int lo = 0, hi = n;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (rp[mid] <= e) lo = mid; else hi = mid;
-            }
-            const int src = lo, d = dst[e];
-            float in[U], out[U];
-#pragma unroll
-            for (int k = 0; k < U; k += 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(Wst + (size_t)e * U + k));
-                in[k] = v.x; in[k + 1] = v.y; in[k + 2] = v.z; in[k + 3] = v.w;
-            }
-            linear32(We, in, out);
-#pragma unroll
-            for (int k = 0; k < U; k += 4) {
-                const float4 a3 = __ldcg(reinterpret_cast<const float4*>(X3 + (size_t)src * U + k));
-                const float4 a4 = __ldcg(reinterpret_cast<const float4*>(X4 + (size_t)d * U + k));
-                const float z[4] = {out[k] + a3.x + a4.x, out[k + 1] + a3.y + a4.y, out[k + 2] + a3.z + a4.z, out[k + 3] + a3.w + a4.w};
-                float r[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int f = k + c;
-                    const float y = (z[c] - bne[2 * U + f]) * bne[3 * U + f] * bne[f] + bne[U + f];
-                    r[c] = in[f] + silu_f(y);
-                }
-                *reinterpret_cast<float4*>(Wst + (size_t)e * U + k) = make_float4(r[0], r[1], r[2], r[3]);
-            }
-        }
-        // ---- node update: task = (node, feature)
-        for (int t = tid; t < n * U; t += nth) {
-            const int f = t % U;
-            const float z = __ldcg(X1 + t) + __ldcg(AG + t);
-            const float y = (z - bnv[2 * U + f]) * bnv[3 * U + f] * bnv[f] + bnv[U + f];
-            X[t] = __ldcg(X + t) + silu_f(y);
-        }
-        __syncthreads();
-    }
+    prep_linear(wsplit, bias, head_g);
+    prep_linear(wsplit + kSplitFloats, bias + U, head_g + LINF);
+    for (int i = tid; i < U + 1; i += nth) h2[i] = __ldg(head_g + 2 * LINF + i);
     if (p.dense_out) {          // background of the dense matrix: 0 + eps off-graph
         float* M = p.dense_out + (size_t)b * n * n;
         for (int i = tid; i < n * n; i += nth) M[i] = p.dense_eps;
-        __syncthreads();
     }
-    // ---- head MLP per edge
-    const float* H0 = head, *H1 = head + (U * U + U), *H2 = head + 2 * (U * U + U);
+    __syncthreads();
+    // ---- head MLP per tile of 16 edges: 32 -> 32 -> 32 on the tensor cores, 32 -> 1 by a quad reduction
     const int32_t* order = p.order + (size_t)b * E;
-    for (int e = tid; e < E; e += nth) {
-        float in[U], h[U];
+    for (int tile = warp; tile < edge_tiles; tile += nwarp) {
+        stage_tile(As, Wst, tile * kTileRows, E);
+        float d[4][4];
+        tile_linear(As, wsplit, d);
+        __syncwarp();                                             // every lane has read its fragments of the input tile
 #pragma unroll
-        for (int k = 0; k < U; k += 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(Wst + (size_t)e * U + k));
-            in[k] = v.x; in[k + 1] = v.y; in[k + 2] = v.z; in[k + 3] = v.w;
-        }
-        linear32(H0, in, h);
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int k = 0; k < U; ++k) in[k] = silu_f(h[k]);
-        linear32(H1, in, h);
-        float acc = H2[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) acc = fmaf(H2[k], silu_f(h[k]), acc);
-        const float hv = sigmoid_f(acc);
-        if (p.out) p.out[(size_t)b * E + order[e]] = hv;
-        if (p.dense_out) {
-            int lo = 0, hi = n;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (rp[mid] <= e) lo = mid; else hi = mid;
+            for (int nt = 0; nt < 4; ++nt) {
+                const int c = nt * 8 + 2 * t;
+                *reinterpret_cast<float2*>(As + (g + 8 * h) * TS + c) =
+                    make_float2(silu_f(d[nt][2 * h] + bias[c]), silu_f(d[nt][2 * h + 1] + bias[c + 1]));
             }
-            p.dense_out[((size_t)b * n + lo) * n + dst[e]] = hv + p.dense_eps;
+        __syncwarp();
+        tile_linear(As, wsplit + kSplitFloats, d);
+        float part[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int c = nt * 8 + 2 * t;
+                part[h] = fmaf(h2[c], silu_f(d[nt][2 * h] + bias[U + c]), part[h]);
+                part[h] = fmaf(h2[c + 1], silu_f(d[nt][2 * h + 1] + bias[U + c + 1]), part[h]);
+            }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            part[h] += __shfl_xor_sync(DACO_FULL, part[h], 1);
+            part[h] += __shfl_xor_sync(DACO_FULL, part[h], 2);
+            const int e = tile * kTileRows + g + 8 * h;
+            if (t == 0 && e < E) {
+                const float hv = sigmoid_f(part[h] + h2[U]);
+                if (p.out) p.out[(size_t)b * E + order[e]] = hv;
+                if (p.dense_out) p.dense_out[((size_t)b * n + src_of(e)) * n + dst[e]] = hv + p.dense_eps;
+            }
         }
+        __syncwarp();
     }
+}
+
+inline size_t gnn_forward_smem(int feats, int threads) {
+    return ((size_t)5 * kSplitFloats + 5 * U + 8 * U + U + 4 + ((U * feats + 3 * U + 3) & ~3) + (size_t)(threads / 32) * kTileRows * TS) * 4 + 128;
 }
 
 }  // namespace deepaco

@@ -130,7 +130,7 @@ def csr_by_source(edge_index, n_nodes):
     return row_ptr, order.to(torch.int32)
 
 
-def _launch_gnn(weights, feats, xin, row_ptr, dst_s, attr_s, order, want_vec, dense_eps):
+def _launch_gnn(weights, feats, xin, row_ptr, dst_s, attr_s, order, want_vec, dense_eps, src_s=None):
     B, n = xin.shape[0], xin.shape[1]
     E = dst_s.shape[1]
     dev = xin.device
@@ -141,7 +141,8 @@ def _launch_gnn(weights, feats, xin, row_ptr, dst_s, attr_s, order, want_vec, de
     with torch.cuda.device(dev):
         check(lib().deepaco_gnn_forward(ptr(xin), ptr(row_ptr), ptr(dst_s), ptr(attr_s), ptr(order), ptr(weights), n, E, feats,
                                         B, ptr(node_ws), ptr(edge_ws), ptr(out), ptr(dense),
-                                        float(dense_eps if dense_eps is not None else 0.0), stream_ptr(dev)), "deepaco_gnn_forward")
+                                        float(dense_eps if dense_eps is not None else 0.0), ptr(src_s), stream_ptr(dev)),
+              "deepaco_gnn_forward")
     return out, dense
 
 
@@ -164,8 +165,9 @@ def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None, graph=
     row_ptr, order = torch.stack(rps).contiguous(), torch.stack(orders).contiguous()
     ol = order.long()
     dst_s = torch.gather(edge_index[:, 1], 1, ol).to(torch.int32).contiguous()
+    src_s = torch.gather(edge_index[:, 0], 1, ol).to(torch.int32).contiguous()
     attr_s = torch.gather(edge_attr.reshape(B, E).to(torch.float32), 1, ol).contiguous()
-    out, dense = _launch_gnn(weights, feats, x.to(torch.float32).contiguous(), row_ptr, dst_s, attr_s, order, True, dense_eps)
+    out, dense = _launch_gnn(weights, feats, x.to(torch.float32).contiguous(), row_ptr, dst_s, attr_s, order, True, dense_eps, src_s)
     if dense_eps is None:
         return out if batched else out[0]
     return (out, dense) if batched else (out[0], dense[0])
@@ -181,9 +183,10 @@ def knn_heuristic_matrices(weights, feats, node_features, distances, k_sparse, e
     E = n * k_sparse
     row_ptr = (torch.arange(n + 1, device=dev, dtype=torch.int32) * k_sparse).expand(B, n + 1).contiguous()
     order = torch.arange(E, device=dev, dtype=torch.int32).expand(B, E).contiguous()
+    src_s = (order // k_sparse).contiguous()                                          # constant degree: source = e // k
     _, dense = _launch_gnn(weights, feats, node_features.to(torch.float32).contiguous(), row_ptr,
                            near_i.reshape(B, E).to(torch.int32).contiguous(), near_d.reshape(B, E).to(torch.float32).contiguous(),
-                           order, False, eps)
+                           order, False, eps, src_s)
     return dense
 
 
@@ -212,7 +215,7 @@ def dense_heuristic_matrices(weights, feats, node_features, distances, eps=1e-10
     if ctas > 1:
         vec = gnn_forward_group(weights, feats, x, None, None, ctas, graph=g)
     else:
-        vec, _ = _launch_gnn(weights, feats, x, g["row_ptr"], g["dst"], g["attr"], g["order"], True, None)
+        vec, _ = _launch_gnn(weights, feats, x, g["row_ptr"], g["dst"], g["attr"], g["order"], True, None, g["src"])
     return vec.view(B, N, N) + eps
 
 

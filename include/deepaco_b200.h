@@ -198,12 +198,15 @@ int deepaco_tours_to_paths(const uint16_t* tours, int64_t* paths, int n, int n_a
  * deepaco_b200/net.py:pack_weights; deepaco_gnn_weight_count(feats) values).  node_ws f32 [B][n][192] and
  * edge_ws f32 [B][E][32] are scratch.  heu_out f32 [B][E] = Net.forward(pyg) per original edge (may be NULL).
  * dense_out (optional f32 [B][n][n]) = Net.reshape(pyg, heu) + dense_eps, i.e. the heuristic matrix the drivers
- * hand to ACO (tsp/test.ipynb cell 1), written by the same launch. */
+ * hand to ACO (tsp/test.ipynb cell 1), written by the same launch.
+ * src_sorted (optional int32 [B][E]): source node of each sorted edge; NULL = found by binary search in row_ptr.
+ * The 32x32 linears (tsp/net.py:36-43,62-75) run on the tensor cores (mma.sync TF32 with the 3xTF32 split: fp32-level
+ * accuracy, fp32 accumulate); everything else is fp32. */
 int64_t deepaco_gnn_weight_count(int feats);
 int deepaco_gnn_forward(const float* x, const int32_t* row_ptr, const int32_t* dst_sorted, const float* attr_sorted,
                         const int32_t* order, const float* weights, int n_nodes, int n_edges, int feats,
                         int n_instances, float* node_ws, float* edge_ws, float* heu_out, float* dense_out,
-                        float dense_eps, void* stream);
+                        float dense_eps, const int32_t* src_sorted, void* stream);
 
 /* ---- heuristic network, TRAINING mode: forward with batch-statistics BatchNorm, and its backward
  * (Net.forward under net.train() as driven by train_instance: tsp/train.ipynb cell 1, tsp_nls/train.py:15-44,

@@ -27,6 +27,10 @@ struct alignas(16) float4 {
     float x, y, z, w;
 };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(8) float2 {
+    float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 namespace emu {
 struct Dim3 {

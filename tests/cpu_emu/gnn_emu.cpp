@@ -33,8 +33,8 @@ extern "C" const char* emu_gnn_forward(const float* x, const int32_t* row_ptr, c
                                        float* edge_ws, float* heu_out, float* dense_out, float dense_eps, int threads) {
     if (!(x && row_ptr && dst_sorted && attr_sorted && order && weights && node_ws && edge_ws && (heu_out || dense_out))) return "NULL argument";
     if (!(n >= 1 && E >= 1 && feats >= 1 && feats <= 8 && B >= 1 && threads >= 32 && threads % 32 == 0)) return "bad sizes";
-    const GnnParams p{x, row_ptr, dst_sorted, attr_sorted, order, weights, node_ws, edge_ws, heu_out, dense_out, dense_eps, n, E, feats};
-    const size_t smem = ((size_t)2 * kLayerFloats + 2 * (U * U + U) + U + 1 + (size_t)U * feats + 3 * U) * 4 + 64;
-    emu::launch(gnn_forward_kernel, p, B, 1, threads, smem);
+    const GnnParams p{x, row_ptr, dst_sorted, attr_sorted, order, weights, node_ws, edge_ws, heu_out, dense_out, dense_eps, n, E, feats,
+                      nullptr};
+    emu::launch(gnn_forward_kernel, p, B, 1, threads, gnn_forward_smem(feats, threads));
     return nullptr;
 }

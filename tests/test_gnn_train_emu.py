@@ -274,10 +274,11 @@ def emu_g():
 
 
 @pytest.mark.parametrize("kind,fixture", CASES)
-def test_one_cta_eval_kernel_on_host_matches_the_restatement_and_the_group_kernel_bit_for_bit(emu, emu_g, golden, kind, fixture):
-    """deepaco_gnn_forward (csrc/gnn.cuh: one CTA per instance, TMA double-buffered weights, fused reshape + EPS) through
-    its host build: equal to the eval-mode torch restatement to fp32 rounding, equal to deepaco_gnn_forward_group's host
-    build BIT FOR BIT (the two kernels are interchangeable), and the dense output is Net.reshape(...) + EPS."""
+def test_one_cta_eval_kernel_on_host_matches_the_restatement_and_the_group_kernel(emu, emu_g, golden, kind, fixture):
+    """deepaco_gnn_forward (csrc/gnn.cuh: one CTA per instance, 16-row tiles through tile_linear -- the tensor-core MMA on
+    the device, its plain-loop stand-in here --, fused reshape + EPS) through its host build: equal to the eval-mode torch
+    restatement and to deepaco_gnn_forward_group's host build to fp32 rounding (different summation order inside the
+    32-term dot products), and the dense output is Net.reshape(...) + EPS."""
     from deepaco_b200 import net as N
     from oracle import net_torch
     g = golden(fixture)
@@ -305,4 +306,4 @@ def test_one_cta_eval_kernel_on_host_matches_the_restatement_and_the_group_kerne
     heu_g = torch.full((1, E), float("nan"))
     a, keep = N.train_args(x, graph, w, bufs, net.emb_net.feats, 4, 1e-5, heu_out=heu_g)
     assert emu.emu_gnn_forward_group(ctypes.byref(a), 128) is None
-    assert torch.equal(heu_g, heu)
+    assert torch.allclose(heu_g, heu, rtol=1e-4, atol=1e-7)

@@ -38,6 +38,57 @@ def test_tsp100_heuristic_matches_reference(golden):
     assert torch.allclose(vec, ref, rtol=2e-4, atol=1e-6)
 
 
+def _fp64(net, pyg):
+    """The network evaluated in float64 through the torch restatement (oracle/net_torch.py): the arbiter between the
+    reference's fp32 output (golden) and the kernels' fp32 output."""
+    import copy
+    from deepaco_b200.net import Data
+    from oracle import net_torch
+    net64 = copy.deepcopy(net).double()
+    pyg64 = Data(x=pyg.x.double(), edge_index=pyg.edge_index, edge_attr=pyg.edge_attr.double())
+    with torch.no_grad():
+        return net_torch.net_forward(net64, pyg64)
+
+
+def _rel_err(a, truth):
+    return float(((a.double() - truth).abs() / truth.abs().clamp(min=1e-300)).max())
+
+
+@pytest.mark.parametrize("case", ["tsp100", "tsp_nls200", "cvrp100"])
+def test_kernels_are_as_close_to_fp64_as_the_reference_is(golden, case, monkeypatch):
+    """Which side of `kernel vs reference` is off?  Both are fp32 evaluations of a 12-layer network whose output spans
+    1e-14 .. 1; against a float64 evaluation the reference's own fp32 output (golden vectors from the unmodified
+    net.py) is off by ~2e-5 relative (tsp100) and more in the deep sigmoid tails.  Both kernels -- the tensor-core
+    one-CTA kernel (3xTF32) and the fp32 group kernel -- must be within 2x of the reference's own distance from fp64
+    (floor 1e-5 relative)."""
+    if case == "tsp100":
+        from deepaco_b200.tsp.net import Net
+        from deepaco_b200.tsp.utils import gen_pyg_data
+        g = golden("tsp_n100_a32_gnn")
+        net, pyg = _load(Net, "weights_tsp100"), gen_pyg_data(torch.from_numpy(g["coords"]).to(DEV), 20)[0]
+    elif case == "tsp_nls200":
+        from deepaco_b200.tsp_nls.net import Net
+        from deepaco_b200.tsp_nls.utils import gen_pyg_data
+        g = golden("tsp_nls_n200_a16")
+        net, pyg = _load(Net, "weights_tsp_nls500"), gen_pyg_data(torch.from_numpy(g["coords"]).to(DEV), 20, start_node=0)[0]
+    else:
+        from deepaco_b200.cvrp.net import Net
+        from deepaco_b200.cvrp.utils import gen_pyg_data
+        g = golden("cvrp_n100_a32_gnn")
+        net = _load(Net, "weights_cvrp100")
+        pyg = gen_pyg_data(torch.from_numpy(g["demand"]).to(DEV), torch.from_numpy(g["dist"]).to(DEV), DEV)
+    truth = _fp64(net, pyg)
+    ref_err = _rel_err(torch.from_numpy(g["heu_vec"]).to(DEV), truth)
+    with torch.no_grad():
+        grouped = net(pyg)                                        # group kernel (fp32 FMA)
+        monkeypatch.setenv("DEEPACO_GNN_CTAS", "1")
+        single = net(pyg)                                         # one-CTA kernel (tensor cores, 3xTF32)
+    errs = {"group": _rel_err(grouped, truth), "tensor_core": _rel_err(single, truth)}
+    print(f"{case}: relative error vs fp64 -- reference {ref_err:.3e}, kernels {errs}")
+    bound = max(2.0 * ref_err, 1e-5)
+    assert errs["group"] <= bound and errs["tensor_core"] <= bound, (ref_err, errs)
+
+
 def test_tsp_nls_and_cvrp_heuristics_match_reference(golden):
     from deepaco_b200.cvrp.net import Net as CNet
     from deepaco_b200.cvrp.utils import gen_pyg_data as cvrp_graph
@@ -70,8 +121,8 @@ def test_batched_forward_equals_single():
     ea = torch.stack([g.edge_attr for g in graphs])
     out = gnn_forward(net._weights(), 2, x, ei, ea)
     for b in range(6):
-        with torch.no_grad():
-            assert torch.equal(out[b], net(graphs[b]))
+        with torch.no_grad():      # single instance: group kernel (fp32 FMA); batch: one-CTA kernel (tensor cores, 3xTF32)
+            assert torch.allclose(out[b], net(graphs[b]), rtol=1e-4, atol=1e-12)     # each is ~2e-5 from fp64
 
 
 def test_batched_front_end_equals_per_instance_path():
@@ -88,14 +139,15 @@ def test_batched_front_end_equals_per_instance_path():
         pyg, _ = gen_pyg_data(coords[b], 20)
         with torch.no_grad():
             want = net.reshape(pyg, net(pyg)) + 1e-10
-        assert torch.equal(dense[b], want)
+        assert torch.allclose(dense[b], want, rtol=1e-4, atol=1e-12)
+        assert torch.equal(dense[b] == 1e-10, want == 1e-10)          # same sparsity pattern
 
 
 @pytest.mark.parametrize("kind", ["tsp", "tsp_nls", "cvrp"])
-def test_group_forward_returns_the_bits_of_the_single_cta_kernel(kind, monkeypatch):
+def test_group_forward_agrees_with_the_single_cta_kernel(kind, monkeypatch):
     """Eval-mode Net.forward of ONE instance runs on a group of CTAs (deepaco_gnn_forward_group: cluster of 8 at C2,
-    cooperative launch of 64 / 32 at C3 / C4); the one-CTA-per-instance kernel of the batched front end must give the
-    same bits, so a heuristic does not depend on which of the two produced it."""
+    cooperative launch of 64 / 32 at C3 / C4): the same bits whatever the group size; the one-CTA-per-instance kernel
+    of the batched front end (tensor-core tiles) agrees to fp32 rounding."""
     from deepaco_b200 import net as N
     if kind == "tsp":
         from deepaco_b200.tsp.net import Net
@@ -121,7 +173,10 @@ def test_group_forward_returns_the_bits_of_the_single_cta_kernel(kind, monkeypat
         single = net(pyg)
         monkeypatch.setenv("DEEPACO_GNN_CTAS", "4")
         four = net(pyg)
-    assert torch.equal(grouped, single) and torch.equal(four, single)
+    assert torch.equal(four, grouped)                                # group size does not change the bits
+    # tensor-core tiles: other summation order; both sit at the reference's own distance from fp64 (~2e-5 relative, ~2e-3
+    # in the 1e-13 sigmoid tails of the tsp_nls checkpoint -- test_kernels_are_as_close_to_fp64_as_the_reference_is)
+    assert torch.allclose(single, grouped, rtol=5e-3 if kind == "tsp_nls" else 1e-4, atol=1e-12)
     assert float(grouped.min()) >= 0 and float(grouped.max()) <= 1
 
 
@@ -142,4 +197,4 @@ def test_dense_batched_front_end_equals_per_instance_path(customers, count):
     for b, (d, m) in enumerate(insts):
         with torch.no_grad():
             want = net(gen_pyg_data(d, m, DEV)).reshape(N, N) + 1e-10
-        assert torch.equal(dense[b], want)
+        assert torch.allclose(dense[b], want, rtol=1e-4, atol=1e-12)   # batch and single instance may take different kernels

@@ -316,6 +316,23 @@ def leg_reference_cuda(dev, iters=3):
             "sample": f"{iters} ACO iterations of one TSP-100 colony x 512 ants, reference op sequence on cuda (torch {torch.__version__}), {how}"}
 
 
+def leg_gnn_front_end(dev, steps):
+    """K3: instance -> kNN graph -> heuristic network (eval) -> dense heuristic matrix for the batch the ACO iteration
+    consumes (256 x TSP-100, k = 20), one launch of deepaco_gnn_forward (tensor-core tiles) after a batched topk."""
+    B, n, k = 256, 100, 20
+    coords, d = tsp_instances(B, n, 1234, dev)
+    net = load_net("tsp", dev)
+    ms = timed(lambda: net.heuristic_matrices(coords, d, k), max(3, min(steps, 10)))
+    E = n * k
+    flops = B * (12 * (2 * E * 32 * 32 + 4 * 2 * n * 32 * 32) + 2 * 2 * E * 32 * 32)
+    bytes_alg = B * 12 * (2 * 128 * E + 3 * 128 * E + 20 * 1024)          # SURVEY 8d: edge state r/w + gathers + weights
+    out = {"workload": f"{B} x TSP-{n}, k={k}: topk + Net.forward (eval) + reshape + EPS", "ms_per_batch": ms,
+           "us_per_instance": ms / B * 1e3, "tflops_linear": flops / (ms * 1e-3) / 1e12,
+           "roofline": roofline("K3 gnn_forward_kernel (mma.sync TF32 split tiles)", bytes_alg, ms,
+                                "edge state streams through L2 once per layer; whole front end timed (topk included)")}
+    return out
+
+
 def guarded(name, fn, *args, **kw):
     """Run a leg; an exception becomes {"error": ...}.  Collective-bearing legs raise symmetrically on all ranks or not
     at all (their failure modes -- missing checkpoint, symmetric memory unavailable -- do not depend on the rank)."""
