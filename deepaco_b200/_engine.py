@@ -120,6 +120,28 @@ def tsp_sample_shard_p2p(pheromone, heuristic, n_ants_local, ant_base, n_ants_to
                                                  len(peer_ptrs), stream_ptr(dev)), "deepaco_tsp_sample_shard_p2p")
 
 
+def tsp_roulette_sample(prob, n_ants, *, start_node=0, seed=0, offset=0, offsets=None, want_paths=True, want_tours=False):
+    """deepaco_tsp_roulette_sample (the reference's inference sampler, tsp_nls/aco.py:260-297) -> (paths | None, tours | None)."""
+    prob = f32c(require_cuda(prob, "prob"))
+    B, n = _colonies(prob)
+    batched = prob.dim() == 3
+    dev = prob.device
+    paths = torch.empty((B, n, n_ants), dtype=torch.int64, device=dev) if want_paths else None
+    tours = torch.empty((B, n_ants, n), dtype=torch.uint16, device=dev) if want_tours else None
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_roulette_sample(ptr(prob), n, n_ants, B, int(start_node), int(seed), int(offset),
+                                                ptr(_offsets(offsets, B, dev)), ptr(tours), ptr(paths), stream_ptr(dev)),
+              "deepaco_tsp_roulette_sample")
+    if not batched:
+        paths = None if paths is None else paths[0]
+        tours = None if tours is None else tours[0]
+    return paths, tours
+
+
+def tsp_roulette_offset_increment(n, n_ants) -> int:
+    return int(lib().deepaco_tsp_roulette_offset_increment(n, n_ants))
+
+
 def tsp_sample_offset_increment(n, n_ants, start_node=-1) -> int:
     return int(lib().deepaco_tsp_sample_offset_increment(n, n_ants, int(start_node)))
 
@@ -210,6 +232,7 @@ class TspRunner:
         self.knn = sparse_candidates(self.heuristic) if use_knn else None
         # optional local search between construction and cost (tsp_nls): 0 none, 1 2-opt, 2 NLS
         self.local_search, self.ls_max_iterations, self.T_nls, self.T_p, self.heuristic_dist = 0, 0, 10, 20, None
+        self.roulette = False           # True: roulette-wheel construction (tsp_nls run(.., inference=True))
 
     def set_local_search(self, mode, max_iterations, heuristic_dist=None, T_nls=10, T_p=20):
         self.local_search = {None: 0, "2opt": 1, "nls": 2}[mode]
@@ -229,7 +252,7 @@ class TspRunner:
                                int(self.product_valid), ptr(self.tours), ptr(self.costs), ptr(self.neighbours),
                                ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.ph_max), ptr(self.scale), ptr(self.knn),
                                self.local_search, self.ls_max_iterations, self.T_nls, self.T_p, ptr(self.heuristic_dist),
-                               ev0, ev1)
+                               ev0, ev1, int(self.roulette))
 
     def run(self, n_iterations, seed, offset=0, offsets=None, sample_events=None):
         """Launch n_iterations ACO iterations; colony b consumes offsets[b] + offset + t * self.increment.

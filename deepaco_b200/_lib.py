@@ -26,6 +26,8 @@ _SIGNATURES = {
     "deepaco_tsp_sample_shard": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "deepaco_tsp_sample_shard_p2p": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "deepaco_tsp_sample_offset_increment": (_u64, [_i32, _i32, _i32]),
+    "deepaco_tsp_roulette_sample": (_i32, [_vp, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "deepaco_tsp_roulette_offset_increment": (_u64, [_i32, _i32]),
     "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
     "deepaco_two_opt": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
@@ -57,7 +59,8 @@ class TspRunArgs(C.Structure):
                 ("pheromone", _vp), ("heuristic", _vp), ("distances", _vp), ("product", _vp), ("product_valid", _i32),
                 ("tours", _vp), ("costs", _vp), ("neighbours", _vp), ("lowest_cost", _vp), ("shortest_path", _vp),
                 ("ph_max", _vp), ("scale", _vp), ("knn", _vp), ("local_search", _i32), ("ls_max_iterations", _i32),
-                ("T_nls", _i32), ("T_p", _i32), ("heuristic_dist", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp)]
+                ("T_nls", _i32), ("T_p", _i32), ("heuristic_dist", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp),
+                ("roulette", _i32)]
 
 
 class ShardArgs(C.Structure):

@@ -130,7 +130,7 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
                    "deepaco_tsp_run: bad local_search / missing heuristic_dist");
     cudaStream_t st = (cudaStream_t)stream;
     const int n = a->n, A = a->n_ants, B = a->n_colonies;
-    const uint64_t inc = deepaco_tsp_sample_offset_increment(n, A, a->start_node);
+    const uint64_t inc = a->roulette ? deepaco_tsp_roulette_offset_increment(n, A) : deepaco_tsp_sample_offset_increment(n, A, a->start_node);
     const size_t cnt = (size_t)B * n * n;
     if (n_iterations > 0 && !a->product_valid) {
         hadamard2_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 8), 256, 0, st>>>(a->pheromone, a->heuristic,
@@ -140,7 +140,9 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
     for (int it = 0; it < n_iterations; ++it) {
         if (a->ev_sample_begin) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_begin, st));
         int fused = 0;
-        int rc = tsp_sample_fused(a->product, n, A, B, a->start_node, a->double_norm, a->seed, a->offset + (uint64_t)it * inc,
+        int rc = a->roulette ? deepaco_tsp_roulette_sample(a->product, n, A, B, a->start_node, a->seed, a->offset + (uint64_t)it * inc,
+                                                           a->offsets, a->tours, nullptr, st)
+                             : tsp_sample_fused(a->product, n, A, B, a->start_node, a->double_norm, a->seed, a->offset + (uint64_t)it * inc,
                                   a->offsets, a->tours, a->knn, a->local_search ? nullptr : a->distances, a->costs, a->neighbours,
                                   &fused, st);
         if (rc) return rc;

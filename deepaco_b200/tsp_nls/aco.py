@@ -29,13 +29,33 @@ class ACO(_TspACO):
 
     # ---- sampling ----------------------------------------------------------------------------
     def sample(self, inference=False):
-        '''tsp_nls/aco.py:80-90.  inference=True replaces the numba roulette sampler (whose RNG is numba's own,
-        not reproducible from torch) by the same on-device Categorical construction without log-probs.'''
+        '''tsp_nls/aco.py:80-90.  inference=True: the roulette-wheel sampler of `inference_batch_sample` (:81-85) on the
+        device (deepaco_tsp_roulette_sample), start node 0, no log-probs; its uniforms come from the default CUDA
+        generator (the reference's come from numba's private generator: statistical parity).'''
         if inference:
-            paths = self.gen_path(require_prob=False)
+            paths = self._roulette_paths()
             return self.gen_path_costs(paths), None, paths
         paths, log_probs = self.gen_path(require_prob=True)
         return self.gen_path_costs(paths), log_probs, paths
+
+    @torch.no_grad()
+    def _roulette_paths(self):
+        ph, heu = self._weights()
+        probmat = (ph.detach() * heu.detach()).to(torch.float32)              # tsp_nls/aco.py:82
+        gen, seed, offset = generator_state(self.device)
+        paths, _ = E.tsp_roulette_sample(probmat, self.n_ants, start_node=0, seed=seed, offset=offset)
+        gen.set_offset(offset + E.tsp_roulette_offset_increment(self.problem_size, self.n_ants))
+        return paths
+
+    @property
+    def distances_numpy(self):
+        '''tsp_nls/aco.py:222-224 (host copy for callers that want it; nothing in this class computes on it).'''
+        return self.distances.detach().cpu().numpy().astype("float32")
+
+    @property
+    def heuristic_numpy(self):
+        '''tsp_nls/aco.py:226-228.'''
+        return self.heuristic.detach().cpu().numpy().astype("float32")
 
     def gen_numpy_path_costs(self, paths, numpy_distances):
         '''tsp_nls/aco.py:171-182: closed-tour lengths of host tours, paths numpy [n_ants, problem_size] (note the
@@ -93,9 +113,11 @@ class ACO(_TspACO):
         r = self._runner
         r.set_local_search(self.local_search_type, self._max_passes(inference),
                            self.heuristic_dist if self.local_search_type == "nls" else None)
+        r.roulette = bool(inference)            # tsp_nls/aco.py:106-110: inference constructs with the roulette sampler
         gen, seed, offset = generator_state(self.device)
         r.run(n_iterations, seed, offset)
-        gen.set_offset(offset + n_iterations * r.increment)
+        inc = E.tsp_roulette_offset_increment(self.problem_size, self.n_ants) if inference else r.increment
+        gen.set_offset(offset + n_iterations * inc)
         self._pheromone = r.pheromone[0].clone()
         self._shortest_path = r.shortest_path[0].clone()
         self._lowest_cost = float(r.lowest_cost[0].item())
@@ -107,7 +129,7 @@ class ACO(_TspACO):
         '''The same iteration composed from the per-step methods (one host read of the best cost per iteration, as the
         reference has at tsp_nls/aco.py:120); used when alpha / beta are not 1.'''
         for _ in range(n_iterations):
-            paths = self.local_search(self.gen_path(require_prob=False), inference)
+            paths = self.local_search(self._roulette_paths() if inference else self.gen_path(require_prob=False), inference)
             costs = self.gen_path_costs(paths)
             best = torch.argmin(costs)
             best_cost = float(costs[best].item())
@@ -120,3 +142,18 @@ class ACO(_TspACO):
                     self.max = new_max
             self.update_pheronome(paths, costs)
         return self._lowest_cost
+
+
+def inference_batch_sample(probmat, count=1, startnode=None):
+    '''tsp_nls/aco.py:277-297: `count` roulette-wheel tours over the numpy matrix `probmat` [n, n] -> uint16 [count, n]
+    (startnode None: uniform random start per tour; an int: that start).  Runs deepaco_tsp_roulette_sample on the
+    current CUDA device with the default CUDA generator; host arrays in and out like the reference function.'''
+    import numpy as np
+    dev = torch.device("cuda", torch.cuda.current_device())
+    prob = torch.as_tensor(np.asarray(probmat, dtype=np.float32), device=dev)
+    n = prob.shape[0]
+    gen, seed, offset = generator_state(dev)
+    _, tours = E.tsp_roulette_sample(prob, int(count), start_node=-1 if startnode is None else int(startnode), seed=seed,
+                                     offset=offset, want_paths=False, want_tours=True)
+    gen.set_offset(offset + E.tsp_roulette_offset_increment(n, int(count)))
+    return tours.cpu().numpy()

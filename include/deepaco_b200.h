@@ -136,6 +136,8 @@ typedef struct {
     const float* heuristic_dist; /* NLS only: [B][n][n], 1 / (heuristic / rowmax + 1e-5), tsp_nls/aco.py:230-232 */
     void* ev_sample_begin; /* optional cudaEvent_t recorded before / after each sampling launch (profiling) */
     void* ev_sample_end;
+    int roulette;          /* 1: construct with the roulette-wheel sampler (run(.., inference=True), tsp_nls/aco.py:106-110);
+                              iteration t then consumes the Philox stream at offset + t * deepaco_tsp_roulette_offset_increment() */
 } deepaco_tsp_run_args;
 int deepaco_tsp_run(const deepaco_tsp_run_args* args, int n_iterations, void* stream);
 /* Same with HOST matrices ([B][n][n] fp32 each) -- `ACO(distances, heuristic=...).run(T)` for a caller whose data lives
@@ -148,6 +150,17 @@ int deepaco_tsp_run(const deepaco_tsp_run_args* args, int n_iterations, void* st
 int deepaco_tsp_run_host(const deepaco_tsp_run_args* args, int n_iterations, const float* distances_host,
                          const float* heuristic_host, float* pheromone_host, float* lowest_cost_host,
                          int64_t* shortest_path_host, int copy_back_pheromone, void* stream);
+
+/* ---- roulette-wheel construction: the reference's INFERENCE sampler (tsp_nls/aco.py:260-297 _inference_sample /
+ * inference_batch_sample; used by sample(inference=True) :81-85 and run(.., inference=True) :106-110).
+ * prob = pheromone^alpha (.) heuristic^beta, fp32 [B][n][n].  Per step: rand = U * sum(prob[last] * mask), next = first
+ * column whose running sum reaches rand.  U comes from Philox at (seed, offset) -- the reference uses numba's private
+ * generator, so parity is statistical.  start_node >= 0: fixed start (the reference passes 0); -1: random start.
+ * Outputs (either may be NULL): tours u16 [B][A][n], paths i64 [B][n][A].  Advance the generator by
+ * deepaco_tsp_roulette_offset_increment(n, n_ants) per call. */
+int deepaco_tsp_roulette_sample(const float* prob, int n, int n_ants, int n_colonies, int start_node, uint64_t seed,
+                                uint64_t offset, const uint64_t* offsets, uint16_t* tours, int64_t* paths, void* stream);
+uint64_t deepaco_tsp_roulette_offset_increment(int n, int n_ants);
 
 /* ---- ACO.run with the ANTS of every colony split over the GPUs of one box (no reference counterpart: the reference is
  * single-device; semantics reproduced: tsp/aco.py:74-92, bit-identical to deepaco_tsp_run on one GPU for any world size).

@@ -52,6 +52,13 @@ def main():
         out[sub] = {
             "ACO": {k: v for k, v in methods(aco.ACO).items() if k not in skip},
             "ACO_attributes": sorted(k for k in vars(inst) if not k.startswith("_")),
+            # properties / cached properties of the class (tsp_nls: distances_numpy, heuristic_numpy, heuristic_dist)
+            "ACO_properties": sorted(k for k, v in vars(aco.ACO).items()
+                                     if not k.startswith("_") and (isinstance(v, property) or type(v).__name__ == "cached_property")),
+            # public module-level functions of aco.py (tsp_nls: inference_batch_sample)
+            "aco_functions": {k: params(v) for k, v in vars(aco).items()
+                              if not k.startswith("_") and callable(v) and getattr(v, "__module__", None) == aco.__name__
+                              and not inspect.isclass(v)},
             "Net": methods(net.Net),
             "Net_state_dict_keys": sorted(net.Net().state_dict().keys()),
             "utils": {k: params(v) for k, v in vars(utils).items()

@@ -60,3 +60,14 @@ def test_utils_functions(sub):
     for name, want in SURFACE[sub]["utils"].items():
         assert hasattr(utils, name), (sub, name)
         assert _params(getattr(utils, name)) == want, (sub, name)
+
+
+@pytest.mark.parametrize("sub", ["tsp", "tsp_nls", "cvrp"])
+def test_aco_properties_and_module_functions(sub):
+    """Properties of the reference class (tsp_nls: distances_numpy / heuristic_numpy / heuristic_dist) and the public
+    module-level functions of aco.py (tsp_nls: inference_batch_sample) exist with the reference's parameters."""
+    mod = importlib.import_module(f"deepaco_b200.{sub}.aco")
+    for name in SURFACE[sub]["ACO_properties"]:
+        assert isinstance(_lookup(mod.ACO, name), property) or type(_lookup(mod.ACO, name)).__name__ == "cached_property", (sub, name)
+    for name, want in SURFACE[sub]["aco_functions"].items():
+        assert _params(getattr(mod, name)) == want, (sub, name)
