@@ -35,6 +35,20 @@ def _offsets(offsets, B, dev):
 KNN_WIDTH = 32
 
 
+def state_key(*objs):
+    """Fingerprint of the tensors / scalars a cached runner was built from: (storage address, version counter, shape)
+    per tensor, the value per Python scalar.  A caller that rebinds or mutates `aco.pheromone`, `aco.heuristic`,
+    `aco.lowest_cost` ... between run() calls changes it, and run() then restarts from the new state, as the reference
+    (which keeps no cached state) does."""
+    key = []
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            key.append((o.data_ptr(), o._version, tuple(o.shape)))
+        else:
+            key.append(o)
+    return tuple(key)
+
+
 def sparse_candidates(heuristic, ratio=1e-6):
     """Candidate lists for the kNN sampling kernel: uint8 [..., n, 32] = columns of the 32 largest heuristic
     values per row, or None when the heuristic is not sparse (the 33rd largest value of a typical row is not

@@ -63,6 +63,7 @@ class ACO:
         self.lowest_cost = float('inf')
         self.device = distances.device if str(device) == 'cpu' else torch.device(device)
         self._runner = None
+        self._runner_key = None
 
     def sample(self):
         paths, log_probs = self.gen_path(require_prob=True)
@@ -138,6 +139,8 @@ class ACO:
         iteration; the generator offset (data dependent: one draw per step of the slowest ant) is read back once.'''
         if self.alpha != 1 or self.beta != 1:
             return self._run_stepwise(n_iterations)
+        if self._runner is not None and self._runner_key != self._state_key():
+            self._runner = None             # pheromone / heuristic / lowest_cost / ... were replaced or mutated since
         if self._runner is None:
             r = E.CvrpRunner(self.distances, self.demand, self.heuristic, self.pheromone, self.n_ants,
                              capacity=self.capacity, decay=self.decay, elitist=self.elitist, min_max=self.min_max,
@@ -158,7 +161,12 @@ class ACO:
             self.shortest_path = r.shortest_path[0, :rows].clone()
         if self.min_max:
             self.max = r.ph_max[0].clone()
+        self._runner_key = self._state_key()
         return self.lowest_cost
+
+    def _state_key(self):
+        return E.state_key(self.pheromone, self.heuristic, self.distances, self.demand, self.lowest_cost,
+                           self.max if self.min_max else None, self.n_ants, self.decay, self.elitist, self.capacity)
 
     def _run_stepwise(self, n_iterations):
         for _ in range(n_iterations):

@@ -255,7 +255,8 @@ def train_buffers(B, n, E, device):
             "sync_ws": torch.zeros(B, dtype=torch.int32, device=device)}
 
 
-_EVAL_SCRATCH = {}
+_EVAL_SCRATCH = {}        # (B, n, E, device, stream) -> buffers: one set per device AND stream (stream-ordered reuse)
+_EVAL_SCRATCH_MAX = 8
 
 
 def eval_buffers(B, n, E, device):
@@ -293,9 +294,11 @@ def gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas, graph=None
         graph = train_graph(edge_index, edge_attr, n, backward=False)
     dev = x.device
     key = (B, n, graph["E"], dev, torch.cuda.current_stream(dev).cuda_stream)
-    if _EVAL_SCRATCH.get("key") != key:          # scratch is reused call after call on one stream (stream-ordered)
-        _EVAL_SCRATCH["key"], _EVAL_SCRATCH["bufs"] = key, eval_buffers(B, n, graph["E"], dev)
-    bufs = _EVAL_SCRATCH["bufs"]
+    bufs = _EVAL_SCRATCH.get(key)                # reused call after call on the SAME device and stream only
+    if bufs is None:
+        if len(_EVAL_SCRATCH) >= _EVAL_SCRATCH_MAX:
+            _EVAL_SCRATCH.pop(next(iter(_EVAL_SCRATCH)))
+        bufs = _EVAL_SCRATCH[key] = eval_buffers(B, n, graph["E"], dev)
     heu = torch.empty((B, graph["E"]), dtype=torch.float32, device=dev)
     a, keep = train_args(x.to(torch.float32).contiguous(), graph, weights, bufs, feats, ctas, 1e-5, heu_out=heu)
     with torch.cuda.device(dev):
@@ -408,6 +411,7 @@ class _GnnTrain(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib().deepaco_gnn_train_forward(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_train_forward")
         ctx.state = (flat, x, graph, bufs, feats, ctas, bn_eps, slots)
+        ctx.flat_version = flat._version        # the backward re-reads the live weight buffer: it must not have moved on
         ctx.mark_non_differentiable(bufs["stats"])
         return heu, bufs["stats"]
 
@@ -415,6 +419,10 @@ class _GnnTrain(torch.autograd.Function):
     def backward(ctx, g_heu, _g_stats):
         import ctypes
         flat, x, graph, bufs, feats, ctas, bn_eps, slots = ctx.state
+        if flat._version != ctx.flat_version:
+            raise RuntimeError("one of the variables needed for gradient computation has been modified by an inplace "
+                               "operation: the network parameters changed between Net.forward and backward "
+                               "(optimizer.step / load_state_dict in between?)")
         dev = x.device
         g_heu = g_heu.to(torch.float32).contiguous()
         grad = torch.zeros((graph["B"] * ctas, flat.numel()), dtype=torch.float32, device=dev)

@@ -167,6 +167,7 @@ class ACO:
     @torch.no_grad()
     def run(self, n_iterations):
         '''tsp/aco.py:74-92 for n_iterations, entirely on the device; returns lowest_cost (0-d tensor).'''
+        self._check_runner()
         if self._runner is None:
             self._runner = self._make_runner()
         r = self._runner
@@ -181,7 +182,18 @@ class ACO:
         self._shortest_path = r.shortest_path[0].clone()
         if self.min_max:
             self.max = r.ph_max[0].clone()
+        self._runner_key = self._state_key()
         return self._lowest_cost
+
+    def _state_key(self):
+        return E.state_key(self._pheromone, self.heuristic, self.distances, self._lowest_cost,
+                           self.max if self.min_max else None, self.n_ants, self.decay, self.elitist)
+
+    def _check_runner(self):
+        """Drop the cached device state when anything it was built from has been rebound or mutated in place since the
+        last run() (`aco.heuristic = ...`, `aco.pheromone.mul_(2)`, `aco.n_ants = ...`): the reference keeps no cache."""
+        if self._runner is not None and getattr(self, "_runner_key", None) != self._state_key():
+            self._runner = None
 
     def _run_stepwise(self, n_iterations):
         for _ in range(n_iterations):

@@ -106,8 +106,12 @@ class ACO(_TspACO):
         '''tsp_nls/aco.py:104-129 on the device: construction, local search (2-opt / NLS), cost, best tracking and
         pheromone update of every iteration are enqueued without a host round trip (the reference crosses to the CPU
         for the numba local search each iteration).  Returns lowest_cost as a Python float like the reference (:120).'''
-        if self.alpha != 1 or self.beta != 1:
-            return self._run_stepwise(n_iterations, inference)     # general exponents: torch.pow supplies the powers
+        if self.alpha != 1 or self.beta != 1 or self.min_max:
+            # general exponents: torch.pow supplies the powers.  min_max: the reference keeps lowest_cost as a Python float
+            # (:120), so max = n / lowest is computed in double and the MMAS rescale is reciprocal(ph.max()) * scalar --
+            # the stepwise path reproduces exactly that; the device loop's fp32 bookkeeping is the tsp/ variant.
+            return self._run_stepwise(n_iterations, inference)
+        self._check_runner()
         if self._runner is None:
             self._runner = self._make_runner()
         r = self._runner
@@ -121,8 +125,7 @@ class ACO(_TspACO):
         self._pheromone = r.pheromone[0].clone()
         self._shortest_path = r.shortest_path[0].clone()
         self._lowest_cost = float(r.lowest_cost[0].item())
-        if self.min_max:
-            self.max = r.ph_max[0].clone()
+        self._runner_key = self._state_key()
         return self._lowest_cost
 
     def _run_stepwise(self, n_iterations, inference=False):

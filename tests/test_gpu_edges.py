@@ -112,3 +112,54 @@ def test_ant_sharded_cuda_backend_is_world_size_invariant_and_matches_reference(
     ref.run(4)
     assert np.array_equal(ref.pheromone.cpu().numpy(), one[0][0])
     assert float(ref.lowest_cost) == one[0][1]
+
+
+def test_run_restarts_from_state_rebound_or_mutated_between_calls():
+    """The reference keeps no cached device state: `aco.heuristic = X`, `aco.pheromone = Y`, an in-place edit of either,
+    or `aco.lowest_cost = c` between run() calls take effect on the next call (tsp/, tsp_nls/ and cvrp/ alike)."""
+    from deepaco_b200.cvrp.aco import ACO as CvrpACO
+    from deepaco_b200.cvrp.utils import gen_instance
+    from deepaco_b200.tsp.aco import ACO as TspACO
+    torch.manual_seed(1)
+    n = 40
+    xy = torch.rand(n, 2, device=DEV)
+    d = torch.norm(xy[:, None] - xy, dim=2, p=2)
+    d[torch.arange(n), torch.arange(n)] = 1e9
+    heu2 = torch.rand(n, n, device=DEV) + 0.1
+
+    def tsp_case(edit):
+        torch.manual_seed(5)
+        a = TspACO(d, n_ants=16, device=DEV)
+        a.run(2)
+        edit(a)
+        a.run(2)
+        torch.manual_seed(5)
+        b = TspACO(d, n_ants=16, device=DEV)
+        b.run(2)
+        edit(b)
+        b._runner = None                                   # what a fresh runner built from the edited state gives
+        b.run(2)
+        assert torch.equal(a.pheromone, b.pheromone) and float(a.lowest_cost) == float(b.lowest_cost)
+        return a
+
+    tsp_case(lambda a: setattr(a, "heuristic", heu2))
+    tsp_case(lambda a: a.heuristic.mul_(heu2))
+    tsp_case(lambda a: a.pheromone.fill_(1.0))
+    demand, dist = gen_instance(20, DEV)
+
+    def cvrp_case(edit):
+        out = []
+        for drop in (False, True):
+            torch.manual_seed(9)
+            a = CvrpACO(dist, demand, n_ants=16, device=DEV)
+            a.run(2)
+            edit(a)
+            if drop:
+                a._runner = None
+            a.run(2)
+            out.append((a.pheromone.clone(), float(a.lowest_cost)))
+        assert torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+
+    cvrp_case(lambda a: setattr(a, "pheromone", torch.ones_like(dist)))
+    cvrp_case(lambda a: setattr(a, "heuristic", torch.rand_like(dist) + 0.1))
+    cvrp_case(lambda a: setattr(a, "lowest_cost", float("inf")))

@@ -164,3 +164,19 @@ def test_train_mode_rejects_cpu_tensors_and_frozen_backbone_gets_no_gradient():
         before = net.emb_net.v_bns[0].module.num_batches_tracked.item()
         out = net(pyg)
         assert not out.requires_grad and net.emb_net.v_bns[0].module.num_batches_tracked.item() == before + 1
+
+
+def test_backward_after_an_in_place_parameter_update_raises_like_autograd():
+    """The backward kernel re-reads the live packed weights; stock autograd raises its version-counter error when a
+    tensor saved for backward was modified in place (optimizer.step between forward and backward) -- so does this."""
+    from deepaco_b200.tsp.utils import gen_pyg_data
+    net = _net("tsp")
+    pyg = gen_pyg_data(torch.rand(30, 2, device=DEV), 6)[0]
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+    net(pyg).sum().backward()                       # populates .grad
+    loss = net(pyg).sum()
+    opt.step()                                      # in-place update of the parameters the graph of `loss` refers to
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        loss.backward()
+    net.zero_grad()
+    net(pyg).sum().backward()                       # a fresh forward / backward pair is fine again
