@@ -247,6 +247,8 @@ class TspRunner:
         # optional local search between construction and cost (tsp_nls): 0 none, 1 2-opt, 2 NLS
         self.local_search, self.ls_max_iterations, self.T_nls, self.T_p, self.heuristic_dist = 0, 0, 10, 20, None
         self.roulette = False           # True: roulette-wheel construction (tsp_nls run(.., inference=True))
+        # candidate lists are re-derived from the product matrix every `knn_refresh` iterations (the runner owns `knn`)
+        self.knn_refresh, self.iterations_done = 4, 0
 
     def set_local_search(self, mode, max_iterations, heuristic_dist=None, T_nls=10, T_p=20):
         self.local_search = {None: 0, "2opt": 1, "nls": 2}[mode]
@@ -266,7 +268,8 @@ class TspRunner:
                                int(self.product_valid), ptr(self.tours), ptr(self.costs), ptr(self.neighbours),
                                ptr(self.lowest_cost), ptr(self.shortest_path), ptr(self.ph_max), ptr(self.scale), ptr(self.knn),
                                self.local_search, self.ls_max_iterations, self.T_nls, self.T_p, ptr(self.heuristic_dist),
-                               ev0, ev1, int(self.roulette))
+                               ev0, ev1, int(self.knn_refresh if self.knn is not None else 0), int(self.iterations_done),
+                               int(self.roulette))
 
     def run(self, n_iterations, seed, offset=0, offsets=None, sample_events=None):
         """Launch n_iterations ACO iterations; colony b consumes offsets[b] + offset + t * self.increment.
@@ -277,6 +280,7 @@ class TspRunner:
             check(lib().deepaco_tsp_run(C.byref(a), int(n_iterations), stream_ptr(self.dev)), "deepaco_tsp_run")
         if n_iterations > 0:
             self.product_valid = True
+        self.iterations_done += int(n_iterations)
         return self.lowest_cost
 
     def run_shard(self, n_iterations, seed, peer, ant_base, n_ants_local, epoch, status, timeout_ms=2000, *, offset=0,
@@ -296,6 +300,7 @@ class TspRunner:
                   "deepaco_tsp_run_shard")
         if n_iterations > 0:
             self.product_valid = True
+        self.iterations_done += int(n_iterations)
         return self.lowest_cost
 
     def run_host(self, n_iterations, seed, distances_h, heuristic_h, pheromone_h, lowest_h, shortest_h, offset=0,
@@ -316,6 +321,7 @@ class TspRunner:
                                              stream_ptr(self.dev)),
                   "deepaco_tsp_run_host")
         self.product_valid = n_iterations > 0
+        self.iterations_done += int(n_iterations)
         return lowest_h
 
 

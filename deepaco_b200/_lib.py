@@ -60,7 +60,7 @@ class TspRunArgs(C.Structure):
                 ("tours", _vp), ("costs", _vp), ("neighbours", _vp), ("lowest_cost", _vp), ("shortest_path", _vp),
                 ("ph_max", _vp), ("scale", _vp), ("knn", _vp), ("local_search", _i32), ("ls_max_iterations", _i32),
                 ("T_nls", _i32), ("T_p", _i32), ("heuristic_dist", _vp), ("ev_sample_begin", _vp), ("ev_sample_end", _vp),
-                ("roulette", _i32)]
+                ("knn_refresh", _i32), ("knn_iteration0", _i32), ("roulette", _i32)]
 
 
 class ShardArgs(C.Structure):

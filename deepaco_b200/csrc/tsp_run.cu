@@ -20,6 +20,7 @@ int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float*
                       const float* heuristic, float* product, cudaStream_t st);
 int tsp_cost_launch(const float* distances, const uint16_t* tours, int n, int n_ants, int n_colonies, float* costs,
                     uint32_t* neighbours, cudaStream_t st);
+int knn_refresh_launch(const float* product, uint8_t* knn, int n, int n_colonies, cudaStream_t st);
 int tsp_sample_fused(const float* product, int n, int n_ants, int n_colonies, int start_node, int double_norm, uint64_t seed,
                      uint64_t offset, const uint64_t* offsets, uint16_t* tours, const uint8_t* knn, const float* dist, float* costs,
                      uint32_t* nbr, int* fused, cudaStream_t st);
@@ -165,6 +166,10 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
         rc = tsp_update_launch(a->pheromone, a->neighbours, a->costs, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min,
                                a->ph_max, a->min_max ? a->scale : nullptr, a->heuristic, a->product, st);
         if (rc) return rc;
+        if (a->knn && a->knn_refresh > 0 && n > 32 && n <= 256 && (a->knn_iteration0 + it + 1) % a->knn_refresh == 0) {
+            rc = knn_refresh_launch(a->product, const_cast<uint8_t*>(a->knn), n, B, st);
+            if (rc) return rc;
+        }
     }
     return DEEPACO_OK;
 }

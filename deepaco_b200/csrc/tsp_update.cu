@@ -64,6 +64,13 @@ static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const
 }
 
 namespace deepaco {
+int knn_refresh_launch(const float* product, uint8_t* knn, int n, int n_colonies, cudaStream_t st) {
+    DACO_CHECK_ARG(n > 32 && n <= 256, "knn refresh: 32 < n <= 256");
+    const int rows = n * n_colonies;
+    knn_refresh_kernel<<<(rows + 7) / 8, 256, 0, st>>>(product, knn, n, rows);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
 int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float* costs, int n, int n_ants, int n_colonies,
                       float decay, int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
                       const float* heuristic, float* product, cudaStream_t st) {

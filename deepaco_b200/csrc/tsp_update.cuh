@@ -202,6 +202,39 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
     }
 }
 
+// Candidate lists for the kNN construction kernel, re-derived from the CURRENT product matrix: columns of the 32 largest
+// entries of every row (ties: lower column first), in any order.  The lists are only a performance hint -- the kernel
+// bounds the unlisted columns by their actual maximum -- but as the pheromone evolves, edges outside the heuristic's
+// top 32 get reinforced and lists taken from the heuristic alone send more and more steps to the dense fallback.
+// One warp per row, n <= 256: rank of an entry = number of entries that beat it.
+__global__ void __launch_bounds__(256) knn_refresh_kernel(const float* __restrict__ prod, uint8_t* __restrict__ knn, int n,
+                                                          int rows_total) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows_total) return;
+    const float* P = prod + (size_t)row * n;
+    const int K = (n + 31) >> 5;
+    float v[8];
+    int rank[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = lane + 32 * k;
+        v[k] = (k < K && idx < n) ? P[idx] : -1.0f;
+        rank[k] = 0;
+    }
+    for (int j = 0; j < n; ++j) {
+        const float pj = P[j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < K) rank[k] += (pj > v[k] || (pj == v[k] && j < lane + 32 * k)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = lane + 32 * k;
+        if (k < K && idx < n && rank[k] < 32) knn[(size_t)row * 32 + rank[k]] = (uint8_t)idx;
+    }
+}
+
 // Same update for colonies with MANY ants (thousands: the ant-sharded path), where a row's 2A deposit events are too
 // many for one warp: one CTA per matrix row.  Ants are processed in chunks of `CH` (ant order, so the per-cell add order
 // is kept across chunks); inside a chunk warp w owns a contiguous ant range and buckets its events by cell into its own

@@ -411,7 +411,8 @@ class _GnnTrain(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib().deepaco_gnn_train_forward(ctypes.byref(a), stream_ptr(dev)), "deepaco_gnn_train_forward")
         ctx.state = (flat, x, graph, bufs, feats, ctas, bn_eps, slots)
-        ctx.flat_version = flat._version        # the backward re-reads the live weight buffer: it must not have moved on
+        ctx.save_for_backward(*params)          # the backward re-reads the live weights (the parameters alias `flat`):
+                                                # autograd's version check on the saved parameters catches in-place updates
         ctx.mark_non_differentiable(bufs["stats"])
         return heu, bufs["stats"]
 
@@ -419,10 +420,7 @@ class _GnnTrain(torch.autograd.Function):
     def backward(ctx, g_heu, _g_stats):
         import ctypes
         flat, x, graph, bufs, feats, ctas, bn_eps, slots = ctx.state
-        if flat._version != ctx.flat_version:
-            raise RuntimeError("one of the variables needed for gradient computation has been modified by an inplace "
-                               "operation: the network parameters changed between Net.forward and backward "
-                               "(optimizer.step / load_state_dict in between?)")
+        _ = ctx.saved_tensors                   # raises "... modified by an inplace operation" if a parameter changed since
         dev = x.device
         g_heu = g_heu.to(torch.float32).contiguous()
         grad = torch.zeros((graph["B"] * ctas, flat.numel()), dtype=torch.float32, device=dev)

@@ -136,6 +136,10 @@ typedef struct {
     const float* heuristic_dist; /* NLS only: [B][n][n], 1 / (heuristic / rowmax + 1e-5), tsp_nls/aco.py:230-232 */
     void* ev_sample_begin; /* optional cudaEvent_t recorded before / after each sampling launch (profiling) */
     void* ev_sample_end;
+    int knn_refresh;       /* R > 0: after every R-th iteration (counted from knn_iteration0) the candidate lists `knn` are
+                              REWRITTEN in place from the current product matrix (columns of each row's 32 largest
+                              entries); a pure performance measure, results do not depend on it.  0: lists stay as given */
+    int knn_iteration0;    /* iterations already run on these lists (the caller's running count) */
     int roulette;          /* 1: construct with the roulette-wheel sampler (run(.., inference=True), tsp_nls/aco.py:106-110);
                               iteration t then consumes the Philox stream at offset + t * deepaco_tsp_roulette_offset_increment() */
 } deepaco_tsp_run_args;

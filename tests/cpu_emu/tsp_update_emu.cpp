@@ -77,6 +77,15 @@ extern "C" const char* emu_tsp_update_rows(float* ph, const uint32_t* nbr, const
     return nullptr;
 }
 
+// knn_refresh_kernel: candidate lists (columns of the 32 largest entries per row) from a product matrix [rows][n]
+extern "C" const char* emu_knn_refresh(const float* prod, uint8_t* knn, int n, int rows) {
+    if (!prod || !knn || n <= 32 || n > 256 || rows < 1) return "bad arguments";
+    struct A { const float* p; uint8_t* k; int n, rows; };
+    const A a{prod, knn, n, rows};
+    emu::launch([](const A& q) { knn_refresh_kernel(q.p, q.k, q.n, q.rows); }, a, (rows + 7) / 8, 1, 256, 16);
+    return nullptr;
+}
+
 // ---- CVRP (one colony per call) ----
 namespace {
 struct CvrpCostArgs {

@@ -125,6 +125,24 @@ def test_row_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, 
     assert torch.equal(prod, ph * heu)
 
 
+@pytest.mark.parametrize("n,rows", [(33, 5), (100, 100), (256, 19)])
+def test_knn_refresh_kernel_on_host_selects_the_32_largest_per_row(emu_u, n, rows):
+    """knn_refresh_kernel: per row the columns of the 32 largest product entries, ties to the lower column (the floor
+    entries of a sparse product are all equal), 32 distinct columns in any order."""
+    emu_u.emu_knn_refresh.restype = ctypes.c_char_p
+    emu_u.emu_knn_refresh.argtypes = [vp, vp, ci, ci]
+    torch.manual_seed(n)
+    prod = torch.full((rows, n), 1e-10)
+    for r in range(rows):                                   # 5 .. 40 distinct large entries per row, the rest tied at the floor
+        k = 5 + (7 * r) % 36
+        prod[r, torch.randperm(n)[:k]] = torch.rand(k) + 0.01
+    prod = prod.contiguous()
+    knn = torch.full((rows, 32), 255, dtype=torch.uint8)
+    assert emu_u.emu_knn_refresh(_ptr(prod), _ptr(knn), n, rows) is None
+    order = torch.argsort(prod, dim=1, descending=True, stable=True)[:, :32]        # stable: ties keep column order
+    assert torch.equal(torch.sort(knn.long(), dim=1).values, torch.sort(order, dim=1).values)
+
+
 # ---- CVRP: open-path cost, one-directional deposit, repeated (0, 0) pairs count once, 1e-10 floor ------------------
 @pytest.fixture(scope="session")
 def emu_c(emu_u):
