@@ -352,8 +352,9 @@ uint64_t deepaco_pick_move_offset_increment(int n, int n_ants);
 /* ---- backward of the log-probabilities (ACO.sample -> REINFORCE loss; tsp/aco.py:165-177, cvrp/aco.py:167-174)
  * Analytic gradient of sum_{t,a} grad_log_probs[t][a] * log_probs[t][a] with respect to the (powered) heuristic
  * and optionally the (powered) pheromone, by replaying the paths (int64 [path_rows][n_ants]).  demand = NULL:
- * TSP masks; demand != NULL: CVRP visit + capacity masks.  Gradients are ACCUMULATED (fp32 atomics) into
- * grad_heuristic / grad_pheromone ([n][n], caller zeroes; grad_pheromone may be NULL). */
+ * TSP masks; demand != NULL: CVRP visit + capacity masks.  Gradients are ACCUMULATED into grad_heuristic /
+ * grad_pheromone ([n][n], caller zeroes; grad_pheromone may be NULL) in a fixed order per matrix element (ants
+ * ascending, steps ascending; no atomics): the result is bit-identical run to run. */
 int deepaco_logp_backward(const float* pheromone_pow, const float* heuristic_pow, const int64_t* paths,
                           const float* grad_log_probs, int n, int n_ants, int path_rows, const float* demand,
                           float capacity, float* grad_heuristic, float* grad_pheromone, void* stream);

@@ -3,6 +3,7 @@
 #include "cuda_emu.h"
 
 #include <algorithm>
+#include <vector>
 #include <cmath>
 using std::min;
 
@@ -114,11 +115,18 @@ extern "C" const char* emu_cvrp_update(float* ph, const uint32_t* nbr, const flo
     return nullptr;
 }
 
-// ---- analytic backward of the log-probabilities (deepaco_logp_backward) ----
+// ---- analytic backward of the log-probabilities (deepaco_logp_backward): prepare + ordered row accumulation ----
 extern "C" const char* emu_logp_backward(const float* ph, const float* heu, const int64_t* paths, const float* glogp, int n, int A,
                                          int rows, const float* demand, float capacity, float* g_heu, float* g_ph) {
     if (!ph || !heu || !paths || !glogp || !g_heu || n < 2 || A < 1 || rows < 2) return "bad arguments";
-    const BackwardParams p{ph, heu, paths, glogp, g_heu, g_ph, demand, capacity, n, A, rows};
-    emu::launch(logp_backward_kernel, p, (A + 7) / 8, 1, 256, 16);
+    const size_t steps = (size_t)(rows - 1) * A;
+    std::vector<float> coef(steps), gact(steps), rem(steps);
+    std::vector<uint8_t> dok(steps);
+    std::vector<uint16_t> when((size_t)A * n, 0xffff), dsteps((size_t)A * rows);
+    std::vector<int32_t> dcnt(A);
+    const BackwardParams p{ph, heu, paths, glogp, g_heu, g_ph, demand, capacity, n, A, rows, coef.data(), gact.data(), rem.data(),
+                           dok.data(), when.data(), dsteps.data(), dcnt.data()};
+    emu::launch(logp_backward_prepare_kernel, p, (A + 7) / 8, 1, 256, 16);
+    emu::launch(logp_backward_rows_kernel, p, n, 1, 128, 16);
     return nullptr;
 }

@@ -1,5 +1,6 @@
 """sample() backward: analytic gradient kernel vs autograd through the op-for-op oracle on the same
-GPU, same seed (hence same paths).  fp32 tolerance: both sides accumulate with atomics."""
+GPU, same seed (hence same paths).  fp32 tolerance against autograd (whose scatter is atomic); the kernel itself
+accumulates in a fixed order and is bit-identical run to run."""
 import pytest
 import torch
 
@@ -128,3 +129,33 @@ def test_train_instance_parameter_gradients_match_reference_pipeline():
     assert checked > 50
     opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
     opt.step()                                              # the optimiser step of train_instance runs
+
+
+@pytest.mark.parametrize("problem", ["tsp", "cvrp"])
+def test_logp_backward_is_bit_identical_run_to_run(problem):
+    """deepaco_logp_backward adds every matrix element's contributions in a fixed order (ants ascending, steps
+    ascending; no atomics): many ants, repeated calls -> identical bits, for the heuristic and the pheromone gradient."""
+    from deepaco_b200 import _engine as E
+    if problem == "tsp":
+        n, A = 100, 512
+        d, heu = _tsp(n, 11)
+        ph = torch.rand(n, n, device=DEV) + 0.5
+        torch.manual_seed(3)
+        paths = O.tsp_gen_path(ph, heu, A)
+        demand, cap = None, 0.0
+    else:
+        n, A = 61, 256
+        torch.manual_seed(6)
+        allc = torch.cat((torch.tensor([[0.5, 0.5]], device=DEV), torch.rand(n - 1, 2, device=DEV)))
+        d = torch.norm(allc[:, None] - allc, dim=2, p=2)
+        d[torch.arange(n), torch.arange(n)] = 1e-10
+        demand = torch.cat((torch.zeros(1, device=DEV), torch.randint(1, 10, (n - 1,), device=DEV).float()))
+        heu = torch.rand(n, n, device=DEV) * 0.98 + 1e-10
+        ph = torch.rand(n, n, device=DEV) + 0.5
+        paths = O.cvrp_gen_path(ph, heu, demand, 50, A)
+        cap = 50.0
+    g = torch.randn(paths.shape[0] - 1, A, device=DEV)
+    runs = [E.logp_backward(ph, heu, paths, g, demand=demand, capacity=cap, want_pheromone_grad=True) for _ in range(4)]
+    for gh, gp in runs[1:]:
+        assert torch.equal(gh, runs[0][0]) and torch.equal(gp, runs[0][1])
+    assert torch.isfinite(runs[0][0]).all() and (runs[0][0] != 0).any()
