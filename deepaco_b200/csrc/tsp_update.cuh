@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
 // entries of every row (ties: lower column first), in any order.  The lists are only a performance hint -- the kernel
 // bounds the unlisted columns by their actual maximum -- but as the pheromone evolves, edges outside the heuristic's
 // top 32 get reinforced and lists taken from the heuristic alone send more and more steps to the dense fallback.
-// One warp per row, n <= 256: rank of an entry = number of entries that beat it.
+// One warp per row, n <= 256, entries >= 0: the bit pattern of a non-negative float is monotonic in its value, so the
+// 32nd largest value is found by a 31-step bisection on the bits (count of entries >= trial via ballots); everything
+// above it is listed, and the remaining places go to the entries equal to it in column order.
 __global__ void __launch_bounds__(256) knn_refresh_kernel(const float* __restrict__ prod, uint8_t* __restrict__ knn, int n,
                                                           int rows_total) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,24 +216,44 @@ __global__ void __launch_bounds__(256) knn_refresh_kernel(const float* __restric
     if (row >= rows_total) return;
     const float* P = prod + (size_t)row * n;
     const int K = (n + 31) >> 5;
-    float v[8];
-    int rank[8];
+    uint32_t v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int idx = lane + 32 * k;
-        v[k] = (k < K && idx < n) ? P[idx] : -1.0f;
-        rank[k] = 0;
+        const int idx = lane + 32 * k;                     // column of slot k; padding slots never qualify (trial >= 1)
+        v[k] = (k < K && idx < n) ? __float_as_uint(fmaxf(P[idx], 0.f)) : 0u;
     }
-    for (int j = 0; j < n; ++j) {
-        const float pj = P[j];
+    uint32_t thr = 0u;                                     // largest t with  #{v >= t} >= 32
+    for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t trial = thr | (1u << bit);
+        int cnt = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (k < K) rank[k] += (pj > v[k] || (pj == v[k] && j < lane + 32 * k)) ? 1 : 0;
+            if (k < K) cnt += __popc(__ballot_sync(DACO_FULL, v[k] >= trial));
+        if (cnt >= 32) thr = trial;
     }
+    // thr == 0: fewer than 32 positive entries -- zeros (and only real columns) fill up in column order
+    int above = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < K) above += __popc(__ballot_sync(DACO_FULL, v[k] > thr && lane + 32 * k < n));
+    int slot_hi = 0, slot_eq = above;                      // next free place for "> thr" and for "== thr" entries
+    const uint32_t lt = (1u << lane) - 1u;
+    uint8_t* out = knn + (size_t)row * 32;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int idx = lane + 32 * k;
-        if (k < K && idx < n && rank[k] < 32) knn[(size_t)row * 32 + rank[k]] = (uint8_t)idx;
+        if (k < K) {
+            const int idx = lane + 32 * k;
+            const bool real = idx < n;
+            const uint32_t hi = __ballot_sync(DACO_FULL, real && v[k] > thr);
+            const uint32_t eq = __ballot_sync(DACO_FULL, real && v[k] == thr);
+            if (real && v[k] > thr) out[slot_hi + __popc(hi & lt)] = (uint8_t)idx;
+            if (real && v[k] == thr) {
+                const int pos = slot_eq + __popc(eq & lt);
+                if (pos < 32) out[pos] = (uint8_t)idx;
+            }
+            slot_hi += __popc(hi);
+            slot_eq += __popc(eq);
+        }
     }
 }
 
