@@ -170,6 +170,15 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    if world > 1:
+        # one process per GPU: run on (and take pinned memory from) the CPUs / NUMA node next to this rank's GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
     if world > 1:
         dist_pg.init_process_group("nccl", device_id=dev)
     B, K, W = args.colonies, args.steps, max(args.warmup, 3)
@@ -331,6 +340,10 @@ def main():
                           "best_tour_identical": bool(torch.equal(mine.shortest_path, ref.shortest_path))}
     except Exception as exc:      # the oracle is test infrastructure; its absence must not break the bench
         line["parity"] = {"error": str(exc)[:200]}
+    try:
+        os.sched_setaffinity(0, all_cpus)       # the CPU baseline may use every host core
+    except Exception:
+        pass
     if not args.no_cpu_baseline:
         line["reference_cuda"] = L.guarded("reference_cuda", L.leg_reference_cuda, dev)
         cb, _, _ = cpu_reference_throughput(100, 2)

@@ -117,3 +117,97 @@ def test_pick_move_log_probs_carry_the_gradient_to_the_heuristic():
     assert none is None
     with pytest.raises(IndexError):
         aco.pick_move(torch.full((A,), n, device=DEV), mask, False)
+
+
+def _categorical_step(ph, heu, prev, mask, mask2, alpha, beta, require_prob):
+    """The statements every reference pick_move / pick_node consists of (op/aco.py:190-197, sop/aco.py:158-170)."""
+    from torch.distributions import Categorical
+    d = (ph[prev] ** alpha) * (heu[prev] ** beta) * mask
+    if mask2 is not None:
+        d = d * mask2
+    dist = Categorical(d)
+    item = dist.sample()
+    return item, (dist.log_prob(item) if require_prob else None)
+
+
+def _op_update_mask(mask, cur, travel, dist, max_len):
+    """op/aco.py:199-219 (orienteering): visited nodes, nodes from which the depot cannot be reached any more, and the
+    dummy node n that absorbs finished ants -- vectorised, same result as the reference's per-ant loop."""
+    A, n1 = mask.shape
+    n = n1 - 1
+    mask = mask.clone()
+    mask[torch.arange(A, device=mask.device), cur] = 0
+    at_real = cur != n
+    trails = travel[:, None] + dist[cur][:, :n] + dist[:n, 0][None, :]
+    mask[:, :n] = torch.where(at_real[:, None] & (trails > max_len), torch.zeros_like(mask[:, :n]), mask[:, :n])
+    mask[:, -1] = 0
+    mask[(mask[:, :-1] == 0).all(dim=1), -1] = 1
+    return mask
+
+
+@pytest.mark.parametrize("style", ["op", "sop"])
+def test_other_problem_directories_run_their_own_mask_rules_through_the_step(style):
+    """The step of op/ (one mask, dummy node, travel budget) and sop/ (two masks: visited + precedence) through
+    deepaco_b200.masked.pick_move: same actions as Categorical on this GPU under the same seed, step after step, with
+    the masks updated by the caller's own rule; log-probs to fp32 rounding; same generator consumption."""
+    from deepaco_b200 import masked
+    torch.manual_seed(11)
+    n, A = 40, 24
+    xy = torch.rand(n, 2, device=DEV)
+    d = torch.norm(xy[:, None] - xy, dim=2, p=2)
+    g = torch.cuda.default_generators[0]
+    if style == "op":
+        N = n + 1                                                   # + dummy node (op/aco.py:35-44)
+        dist = torch.zeros(N, N, device=DEV)
+        dist[:n, :n] = d
+        ph = torch.rand(N, N, device=DEV) + 0.5
+        heu = torch.rand(N, N, device=DEV) + 0.05
+        max_len = 3.0
+
+        def run(step):
+            cur = torch.zeros(A, dtype=torch.long, device=DEV)
+            mask = _op_update_mask(torch.ones(A, N, device=DEV), cur, torch.zeros(A, device=DEV), dist, max_len)
+            travel = torch.zeros(A, device=DEV)
+            sol, lps = [cur], []
+            for _ in range(N):
+                if bool((mask[:, :-1] == 0).all()):
+                    break
+                nxt, lp = step(ph, heu, cur, mask, None)
+                travel = travel + dist[cur, nxt]
+                sol.append(nxt)
+                lps.append(lp)
+                cur = nxt
+                mask = _op_update_mask(mask, cur, travel, dist, max_len)
+            return torch.stack(sol), torch.stack(lps)
+    else:
+        N = n
+        ph = torch.rand(N, N, device=DEV) + 0.5
+        heu = 1.0 / (d + 0.1)
+        prec = torch.triu(torch.rand(N, N, device=DEV) < 0.05, diagonal=1)      # prec[i, j]: i must precede j
+
+        def run(step):
+            cur = torch.zeros(A, dtype=torch.long, device=DEV)
+            visited = torch.zeros(A, N, dtype=torch.bool, device=DEV)
+            visited[:, 0] = True
+            sol, lps = [cur], []
+            for _ in range(N - 1):
+                mask1 = (~visited).float()
+                pending = (prec[None, :, :] & ~visited[:, :, None]).any(dim=1)   # j still has an unvisited predecessor
+                mask2 = (~pending).float()
+                mask2[(mask1 * mask2).sum(1) == 0] = 1.0                          # never an all-zero row
+                nxt, lp = step(ph, heu, cur, mask1, mask2)
+                visited[torch.arange(A, device=DEV), nxt] = True
+                sol.append(nxt)
+                lps.append(lp)
+                cur = nxt
+            return torch.stack(sol), torch.stack(lps)
+
+    torch.manual_seed(77)
+    ref_sol, ref_lp = run(lambda *a: _categorical_step(*a, 1, 1, True))
+    ref_off = g.get_offset()
+    torch.manual_seed(77)
+    sol, lp = run(lambda p, h, prev, m1, m2: masked.pick_move(p, h, prev, m1, m2, require_prob=True))
+    assert g.get_offset() == ref_off
+    assert torch.equal(sol, ref_sol)
+    assert torch.allclose(lp, ref_lp, rtol=0, atol=2e-6)
+    assert sol.shape[0] > 3
