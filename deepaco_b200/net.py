@@ -120,16 +120,6 @@ def weight_count(feats):
     return UNITS * feats + 3 * UNITS + DEPTH * (5 * (UNITS * UNITS + UNITS) + 8 * UNITS) + 2 * (UNITS * UNITS + UNITS) + UNITS + 1
 
 
-def csr_by_source(edge_index, n_nodes):
-    """(row_ptr int32 [n+1], order int32 [E]) grouping edges by edge_index[0] (stable)."""
-    src = edge_index[0]
-    order = torch.argsort(src, stable=True)
-    counts = torch.bincount(src, minlength=n_nodes)
-    row_ptr = torch.zeros(n_nodes + 1, dtype=torch.int32, device=src.device)
-    row_ptr[1:] = torch.cumsum(counts, 0)
-    return row_ptr, order.to(torch.int32)
-
-
 def _launch_gnn(weights, feats, xin, row_ptr, dst_s, attr_s, order, want_vec, dense_eps, src_s=None):
     B, n = xin.shape[0], xin.shape[1]
     E = dst_s.shape[1]
@@ -161,13 +151,10 @@ def gnn_forward(weights, feats, x, edge_index, edge_attr, dense_eps=None, graph=
         if ctas > 1:                          # few instances: several CTAs per graph instead of one (latency)
             out = gnn_forward_group(weights, feats, x, edge_index, edge_attr, ctas, graph=graph)
             return out if batched else out[0]
-    rps, orders = zip(*(csr_by_source(edge_index[b], n) for b in range(B)))
-    row_ptr, order = torch.stack(rps).contiguous(), torch.stack(orders).contiguous()
-    ol = order.long()
-    dst_s = torch.gather(edge_index[:, 1], 1, ol).to(torch.int32).contiguous()
-    src_s = torch.gather(edge_index[:, 0], 1, ol).to(torch.int32).contiguous()
-    attr_s = torch.gather(edge_attr.reshape(B, E).to(torch.float32), 1, ol).contiguous()
-    out, dense = _launch_gnn(weights, feats, x.to(torch.float32).contiguous(), row_ptr, dst_s, attr_s, order, True, dense_eps, src_s)
+    if graph is None:                       # CSR by source for the whole batch at once (no per-instance Python)
+        graph = train_graph(edge_index, edge_attr, n, backward=False)
+    out, dense = _launch_gnn(weights, feats, x.to(torch.float32).contiguous(), graph["row_ptr"], graph["dst"], graph["attr"],
+                             graph["order"], True, dense_eps, graph["src"])
     if dense_eps is None:
         return out if batched else out[0]
     return (out, dense) if batched else (out[0], dense[0])
