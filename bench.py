@@ -158,7 +158,13 @@ def main():
         line = {"impl": "reference", "metric": "ant-tours/sec TSP-100 n_ants=512", "value": cb["value"], "unit": "ant-tours/s",
                 "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "colonies_per_step": 1, "device": "cpu"},
+                "config": {"workload": workload, "colonies_per_step": 1, "device": "cpu",
+                           "same_config_as_gpu_arm": False,
+                           "note": "same colony (TSP-100 x 512 ants, k=20 sparse heuristic) and same unit (ant-tours/s) as the "
+                                   "GPU arm, but ONE colony per step: the reference processes instances one after another "
+                                   "(tsp/test.ipynb cell 1), the GPU arm runs 256 per launch; the GPU arm's `single_colony` "
+                                   "is the one-colony-per-step figure.  Heuristic here: synthetic values on the k-NN graph "
+                                   "(CPU speed does not depend on the values)"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "ant-tours/s", "h2d_bytes_per_step": 0,
                                             "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))

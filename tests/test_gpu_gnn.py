@@ -89,6 +89,32 @@ def test_kernels_are_as_close_to_fp64_as_the_reference_is(golden, case, monkeypa
     assert errs["group"] <= bound and errs["tensor_core"] <= bound, (ref_err, errs)
 
 
+def test_c3_size_heuristic_matches_reference_and_fp64(golden, monkeypatch):
+    """BASELINE config 3 (TSP-NLS n = 500, k = 50, start node 0, tsp500.pt): eval-mode golden from the unmodified
+    reference (tests/golden/make_golden_c3.py), with the reference's own float64 evaluation stored beside it.  Same graph
+    (edge_index equal), both kernels within 2x of the reference's fp32-vs-fp64 distance, and within `rtol 5e-3` of the
+    reference's fp32 output (1e-12 sigmoid tails: the reference itself is 2.2e-3 from fp64 there)."""
+    from deepaco_b200.tsp_nls.net import Net
+    from deepaco_b200.tsp_nls.utils import gen_pyg_data
+    g = golden("tsp_nls_n500_gnn")
+    net = _load(Net, "weights_tsp_nls500")
+    pyg, _ = gen_pyg_data(torch.from_numpy(g["coords"]).to(DEV), 50, start_node=0)
+    assert np.array_equal(pyg.edge_index.cpu().numpy(), g["edge_index"])
+    truth = torch.from_numpy(g["heu_vec_fp64"]).to(DEV)
+    ref = torch.from_numpy(g["heu_vec"]).to(DEV)
+    ref_err = _rel_err(ref, truth)
+    with torch.no_grad():
+        grouped = net(pyg)                                        # 64 CTAs on the one graph
+        monkeypatch.setenv("DEEPACO_GNN_CTAS", "1")
+        single = net(pyg)                                         # one CTA, tensor-core tiles
+    errs = {"group": _rel_err(grouped, truth), "tensor_core": _rel_err(single, truth)}
+    print(f"C3: relative error vs fp64 -- reference {ref_err:.3e}, kernels {errs}")
+    assert max(errs.values()) <= 2.0 * ref_err
+    assert torch.allclose(grouped, ref, rtol=5e-3, atol=1e-14) and torch.allclose(single, ref, rtol=5e-3, atol=1e-14)
+    big = ref > 1e-6                                              # away from the tails the agreement is ~1e-5
+    assert torch.allclose(grouped[big], ref[big], rtol=1e-4) and torch.allclose(single[big], ref[big], rtol=1e-4)
+
+
 def test_tsp_nls_and_cvrp_heuristics_match_reference(golden):
     from deepaco_b200.cvrp.net import Net as CNet
     from deepaco_b200.cvrp.utils import gen_pyg_data as cvrp_graph
