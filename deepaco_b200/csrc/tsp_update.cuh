@@ -294,9 +294,23 @@ __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__
         const int e_lo = 2 * wa0, e_hi = 2 * wa1;          // this warp's events of the chunk: e -> ant a0 + e/2, statement e&1
         for (int i = tid; i < W * n; i += nthreads) cnt[i] = 0;
         if (tid == 0) cellstart[0] = 0;
-        for (int i = tid; i < ca; i += nthreads) {   // coalesced, all loads in flight at once
-            nb_s[i] = N[a0 + i];
-            inv_s[i] = __fdiv_rn(1.0f, C[a0 + i]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+        for (int i0 = tid; i0 < ca; i0 += 4 * nthreads) {   // coalesced; eight loads per thread in flight before the first use
+            uint32_t nb4[4];
+            float c4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * nthreads;
+                nb4[q] = i < ca ? N[a0 + i] : 0u;
+                c4[q] = i < ca ? C[a0 + i] : 1.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * nthreads;
+                if (i < ca) {
+                    nb_s[i] = nb4[q];
+                    inv_s[i] = __fdiv_rn(1.0f, c4[q]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+                }
+            }
         }
         __syncthreads();
         for (int e0 = e_lo; e0 < e_hi; e0 += 32) {   // most ants share a few cells: count per group, not per lane
@@ -364,18 +378,19 @@ __global__ void __launch_bounds__(256) tsp_update_row_kernel(float* __restrict__
             const int end = cellstart[v + 1];
             // the add chain is sequential by definition (fp32, ant order); keep the loads of the next eight ahead of it
             if (i + 8 <= end) {
-                float c[8];
+                float c[8], d[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) c[k] = w_sorted[i + k];
                 i += 8;
-                for (; i + 8 <= end; i += 8) {
-                    float nx[8];
+                for (; i + 16 <= end; i += 16) {      // two batches per trip: the buffers swap roles without register moves
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) nx[k] = w_sorted[i + k];
+                    for (int k = 0; k < 8; ++k) d[k] = w_sorted[i + k];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) x = __fadd_rn(x, c[k]);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) c[k] = nx[k];
+                    for (int k = 0; k < 8; ++k) c[k] = w_sorted[i + 8 + k];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x = __fadd_rn(x, d[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) x = __fadd_rn(x, c[k]);

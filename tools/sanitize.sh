@@ -38,6 +38,36 @@ net = Net().to(dev).eval()
 pyg, _ = gen_pyg_data(torch.rand(50, 2, device=dev), 10)
 with torch.no_grad():
     net(pyg)
+# round 2: batched front end (tensor-core tiles), training-mode network, roulette sampler, many-ants update + general
+# Philox geometry, candidate-list refresh, device-sharded run with virtual ranks, host-buffer pipeline
+net.heuristic_matrices(torch.rand(3, 50, 2, device=dev), torch.cdist(torch.rand(3, 50, 2, device=dev), torch.rand(3, 50, 2, device=dev)) + 0.01, 10)
+net.train()
+net(pyg).sum().backward()
+nl = NlsACO(d[:40, :40].contiguous() + 0.01, n_ants=8, device=dev, local_search="2opt")
+nl.sample(inference=True); nl.run(1, inference=True)
+n = 64
+xy = torch.rand(n, 2, device=dev)
+d2 = torch.norm(xy[:, None] - xy, dim=2, p=2); d2[torch.arange(n), torch.arange(n)] = 1e9
+_, idx = torch.topk(d2, 8, dim=1, largest=False)
+h2 = torch.full_like(d2, 1e-10).scatter_(1, idx, torch.rand(n, 8, device=dev) * 0.9 + 0.05)
+big = E.TspRunner(d2, h2, torch.ones_like(d2), 6000)           # > 303104 / 64 ants: general geometry + row update kernel
+big.run(5, 3)
+from deepaco_b200.dist import DeviceShardedColony, local_peer_memory
+peers = local_peer_memory(1, 96, n, torch.device(dev, 0), 2)
+cols = [DeviceShardedColony(E.TspRunner(d2, h2, torch.ones_like(d2), 96), peers[r], timeout_ms=20000) for r in range(2)]
+streams = [torch.cuda.Stream() for _ in range(2)]
+torch.cuda.synchronize()
+for r in range(2):
+    with torch.cuda.stream(streams[r]):
+        cols[r].run(2, 5)
+torch.cuda.synchronize()
+for c in cols:
+    c.check()
+B = 16
+dh = d2.expand(B, n, n).contiguous().cpu().pin_memory(); hh = h2.expand(B, n, n).contiguous().cpu().pin_memory()
+ph = torch.ones(B, n, n).pin_memory(); lo = torch.empty(B).pin_memory(); sp = torch.empty((B, n), dtype=torch.int64).pin_memory()
+rh = E.TspRunner(torch.zeros(B, n, n, device=dev), torch.zeros(B, n, n, device=dev), torch.zeros(B, n, n, device=dev), 32)
+rh.run_host(2, 7, dh, hh, ph, lo, sp)
 torch.cuda.synchronize()
 print("sanitize script done")
 PY
