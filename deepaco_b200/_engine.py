@@ -210,6 +210,25 @@ def tsp_update_(pheromone, neighbours, costs, *, decay=0.9, elitist=False, min_m
     return pheromone
 
 
+def tsp_update_tours_(pheromone, tours, costs, *, decay=0.9, elitist=False, min_max=False, ph_min=0.0, ph_max=None):
+    """deepaco_tsp_update_tours, in place on `pheromone`: the ant-sequential update from compact uint16 tours."""
+    require_cuda(pheromone, "pheromone")
+    if pheromone.dtype != torch.float32 or not pheromone.is_contiguous():
+        raise _lib.DeepAcoError("pheromone must be contiguous fp32 for the in-place update")
+    B, n = _colonies(pheromone)
+    _check_tours(tours, n)
+    n_ants = tours.shape[-2]
+    costs = f32c(costs)
+    dev = pheromone.device
+    if min_max:
+        ph_max = f32c(torch.as_tensor(ph_max, device=dev).reshape(-1))
+    with torch.cuda.device(dev):
+        check(lib().deepaco_tsp_update_tours(ptr(pheromone), ptr(tours), ptr(costs), n, n_ants, B, float(decay), int(elitist),
+                                             int(min_max), float(ph_min), ptr(ph_max) if min_max else None, stream_ptr(dev)),
+              "deepaco_tsp_update_tours")
+    return pheromone
+
+
 class TspRunner:
     """Device-resident state of `ACO.run` for one or many TSP colonies (deepaco_tsp_run).
 

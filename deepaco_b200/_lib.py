@@ -30,6 +30,7 @@ _SIGNATURES = {
     "deepaco_tsp_roulette_offset_increment": (_u64, [_i32, _i32]),
     "deepaco_tsp_cost": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_tsp_update": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
+    "deepaco_tsp_update_tours": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _f32, _vp, _vp]),
     "deepaco_two_opt": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "deepaco_tsp_nls": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_paths_to_tours": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),

@@ -24,6 +24,10 @@ int tsp_update_launch(float* pheromone, const uint32_t* neighbours, const float*
 int tsp_cost_launch(const float* distances, const uint16_t* tours, int n, int n_ants, int n_colonies, float* costs,
                     uint32_t* neighbours, cudaStream_t st);
 int knn_refresh_launch(const float* product, uint8_t* knn, int n, int n_colonies, cudaStream_t st);
+bool tsp_update_seq_preferred(int n, int n_ants, int n_colonies);
+int tsp_update_seq_launch(float* pheromone, const uint16_t* tours, const float* costs, int n, int n_ants, int n_colonies,
+                          float decay, int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
+                          const float* heuristic, float* product, cudaStream_t st);
 int tsp_sample_peers(const float* product, int n, int n_ants_local, int n_colonies, int start_node, int double_norm, uint64_t seed,
                      uint64_t offset, const uint64_t* offsets, const uint8_t* knn, int ant_base, int n_ants_total,
                      const uint64_t* peer_tours_host, int n_peers, cudaStream_t st);
@@ -113,13 +117,16 @@ extern "C" int deepaco_tsp_run_shard(const deepaco_tsp_run_args* a, const deepac
             shard_barrier_kernel<<<1, 32, 0, st>>>(bp);
             DACO_CHECK_LAUNCH();
         }
-        rc = tsp_cost_launch(a->distances, tours, n, A, B, a->costs, a->neighbours, st);
+        const bool seq = tsp_update_seq_preferred(n, A, B);
+        rc = tsp_cost_launch(a->distances, tours, n, A, B, a->costs, seq ? nullptr : a->neighbours, st);
         if (rc) return rc;
         rc = best_launch(a->costs, tours, a->pheromone, n, n, A, B, a->min_max, a->lowest_cost, a->shortest_path, a->ph_max,
                          a->min_max ? a->scale : nullptr, nullptr, nullptr, st);
         if (rc) return rc;
-        rc = tsp_update_launch(a->pheromone, a->neighbours, a->costs, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min,
-                               a->ph_max, a->min_max ? a->scale : nullptr, a->heuristic, a->product, st);
+        rc = seq ? tsp_update_seq_launch(a->pheromone, tours, a->costs, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min, a->ph_max,
+                                         a->min_max ? a->scale : nullptr, a->heuristic, a->product, st)
+                 : tsp_update_launch(a->pheromone, a->neighbours, a->costs, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min,
+                                     a->ph_max, a->min_max ? a->scale : nullptr, a->heuristic, a->product, st);
         if (rc) return rc;
         if (a->knn && a->knn_refresh > 0 && n > 32 && n <= 256 && (a->knn_iteration0 + it + 1) % a->knn_refresh == 0) {
             rc = knn_refresh_launch(a->product, const_cast<uint8_t*>(a->knn), n, B, st);

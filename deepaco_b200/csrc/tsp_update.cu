@@ -64,6 +64,31 @@ static int launch_tsp_update(float* pheromone, const uint32_t* neighbours, const
 }
 
 namespace deepaco {
+// ant-sequential update straight from the compact tours (no neighbour table): small / medium colonies whose pheromone
+// matrix fits in shared memory
+bool tsp_update_seq_ok(int n, int n_ants) {
+    return n >= 3 && n <= 224 && n_ants <= 1024 && !getenv("DEEPACO_UPDATE_ROWS_ONLY");
+}
+// ... and worth it: the kernel is one sequential chain per colony (~400 cycles per ant), so it pays when many colonies
+// run side by side (several CTAs per SM: n <= 128) and loses to the row-parallel kernel when only a few do.
+// Measured on 256 x TSP-100 x 512: 100 us against 149 + the 20 us the cost kernel spends on the neighbour table; one
+// colony: 100 us against 15.
+bool tsp_update_seq_preferred(int n, int n_ants, int n_colonies) {
+    if (getenv("DEEPACO_UPDATE_SEQ")) return tsp_update_seq_ok(n, n_ants);
+    return tsp_update_seq_ok(n, n_ants) && n <= 128 && n_colonies >= 64;
+}
+int tsp_update_seq_launch(float* pheromone, const uint16_t* tours, const float* costs, int n, int n_ants, int n_colonies,
+                          float decay, int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
+                          const float* heuristic, float* product, cudaStream_t st) {
+    const size_t smem = ((size_t)n * n + n_ants) * sizeof(float) + (size_t)2 * (16 * n + 2) * sizeof(uint16_t);
+    DACO_CHECK_ARG(tsp_update_seq_ok(n, n_ants) && smem <= 220 * 1024, "tsp_update_seq: n=%d / n_ants=%d outside its range", n, n_ants);
+    DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_update_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = n <= 64 ? 128 : 256;     // >= 2n threads when n <= 128: one cell per thread and ant
+    tsp_update_seq_kernel<<<n_colonies, threads, smem, st>>>(pheromone, tours, costs, n, n_ants, decay, elitist, min_max, ph_min, ph_max,
+                                                            scale, heuristic, product);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
 int knn_refresh_launch(const float* product, uint8_t* knn, int n, int n_colonies, cudaStream_t st) {
     DACO_CHECK_ARG(n > 32 && n <= 256, "knn refresh: 32 < n <= 256");
     const int rows = n * n_colonies;
@@ -91,4 +116,16 @@ extern "C" int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, 
     DACO_CHECK_ARG(!min_max || ph_max, "deepaco_tsp_update: min_max needs ph_max");
     return launch_tsp_update(pheromone, neighbours, costs, n, n_ants, n_colonies, decay, elitist, min_max, ph_min, ph_max,
                              nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int deepaco_tsp_update_tours(float* pheromone, const uint16_t* tours, const float* costs, int n, int n_ants,
+                                        int n_colonies, float decay, int elitist, int min_max, float ph_min,
+                                        const float* ph_max, void* stream) {
+    DACO_CHECK_ARG(pheromone && tours && costs, "deepaco_tsp_update_tours: NULL argument");
+    DACO_CHECK_ARG(n >= 3 && n_ants >= 1 && n_colonies >= 1, "deepaco_tsp_update_tours: bad sizes");
+    DACO_CHECK_ARG(!min_max || ph_max, "deepaco_tsp_update_tours: min_max needs ph_max");
+    DACO_CHECK_ARG(tsp_update_seq_ok(n, n_ants), "deepaco_tsp_update_tours: needs 3 <= n <= 224 and n_ants <= 1024 (use deepaco_tsp_cost's "
+                   "neighbour table + deepaco_tsp_update beyond that)");
+    return tsp_update_seq_launch(pheromone, tours, costs, n, n_ants, n_colonies, decay, elitist, min_max, ph_min, ph_max, nullptr, nullptr,
+                                 nullptr, (cudaStream_t)stream);
 }

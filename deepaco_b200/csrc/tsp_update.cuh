@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) tsp_cost_tile_kernel(const float* __restr
             const float c = aten_row_sum_fn(edge, n, lbw, vec != 0, lane, vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
             if (lane == 0) costs[(size_t)b * A + a] = c;
         }
-        for (int k = lane; k < n; k += 32) pos_s[(size_t)al * n + tour[k]] = (uint16_t)k;
+        if (nbr)
+            for (int k = lane; k < n; k += 32) pos_s[(size_t)al * n + tour[k]] = (uint16_t)k;
     }
     __syncthreads();
     if (nbr) {
@@ -199,6 +200,155 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
             row[v] = val;
             if (prod) prod[((size_t)b * n + u) * n + v] = __fmul_rn(val, heu[((size_t)b * n + u) * n + v]);
         }
+    }
+}
+
+// The same update the way the reference states it (tsp/aco.py:101-114): ants one after another, each ant's 2n cells in
+// parallel.  One CTA per colony keeps the whole pheromone matrix in shared memory; thread k owns tour edge k of the
+// current ant and adds 1 / cost to cells (t_k, t_k+1) and (t_k+1, t_k) -- the cells of one ant are pairwise distinct for
+// n >= 3, so there is nothing to order inside an ant, and the per-ant barrier gives every cell its additions in ant
+// order: bit-identical to the reference, with ~20 warp-instructions per ant instead of a counting sort per matrix row
+// (4.2 k instructions for each of the n rows).  No neighbour table is needed.  Used when the matrix fits in shared memory and the colony has at most ~1 k ants (the
+// chain is sequential in the ants; big colonies take tsp_update_row_kernel).
+//   smem: M f32 [n][n] | inv f32 [A] | tour ring u16 [2][16 * n]
+__global__ void __launch_bounds__(256) tsp_update_seq_kernel(float* __restrict__ ph, const uint16_t* __restrict__ tours,
+                                                             const float* __restrict__ costs, int n, int A, float decay, int elitist,
+                                                             int min_max, float ph_min, const float* __restrict__ ph_max,
+                                                             const float* __restrict__ scale, const float* __restrict__ heu,
+                                                             float* __restrict__ prod) {
+    DACO_DYN_SMEM16(smem);
+    __shared__ int s_best;
+    constexpr int D = 8;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    float* M = reinterpret_cast<float*>(smem);
+    float* inv = M + (size_t)n * n;
+    float* P = ph + (size_t)b * n * n;
+    const float* C = costs + (size_t)b * A;
+    const float sc = scale ? scale[b] : 1.0f;
+    for (int i = tid; i < n * n; i += nth) {
+        float x = P[i];
+        if (scale) x = __fmul_rn(x, sc);      // MMAS rescale on the first improvement (tsp/aco.py:86-87)
+        M[i] = __fmul_rn(x, decay);
+    }
+    for (int a = tid; a < A; a += nth) inv[a] = __fdiv_rn(1.0f, C[a]);   // `1.0 / cost` = reciprocal(cost) * 1.0
+    int a_lo = 0, a_hi = A;
+    if (elitist) {   // costs.min(dim=0): first index of the minimum
+        if (warp == 0) {
+            float bc = INFINITY;
+            int bi = 0x7fffffff;
+            for (int a = lane; a < A; a += 32) {
+                const float c = C[a];
+                if (c < bc) { bc = c; bi = a; }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                const float oc = __shfl_xor_sync(DACO_FULL, bc, off);
+                const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
+                if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+            }
+            if (lane == 0) s_best = bi;
+        }
+        __syncthreads();
+        a_lo = s_best;
+        a_hi = a_lo + 1;
+    }
+    __syncthreads();
+    // Tours reach the chain through a double-buffered shared-memory ring of kBlk ants: the global loads of block j + 1 are
+    // issued (into registers) before block j is processed and parked in shared memory after it, so their latency is
+    // covered by kBlk ant steps; inside a block the next ant's edge is read from shared memory one step ahead.
+    constexpr int kBlk = 16;
+    const uint16_t* T = tours + ((size_t)b * A + a_lo) * n;          // ants [a_lo, a_hi) are contiguous
+    const int count = a_hi - a_lo;
+    uint16_t* ring = reinterpret_cast<uint16_t*>(inv + A);            // [2][kBlk * n]
+    const int words = (kBlk * n + 1) / 2;                             // 32-bit words per block (tour rows are contiguous)
+    // thread roles: with at least 2n threads the lower half adds to cell (t_k, t_k+1) and the upper half to (t_k+1, t_k)
+    // -- one load / add / store per thread and ant; with fewer, thread k does both cells of edge k
+    const bool split = nth >= 2 * n;
+    const int half = nth >> 1;
+    const int ke = split ? (tid >= half ? tid - half : tid) : tid;   // edge index of this thread
+    const bool flip = split && tid >= half;
+    const bool on = ke < n;
+    const int k0 = flip ? (ke + 1 == n ? 0 : ke + 1) : ke;            // row endpoint, column endpoint of this thread's cell
+    const int k1 = flip ? ke : (ke + 1 == n ? 0 : ke + 1);
+    constexpr int kRegs = 8;                                          // words per thread per block: 8 * 256 * 2 >= kBlk * 224
+    uint32_t stage[kRegs];
+    auto fetch = [&](int blk) {                                       // global -> registers (block `blk`), 4-byte loads
+        const size_t base = (size_t)blk * kBlk * n;                   // in uint16 units; even because kBlk is
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(T + base);
+        const int elems = min(kBlk, count - blk * kBlk) * n, full = elems >> 1;   // an odd last element gets a 2-byte load
+#pragma unroll
+        for (int q = 0; q < kRegs; ++q) {
+            const int wi = tid + q * nth;
+            uint32_t w = 0u;
+            if (wi < full) w = src[wi];
+            else if (wi == full && (elems & 1)) w = T[base + elems - 1];
+            stage[q] = w;
+        }
+    };
+    auto park = [&](int blk) {                                        // registers -> ring slot blk & 1
+        uint32_t* dst = reinterpret_cast<uint32_t*>(ring + (size_t)(blk & 1) * (2 * words));
+#pragma unroll
+        for (int q = 0; q < kRegs; ++q) {
+            const int wi = tid + q * nth;
+            if (wi < words) dst[wi] = stage[q];
+        }
+    };
+    const int nblk = (count + kBlk - 1) / kBlk;
+    // T + base must be 4-byte aligned: base * 2 bytes with base a multiple of kBlk * n (even); T itself is, when
+    // ((b * A + a_lo) * n) is even -- otherwise fall back to 2-byte loads through the same ring
+    const bool aligned = ((reinterpret_cast<uintptr_t>(T) & 3) == 0);
+    auto fetch16 = [&](int blk) {
+        const uint16_t* src = T + (size_t)blk * kBlk * n;
+        const int avail = min(kBlk, count - blk * kBlk) * n;
+#pragma unroll
+        for (int q = 0; q < kRegs; ++q) {
+            const int wi = tid + q * nth;
+            uint32_t lo = 0, hi16 = 0;
+            if (wi < words) {
+                if (2 * wi < avail) lo = src[2 * wi];
+                if (2 * wi + 1 < avail) hi16 = src[2 * wi + 1];
+            }
+            stage[q] = lo | (hi16 << 16);
+        }
+    };
+    if (nblk > 0) {
+        if (aligned) fetch(0); else fetch16(0);
+        park(0);
+    }
+    __syncthreads();
+    for (int blk = 0; blk < nblk; ++blk) {
+        if (blk + 1 < nblk) { if (aligned) fetch(blk + 1); else fetch16(blk + 1); }
+        const uint16_t* tb = ring + (size_t)(blk & 1) * (2 * words);
+        const int m = min(kBlk, count - blk * kBlk);
+        int u = on ? tb[k0] : 0, v = on ? tb[k1] : 0;
+        for (int i = 0; i < m; ++i) {
+            const float w = inv[a_lo + blk * kBlk + i];
+            int un = 0, vn = 0;
+            if (on && i + 1 < m) {                                    // next ant's edge, ahead of the barrier
+                un = tb[(i + 1) * n + k0];
+                vn = tb[(i + 1) * n + k1];
+            }
+            if (on) {
+                M[u * n + v] = __fadd_rn(M[u * n + v], w);
+                if (!split) M[v * n + u] = __fadd_rn(M[v * n + u], w);
+            }
+            __syncthreads();
+            u = un;
+            v = vn;
+        }
+        if (blk + 1 < nblk) park(blk + 1);                            // slot (blk + 1) & 1 was last read in block blk - 1
+        __syncthreads();
+    }
+    const float hi = min_max ? ph_max[b] : 0.f;
+    for (int i = tid; i < n * n; i += nth) {
+        float x = M[i];
+        if (min_max) {
+            // ph[(ph > 1e-9) * ph < min] = min ; ph[ph > max] = max   (tsp/aco.py:117-118)
+            const float gate = __fmul_rn(x > 1e-9f ? 1.0f : 0.0f, x);
+            if (gate < ph_min) x = ph_min;
+            if (x > hi) x = hi;
+        }
+        P[i] = x;
+        if (prod) prod[(size_t)b * n * n + i] = __fmul_rn(x, heu[(size_t)b * n * n + i]);
     }
 }
 

@@ -98,6 +98,12 @@ int deepaco_tsp_update(float* pheromone, const uint32_t* neighbours, const float
                        int n_colonies, float decay, int elitist, int min_max, float ph_min, const float* ph_max,
                        void* stream);
 
+/* Same update straight from compact tours (u16 [B][A][n]), no neighbour table: ants one after another, each ant's cells in
+ * parallel on a pheromone matrix held in shared memory -- the reference's own loop structure (tsp/aco.py:109-114), same
+ * bits.  For 3 <= n <= 224 and n_ants <= 1024; deepaco_tsp_run picks it automatically. */
+int deepaco_tsp_update_tours(float* pheromone, const uint16_t* tours, const float* costs, int n, int n_ants, int n_colonies,
+                             float decay, int elitist, int min_max, float ph_min, const float* ph_max, void* stream);
+
 /* ---- ACO.run for TSP (tsp/aco.py:74-92; tsp_nls/aco.py:104-129 with local_search=None) -------------
  * n_iterations x { sample -> cost -> best tracking -> evaporate+deposit } on `stream`, no host sync.
  * All buffers are caller-owned device memory:

@@ -78,6 +78,21 @@ extern "C" const char* emu_tsp_update_rows(float* ph, const uint32_t* nbr, const
     return nullptr;
 }
 
+// tsp_update_seq_kernel (one CTA per colony, matrix in shared memory, ants one after another)
+extern "C" const char* emu_tsp_update_seq(float* ph, const uint16_t* tours, const float* costs, int n, int A, int threads, float decay,
+                                          int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
+                                          const float* heu, float* prod) {
+    if (!ph || !tours || !costs || n < 3 || A < 1 || threads < n || (min_max && !ph_max)) return "bad arguments";
+    struct SeqArgs {
+        float* ph; const uint16_t* t; const float* c; int n, A; float decay; int el, mm; float mn; const float* mx; const float* sc;
+        const float* heu; float* prod;
+    };
+    const SeqArgs a{ph, tours, costs, n, A, decay, elitist, min_max, ph_min, ph_max, scale, heu, prod};
+    emu::launch([](const SeqArgs& q) { tsp_update_seq_kernel(q.ph, q.t, q.c, q.n, q.A, q.decay, q.el, q.mm, q.mn, q.mx, q.sc, q.heu, q.prod); },
+                a, 1, 1, threads, ((size_t)n * n + A) * 4 + (size_t)2 * (16 * n + 2) * 2);
+    return nullptr;
+}
+
 // knn_refresh_kernel: candidate lists (columns of the 32 largest entries per row) from a product matrix [rows][n]
 extern "C" const char* emu_knn_refresh(const float* prod, uint8_t* knn, int n, int rows) {
     if (!prod || !knn || n <= 32 || n > 256 || rows < 1) return "bad arguments";

@@ -125,6 +125,35 @@ def test_row_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, 
     assert torch.equal(prod, ph * heu)
 
 
+@pytest.mark.parametrize("kw", [{}, {"elitist": True}, {"min_max": True}, {"min_max": True, "scale": 1.7}])
+@pytest.mark.parametrize("n,A,threads", [(5, 3, 32), (20, 8, 32), (20, 9, 64), (100, 48, 128), (100, 21, 256), (61, 130, 64), (130, 19, 256)])
+def test_seq_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, n, A, threads, kw):
+    """tsp_update_seq_kernel (matrix in shared memory, ants one after another with a barrier each, tours prefetched eight
+    ahead): same bits as the reference's per-ant index_put loop, incl. elitist / min-max / MMAS rescale, partial
+    prefetch windows (A not a multiple of 8) and thread counts not equal to n."""
+    emu_u.emu_tsp_update_seq.restype = ctypes.c_char_p
+    emu_u.emu_tsp_update_seq.argtypes = [vp, vp, vp, ci, ci, ci, cf, ci, ci, cf, vp, vp, vp, vp]
+    dist, paths = _instance(n, A, 5 * n + A)
+    torch.manual_seed(3)
+    ph0 = (torch.rand(n, n) + 0.2).contiguous()
+    costs = O.tsp_path_costs(dist, paths).contiguous()
+    elitist, min_max, scale = kw.get("elitist", False), kw.get("min_max", False), kw.get("scale")
+    ph_max = torch.tensor([float(n / costs.min())])
+    ref_in = ph0 * scale if scale else ph0
+    want = O.tsp_update_pheromone(ref_in.clone(), paths, costs, decay=0.9, elitist=elitist, min_max=min_max, ph_min=0.1,
+                                  ph_max=float(ph_max))
+    ph = ph0.clone()
+    heu = torch.rand(n, n).contiguous()
+    prod = torch.full((n, n), float("nan"))
+    sc = torch.tensor([scale], dtype=torch.float32) if scale else None
+    tours = paths.T.contiguous().to(torch.int16)
+    err = emu_u.emu_tsp_update_seq(_ptr(ph), _ptr(tours), _ptr(costs), n, A, threads, 0.9, int(elitist), int(min_max), 0.1,
+                                   _ptr(ph_max) if min_max else None, _ptr(sc), _ptr(heu), _ptr(prod))
+    assert err is None, err
+    assert torch.equal(ph, want)
+    assert torch.equal(prod, ph * heu)
+
+
 @pytest.mark.parametrize("n,rows", [(33, 5), (100, 100), (256, 19)])
 def test_knn_refresh_kernel_on_host_selects_the_32_largest_per_row(emu_u, n, rows):
     """knn_refresh_kernel: per row the columns of the 32 largest product entries, ties to the lower column (the floor
