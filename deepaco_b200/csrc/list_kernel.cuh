@@ -663,10 +663,12 @@ static __global__ void __launch_bounds__(MAXW * 32, 1024 / (MAXW * 32)) aco_knn_
         auto edge = [&](int k) -> float { return __ldg(D + (size_t)tour_sm[k] * n + tour_sm[k == 0 ? n - 1 : k - 1]); };
         const float c = aten_row_sum_fn(edge, n, p.lbw, p.vec != 0, lane, p.vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
         if (lane == 0) p.costs[(size_t)b * p.A + a] = c;
-        uint32_t* N = p.nbr + (size_t)b * n * p.A;
-        for (int k = lane; k < n; k += 32) {
-            const uint32_t u = tour_sm[k], pr = tour_sm[k == 0 ? n - 1 : k - 1], su = tour_sm[k == n - 1 ? 0 : k + 1];
-            N[(size_t)u * p.A + a] = (pr << 16) | su;
+        if (p.nbr) {   // neighbour table only for the row-parallel update (the ant-sequential one reads the tours)
+            uint32_t* N = p.nbr + (size_t)b * n * p.A;
+            for (int k = lane; k < n; k += 32) {
+                const uint32_t u = tour_sm[k], pr = tour_sm[k == 0 ? n - 1 : k - 1], su = tour_sm[k == n - 1 ? 0 : k + 1];
+                N[(size_t)u * p.A + a] = (pr << 16) | su;
+            }
         }
     }
 }

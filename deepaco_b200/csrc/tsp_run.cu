@@ -144,12 +144,13 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
     }
     for (int it = 0; it < n_iterations; ++it) {
         if (a->ev_sample_begin) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_begin, st));
+        const bool seq = tsp_update_seq_preferred(n, A, B);      // ant-sequential update from the tours: no neighbour table needed
         int fused = 0;
         int rc = a->roulette ? deepaco_tsp_roulette_sample(a->product, n, A, B, a->start_node, a->seed, a->offset + (uint64_t)it * inc,
                                                            a->offsets, a->tours, nullptr, st)
                              : tsp_sample_fused(a->product, n, A, B, a->start_node, a->double_norm, a->seed, a->offset + (uint64_t)it * inc,
-                                  a->offsets, a->tours, a->knn, a->local_search ? nullptr : a->distances, a->costs, a->neighbours,
-                                  &fused, st);
+                                  a->offsets, a->tours, a->knn, a->local_search ? nullptr : a->distances, a->costs,
+                                  seq ? nullptr : a->neighbours, &fused, st);
         if (rc) return rc;
         if (a->ev_sample_end) DACO_CHECK_CUDA(cudaEventRecord((cudaEvent_t)a->ev_sample_end, st));
         if (a->local_search == 1) {
@@ -160,7 +161,6 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
                                  nullptr, st);
             if (rc) return rc;
         }
-        const bool seq = tsp_update_seq_preferred(n, A, B);      // ant-sequential update from the tours: no neighbour table needed
         if (!fused) {
             rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, seq ? nullptr : a->neighbours, st);
             if (rc) return rc;
