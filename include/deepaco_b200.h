@@ -109,7 +109,8 @@ int deepaco_tsp_update_tours(float* pheromone, const uint16_t* tours, const floa
  * All buffers are caller-owned device memory:
  *   pheromone [B][n][n] in/out; heuristic, distances [B][n][n] in;
  *   product [B][n][n] scratch holding pheromone (.) heuristic (product_valid = 1 if already up to date);
- *   tours u16 [B][A][n], costs f32 [B][A], neighbours u32 [B][n][A]: scratch, hold the LAST iteration;
+ *   tours u16 [B][A][n], costs f32 [B][A], neighbours u32 [B][n][A]: scratch, hold the LAST iteration (neighbours is
+ *   only written when the row-parallel update is used: few colonies, n > 128 or more than 1024 ants);
  *   lowest_cost f32 [B] in/out (+inf before the first run); shortest_path i64 [B][n] in/out;
  *   ph_max f32 [B] in/out (min_max only; 0 = not set yet); scale f32 [B] scratch (min_max only).
  * Iteration t of colony b consumes the Philox stream at offsets[b] + offset + t * increment, increment =
@@ -135,7 +136,7 @@ typedef struct {
     int64_t* shortest_path;
     float* ph_max;
     float* scale;
-    const uint8_t* knn;    /* optional candidate lists, see deepaco_tsp_sample */
+    const uint8_t* knn;    /* optional candidate lists, see deepaco_tsp_sample (rewritten in place when knn_refresh > 0) */
     int local_search;      /* tsp_nls/aco.py:97-102 between construction and cost: 0 none, 1 2-opt, 2 NLS */
     int ls_max_iterations; /* 2-opt passes per call (n/4 in training, 10000 at inference) */
     int T_nls, T_p;        /* NLS rounds / perturbation passes (10 / 20 in the reference) */
