@@ -234,7 +234,13 @@ def symmetric_peer_memory(B, A, n, device, group=None) -> PeerMemory:
 def local_peer_memory(B, A, n, device, world):
     """`world` virtual ranks on ONE device (plain device pointers are their own peer mapping): exercises the complete
     device-side protocol -- fused peer stores, flag barrier, double buffering -- on a single GPU, each virtual rank on its
-    own stream.  -> list of PeerMemory, one per virtual rank."""
+    own stream.  -> list of PeerMemory, one per virtual rank.
+
+    One process drives all virtual ranks, so the FIRST launch of a kernel must not happen while another rank's barrier
+    kernel is already spinning: CUDA loads kernels lazily and loading synchronises with the device, i.e. the host would
+    wait for a barrier that waits for launches the host has not issued yet (until the barrier's time-out).  Run the same
+    shapes once with world = 1 first (`warm_virtual_ranks`); real multi-GPU runs (one process per GPU) have no such
+    coupling."""
     tour_bytes, total = _peer_layout(B, A, n)
     bufs = [torch.empty((total,), dtype=torch.uint8, device=device) for _ in range(world)]
     for b in bufs:
@@ -243,6 +249,21 @@ def local_peer_memory(B, A, n, device, world):
     tour_ptrs = [[base[r] + k * tour_bytes for k in range(TOUR_BUFFERS)] for r in range(world)]
     flag_ptrs = [base[r] + TOUR_BUFFERS * tour_bytes for r in range(world)]
     return [PeerMemory(r, world, tour_ptrs, flag_ptrs, bufs) for r in range(world)]
+
+
+def warm_virtual_ranks(make_runner, world=1, n_iterations=1, seed=0):
+    """Load every kernel of the sharded path (see `local_peer_memory`): one world-1 run of a runner built by
+    `make_runner()` (cost / best / update variants of the full colony), plus one construction launch per distinct shard
+    size of a `world`-way split (the construction kernel's instantiation depends on the ants per launch); synchronised."""
+    from . import _engine as E
+    r = make_runner()
+    col = DeviceShardedColony(r, local_peer_memory(r.B, r.n_ants, r.n, r.dev, 1)[0])
+    col.run(n_iterations, seed)
+    for count in {shard_range(r.n_ants, world, k)[1] for k in range(world)} - {0, r.n_ants}:
+        E.tsp_sample_shard(r.product, None, count, 0, r.n_ants, start_node=r.start_node, double_norm=r.double_norm, seed=seed,
+                           knn=r.knn)
+    torch.cuda.synchronize(r.dev)
+    col.check()
 
 
 def shard_tables(peer: PeerMemory):

@@ -8,7 +8,7 @@ import torch
 
 from deepaco_b200 import _engine as E
 from deepaco_b200._lib import DeepAcoError
-from deepaco_b200.dist import DeviceShardedColony, local_peer_memory, shard_range
+from deepaco_b200.dist import DeviceShardedColony, local_peer_memory, shard_range, warm_virtual_ranks
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
@@ -30,6 +30,8 @@ def _instances(B, n, k, sparse, seed=3):
 
 def _run_sharded(d, heu, A, world, T, seed, offsets, calls=1, **kw):
     B, n = d.shape[0], d.shape[1]
+    # one process drives all virtual ranks: load this shape's kernels before any barrier can spin (dist.local_peer_memory)
+    warm_virtual_ranks(lambda: E.TspRunner(d, heu, torch.ones_like(d), A, **kw), world)
     peers = local_peer_memory(B, A, n, DEV, world)
     streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
     cols = [DeviceShardedColony(E.TspRunner(d, heu, torch.ones_like(d), A, **kw), peers[r], timeout_ms=4000)

@@ -52,7 +52,8 @@ _, idx = torch.topk(d2, 8, dim=1, largest=False)
 h2 = torch.full_like(d2, 1e-10).scatter_(1, idx, torch.rand(n, 8, device=dev) * 0.9 + 0.05)
 big = E.TspRunner(d2, h2, torch.ones_like(d2), 6000)           # > 303104 / 64 ants: general geometry + row update kernel
 big.run(5, 3)
-from deepaco_b200.dist import DeviceShardedColony, local_peer_memory
+from deepaco_b200.dist import DeviceShardedColony, local_peer_memory, warm_virtual_ranks
+warm_virtual_ranks(lambda: E.TspRunner(d2, h2, torch.ones_like(d2), 96), 2)
 peers = local_peer_memory(1, 96, n, torch.device(dev, 0), 2)
 cols = [DeviceShardedColony(E.TspRunner(d2, h2, torch.ones_like(d2), 96), peers[r], timeout_ms=20000) for r in range(2)]
 streams = [torch.cuda.Stream() for _ in range(2)]
