@@ -22,6 +22,10 @@ int tsp_cost_launch(const float* distances, const uint16_t* tours, int n, int n_
                     uint32_t* neighbours, cudaStream_t st);
 int knn_refresh_launch(const float* product, uint8_t* knn, int n, int n_colonies, cudaStream_t st);
 bool tsp_update_seq_preferred(int n, int n_ants, int n_colonies);
+bool tsp_tail_ok(int n, int n_ants, int n_colonies);
+int tsp_tail_launch(float* pheromone, const uint16_t* tours, const float* distances, const float* heuristic, float* product,
+                    float* costs, float* lowest, int64_t* shortest, float* ph_max, int n, int n_ants, int n_colonies, float decay,
+                    int elitist, int min_max, float ph_min, cudaStream_t st);
 int tsp_update_seq_launch(float* pheromone, const uint16_t* tours, const float* costs, int n, int n_ants, int n_colonies,
                           float decay, int elitist, int min_max, float ph_min, const float* ph_max, const float* scale,
                           const float* heuristic, float* product, cudaStream_t st);
@@ -160,6 +164,16 @@ extern "C" int deepaco_tsp_run(const deepaco_tsp_run_args* a, int n_iterations, 
             rc = deepaco_tsp_nls(a->distances, a->heuristic_dist, a->tours, n, A, B, a->ls_max_iterations, a->T_nls, a->T_p, nullptr,
                                  nullptr, st);
             if (rc) return rc;
+        }
+        if (!fused && seq && tsp_tail_ok(n, A, B)) {   // cost + best tracking + update in one launch per colony
+            rc = tsp_tail_launch(a->pheromone, a->tours, a->distances, a->heuristic, a->product, a->costs, a->lowest_cost,
+                                 a->shortest_path, a->ph_max, n, A, B, a->decay, a->elitist, a->min_max, a->ph_min, st);
+            if (rc) return rc;
+            if (a->knn && a->knn_refresh > 0 && n > 32 && n <= 256 && (a->knn_iteration0 + it + 1) % a->knn_refresh == 0) {
+                rc = knn_refresh_launch(a->product, const_cast<uint8_t*>(a->knn), n, B, st);
+                if (rc) return rc;
+            }
+            continue;
         }
         if (!fused) {
             rc = tsp_cost_launch(a->distances, a->tours, n, A, B, a->costs, seq ? nullptr : a->neighbours, st);

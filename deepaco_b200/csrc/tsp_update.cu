@@ -89,6 +89,26 @@ int tsp_update_seq_launch(float* pheromone, const uint16_t* tours, const float* 
     DACO_CHECK_LAUNCH();
     return DEEPACO_OK;
 }
+// cost + best tracking + ant-sequential update of one iteration in one launch per colony (tsp_tail_kernel)
+int tsp_tail_launch(float* pheromone, const uint16_t* tours, const float* distances, const float* heuristic, float* product,
+                    float* costs, float* lowest, int64_t* shortest, float* ph_max, int n, int n_ants, int n_colonies, float decay,
+                    int elitist, int min_max, float ph_min, cudaStream_t st) {
+    const size_t smem = ((size_t)2 * n * n + n_ants) * sizeof(float) + (size_t)2 * (16 * n + 2) * sizeof(uint16_t);
+    DACO_CHECK_ARG(tsp_update_seq_ok(n, n_ants) && smem <= 220 * 1024, "tsp_tail: n=%d / n_ants=%d outside its range", n, n_ants);
+    const SumPlan sp = aten_sum_plan(n, n_ants);
+    int bw = sp.block_width > 32 ? 32 : sp.block_width, lbw = 0;
+    while ((1 << lbw) < bw) ++lbw;
+    TailParams p{pheromone, tours, distances, heuristic, product, costs, lowest, shortest, ph_max, n, n_ants, decay, elitist, min_max,
+                 ph_min, lbw, sp.vectorized};
+    DACO_CHECK_CUDA(cudaFuncSetAttribute(tsp_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tsp_tail_kernel<<<n_colonies, 256, smem, st>>>(p);
+    DACO_CHECK_LAUNCH();
+    return DEEPACO_OK;
+}
+bool tsp_tail_ok(int n, int n_ants, int n_colonies) {
+    return tsp_update_seq_preferred(n, n_ants, n_colonies) && ((size_t)2 * n * n + n_ants) * 4 + 4 * (16 * n + 2) <= 220 * 1024 &&
+           !getenv("DEEPACO_NO_TAIL_KERNEL");
+}
 int knn_refresh_launch(const float* product, uint8_t* knn, int n, int n_colonies, cudaStream_t st) {
     DACO_CHECK_ARG(n > 32 && n <= 256, "knn refresh: 32 < n <= 256");
     const int rows = n * n_colonies;

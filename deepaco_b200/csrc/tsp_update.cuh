@@ -203,14 +203,107 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
     }
 }
 
+// The deposit chain of the ant-sequential update (shared by tsp_update_seq_kernel and tsp_tail_kernel): all threads of the
+// CTA; M = pheromone matrix in shared memory, inv[a] = 1 / cost of ant a, ring = u16 [2][16 * n + 2] scratch.
+// Tours reach the chain through the double-buffered ring in blocks of 16 ants: the global loads of block j + 1 are issued
+// (into registers) before block j is processed and parked in shared memory after it, so their latency is covered by 16
+// ant steps; inside a block the next ant's edge is read from shared memory one step ahead of the barrier.
+// (Measured alternative, dropped: a node-major neighbour table per block in shared memory with thread u as the sole
+// writer of matrix row u -- one barrier per 16 ants instead of one per ant -- is slower: 16 x 2 dependent shared-memory
+// read-modify-writes per thread and block, plus building the table, cost more than 16 barriers.)
+__device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const float* __restrict__ inv, uint16_t* __restrict__ ring,
+                                                  const uint16_t* __restrict__ tours, int b, int n, int A, int a_lo, int a_hi) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    constexpr int kBlk = 16;
+    const uint16_t* T = tours + ((size_t)b * A + a_lo) * n;          // ants [a_lo, a_hi) are contiguous
+    const int count = a_hi - a_lo;
+    const int words = (kBlk * n + 1) / 2;                             // 32-bit words per block (tour rows are contiguous)
+    // thread roles: with at least 2n threads the lower half adds to cell (t_k, t_k+1) and the upper half to (t_k+1, t_k)
+    // -- one load / add / store per thread and ant; with fewer, thread k does both cells of edge k
+    const bool split = nth >= 2 * n;
+    const int half = nth >> 1;
+    const int ke = split ? (tid >= half ? tid - half : tid) : tid;   // edge index of this thread
+    const bool flip = split && tid >= half;
+    const bool on = ke < n;
+    const int k0 = flip ? (ke + 1 == n ? 0 : ke + 1) : ke;            // row endpoint, column endpoint of this thread's cell
+    const int k1 = flip ? ke : (ke + 1 == n ? 0 : ke + 1);
+    constexpr int kRegs = 8;                                          // words per thread per block: 8 * 256 * 2 >= kBlk * 224
+    uint32_t stage[kRegs];
+    auto fetch = [&](int blk) {                                       // global -> registers (block `blk`), 4-byte loads
+        const size_t base = (size_t)blk * kBlk * n;                   // in uint16 units; even because kBlk is
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(T + base);
+        const int elems = min(kBlk, count - blk * kBlk) * n, full = elems >> 1;   // an odd last element gets a 2-byte load
+#pragma unroll
+        for (int q = 0; q < kRegs; ++q) {
+            const int wi = tid + q * nth;
+            uint32_t w = 0u;
+            if (wi < full) w = src[wi];
+            else if (wi == full && (elems & 1)) w = T[base + elems - 1];
+            stage[q] = w;
+        }
+    };
+    auto fetch16 = [&](int blk) {                                     // same with 2-byte loads (T not 4-byte aligned)
+        const uint16_t* src = T + (size_t)blk * kBlk * n;
+        const int avail = min(kBlk, count - blk * kBlk) * n;
+#pragma unroll
+        for (int q = 0; q < kRegs; ++q) {
+            const int wi = tid + q * nth;
+            uint32_t lo = 0, hi16 = 0;
+            if (wi < words) {
+                if (2 * wi < avail) lo = src[2 * wi];
+                if (2 * wi + 1 < avail) hi16 = src[2 * wi + 1];
+            }
+            stage[q] = lo | (hi16 << 16);
+        }
+    };
+    auto park = [&](int blk) {                                        // registers -> ring slot blk & 1
+        uint32_t* dst = reinterpret_cast<uint32_t*>(ring + (size_t)(blk & 1) * (2 * words));
+#pragma unroll
+        for (int q = 0; q < kRegs; ++q) {
+            const int wi = tid + q * nth;
+            if (wi < words) dst[wi] = stage[q];
+        }
+    };
+    const int nblk = (count + kBlk - 1) / kBlk;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(T) & 3) == 0);
+    if (nblk > 0) {
+        if (aligned) fetch(0); else fetch16(0);
+        park(0);
+    }
+    __syncthreads();
+    for (int blk = 0; blk < nblk; ++blk) {
+        if (blk + 1 < nblk) { if (aligned) fetch(blk + 1); else fetch16(blk + 1); }
+        const uint16_t* tb = ring + (size_t)(blk & 1) * (2 * words);
+        const int m = min(kBlk, count - blk * kBlk);
+        int u = on ? tb[k0] : 0, v = on ? tb[k1] : 0;
+        for (int i = 0; i < m; ++i) {
+            const float w = inv[a_lo + blk * kBlk + i];
+            int un = 0, vn = 0;
+            if (on && i + 1 < m) {                                    // next ant's edge, ahead of the barrier
+                un = tb[(i + 1) * n + k0];
+                vn = tb[(i + 1) * n + k1];
+            }
+            if (on) {
+                M[u * n + v] = __fadd_rn(M[u * n + v], w);
+                if (!split) M[v * n + u] = __fadd_rn(M[v * n + u], w);
+            }
+            __syncthreads();
+            u = un;
+            v = vn;
+        }
+        if (blk + 1 < nblk) park(blk + 1);                            // slot (blk + 1) & 1 was last read in block blk - 1
+        __syncthreads();
+    }
+}
+
 // The same update the way the reference states it (tsp/aco.py:101-114): ants one after another, each ant's 2n cells in
 // parallel.  One CTA per colony keeps the whole pheromone matrix in shared memory; thread k owns tour edge k of the
 // current ant and adds 1 / cost to cells (t_k, t_k+1) and (t_k+1, t_k) -- the cells of one ant are pairwise distinct for
 // n >= 3, so there is nothing to order inside an ant, and the per-ant barrier gives every cell its additions in ant
-// order: bit-identical to the reference, with ~20 warp-instructions per ant instead of a counting sort per matrix row
-// (4.2 k instructions for each of the n rows).  No neighbour table is needed.  Used when the matrix fits in shared memory and the colony has at most ~1 k ants (the
+// order: bit-identical to the reference, at a few dozen warp-instructions per ant instead of a counting sort per matrix
+// row (4.2 k instructions for each of the n rows).  No neighbour table in global memory is needed.  Used when the matrix fits in shared memory and the colony has at most ~1 k ants (the
 // chain is sequential in the ants; big colonies take tsp_update_row_kernel).
-//   smem: M f32 [n][n] | inv f32 [A] | tour ring u16 [2][16 * n]
+//   smem: M f32 [n][n] | inv f32 [A] | tour ring u16 [2][16 n + 2]
 __global__ void __launch_bounds__(256) tsp_update_seq_kernel(float* __restrict__ ph, const uint16_t* __restrict__ tours,
                                                              const float* __restrict__ costs, int n, int A, float decay, int elitist,
                                                              int min_max, float ph_min, const float* __restrict__ ph_max,
@@ -218,7 +311,6 @@ __global__ void __launch_bounds__(256) tsp_update_seq_kernel(float* __restrict__
                                                              float* __restrict__ prod) {
     DACO_DYN_SMEM16(smem);
     __shared__ int s_best;
-    constexpr int D = 8;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
     float* M = reinterpret_cast<float*>(smem);
     float* inv = M + (size_t)n * n;
@@ -252,92 +344,7 @@ __global__ void __launch_bounds__(256) tsp_update_seq_kernel(float* __restrict__
         a_hi = a_lo + 1;
     }
     __syncthreads();
-    // Tours reach the chain through a double-buffered shared-memory ring of kBlk ants: the global loads of block j + 1 are
-    // issued (into registers) before block j is processed and parked in shared memory after it, so their latency is
-    // covered by kBlk ant steps; inside a block the next ant's edge is read from shared memory one step ahead.
-    constexpr int kBlk = 16;
-    const uint16_t* T = tours + ((size_t)b * A + a_lo) * n;          // ants [a_lo, a_hi) are contiguous
-    const int count = a_hi - a_lo;
-    uint16_t* ring = reinterpret_cast<uint16_t*>(inv + A);            // [2][kBlk * n]
-    const int words = (kBlk * n + 1) / 2;                             // 32-bit words per block (tour rows are contiguous)
-    // thread roles: with at least 2n threads the lower half adds to cell (t_k, t_k+1) and the upper half to (t_k+1, t_k)
-    // -- one load / add / store per thread and ant; with fewer, thread k does both cells of edge k
-    const bool split = nth >= 2 * n;
-    const int half = nth >> 1;
-    const int ke = split ? (tid >= half ? tid - half : tid) : tid;   // edge index of this thread
-    const bool flip = split && tid >= half;
-    const bool on = ke < n;
-    const int k0 = flip ? (ke + 1 == n ? 0 : ke + 1) : ke;            // row endpoint, column endpoint of this thread's cell
-    const int k1 = flip ? ke : (ke + 1 == n ? 0 : ke + 1);
-    constexpr int kRegs = 8;                                          // words per thread per block: 8 * 256 * 2 >= kBlk * 224
-    uint32_t stage[kRegs];
-    auto fetch = [&](int blk) {                                       // global -> registers (block `blk`), 4-byte loads
-        const size_t base = (size_t)blk * kBlk * n;                   // in uint16 units; even because kBlk is
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(T + base);
-        const int elems = min(kBlk, count - blk * kBlk) * n, full = elems >> 1;   // an odd last element gets a 2-byte load
-#pragma unroll
-        for (int q = 0; q < kRegs; ++q) {
-            const int wi = tid + q * nth;
-            uint32_t w = 0u;
-            if (wi < full) w = src[wi];
-            else if (wi == full && (elems & 1)) w = T[base + elems - 1];
-            stage[q] = w;
-        }
-    };
-    auto park = [&](int blk) {                                        // registers -> ring slot blk & 1
-        uint32_t* dst = reinterpret_cast<uint32_t*>(ring + (size_t)(blk & 1) * (2 * words));
-#pragma unroll
-        for (int q = 0; q < kRegs; ++q) {
-            const int wi = tid + q * nth;
-            if (wi < words) dst[wi] = stage[q];
-        }
-    };
-    const int nblk = (count + kBlk - 1) / kBlk;
-    // T + base must be 4-byte aligned: base * 2 bytes with base a multiple of kBlk * n (even); T itself is, when
-    // ((b * A + a_lo) * n) is even -- otherwise fall back to 2-byte loads through the same ring
-    const bool aligned = ((reinterpret_cast<uintptr_t>(T) & 3) == 0);
-    auto fetch16 = [&](int blk) {
-        const uint16_t* src = T + (size_t)blk * kBlk * n;
-        const int avail = min(kBlk, count - blk * kBlk) * n;
-#pragma unroll
-        for (int q = 0; q < kRegs; ++q) {
-            const int wi = tid + q * nth;
-            uint32_t lo = 0, hi16 = 0;
-            if (wi < words) {
-                if (2 * wi < avail) lo = src[2 * wi];
-                if (2 * wi + 1 < avail) hi16 = src[2 * wi + 1];
-            }
-            stage[q] = lo | (hi16 << 16);
-        }
-    };
-    if (nblk > 0) {
-        if (aligned) fetch(0); else fetch16(0);
-        park(0);
-    }
-    __syncthreads();
-    for (int blk = 0; blk < nblk; ++blk) {
-        if (blk + 1 < nblk) { if (aligned) fetch(blk + 1); else fetch16(blk + 1); }
-        const uint16_t* tb = ring + (size_t)(blk & 1) * (2 * words);
-        const int m = min(kBlk, count - blk * kBlk);
-        int u = on ? tb[k0] : 0, v = on ? tb[k1] : 0;
-        for (int i = 0; i < m; ++i) {
-            const float w = inv[a_lo + blk * kBlk + i];
-            int un = 0, vn = 0;
-            if (on && i + 1 < m) {                                    // next ant's edge, ahead of the barrier
-                un = tb[(i + 1) * n + k0];
-                vn = tb[(i + 1) * n + k1];
-            }
-            if (on) {
-                M[u * n + v] = __fadd_rn(M[u * n + v], w);
-                if (!split) M[v * n + u] = __fadd_rn(M[v * n + u], w);
-            }
-            __syncthreads();
-            u = un;
-            v = vn;
-        }
-        if (blk + 1 < nblk) park(blk + 1);                            // slot (blk + 1) & 1 was last read in block blk - 1
-        __syncthreads();
-    }
+    seq_deposit_chain(M, inv, reinterpret_cast<uint16_t*>(inv + A), tours, b, n, A, a_lo, a_hi);
     const float hi = min_max ? ph_max[b] : 0.f;
     for (int i = tid; i < n * n; i += nth) {
         float x = M[i];
@@ -349,6 +356,165 @@ __global__ void __launch_bounds__(256) tsp_update_seq_kernel(float* __restrict__
         }
         P[i] = x;
         if (prod) prod[(size_t)b * n * n + i] = __fmul_rn(x, heu[(size_t)b * n * n + i]);
+    }
+}
+
+// The whole iteration tail of ACO.run (tsp/aco.py:76-90) for one colony in ONE launch: tour costs (ATen summation order,
+// distance matrix staged in shared memory) -> iteration best vs running best, MMAS bookkeeping (what tsp_best_kernel
+// does) -> evaporation + the ant-sequential deposit chain -> clamp, pheromone and next product matrix out.  Same bits as
+// tsp_cost_tile_kernel + tsp_best_kernel + tsp_update_seq_kernel, two launches and one pass over the tours fewer.
+//   smem: M f32 [n][n] | Dm f32 [n][n] | cs f32 [A] (costs, then 1 / cost) | ring u16 [2][16 n + 2] (phase 1: one tour per warp)
+struct TailParams {
+    float* ph;                 // [B][n][n] in / out
+    const uint16_t* tours;     // [B][A][n]
+    const float* dist;         // [B][n][n]
+    const float* heu;          // [B][n][n]
+    float* prod;               // [B][n][n] out
+    float* costs;              // [B][A] out
+    float* lowest;             // [B] in / out
+    int64_t* shortest;         // [B][n] in / out
+    float* ph_max;             // [B] in / out (min_max)
+    int n, A;
+    float decay;
+    int elitist, min_max;
+    float ph_min;
+    int lbw, vec;              // ATen summation plan of a [A][n] row sum
+};
+
+__global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
+    DACO_DYN_SMEM16(smem);
+    __shared__ float s_c[8], s_m[8];
+    __shared__ int s_i[8];
+    __shared__ int s_improved, s_first, s_bi;
+    __shared__ float s_bc, s_scale;
+    const int n = p.n, A = p.A;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, W = nth >> 5, b = blockIdx.x;
+    float* M = reinterpret_cast<float*>(smem);
+    float* Dm = M + (size_t)n * n;
+    float* cs = Dm + (size_t)n * n;
+    uint16_t* ring = reinterpret_cast<uint16_t*>(cs + A);
+    float* P = p.ph + (size_t)b * n * n;
+    const float* D = p.dist + (size_t)b * n * n;
+    const uint16_t* T = p.tours + (size_t)b * A * n;
+    for (int i = tid; i < n * n; i += nth) {
+        M[i] = P[i];
+        Dm[i] = D[i];
+    }
+    __syncthreads();
+    // ---- costs: a warp per ant, its tour staged in the warp's slice of `ring`, the next ant's tour already in flight
+    {
+        uint16_t* tw = ring + (size_t)warp * n;
+        constexpr int KT = 8;                               // n <= 224 < 8 * 32
+        uint16_t nxt[KT];
+        auto load = [&](int a) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const int k = lane + 32 * j;
+                nxt[j] = (a < A && k < n) ? T[(size_t)a * n + k] : (uint16_t)0;
+            }
+        };
+        load(warp);
+        for (int a = warp; a < A; a += W) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const int k = lane + 32 * j;
+                if (k < n) tw[k] = nxt[j];
+            }
+            __syncwarp();
+            load(a + W);
+            auto edge = [&](int k) -> float { return Dm[(int)tw[k] * n + (int)tw[k == 0 ? n - 1 : k - 1]]; };
+            const float c = aten_row_sum_fn(edge, n, p.lbw, p.vec != 0, lane, p.vec ? (int)(((unsigned)a * (unsigned)n) & 3u) : 0);
+            if (lane == 0) {
+                cs[a] = c;
+                p.costs[(size_t)b * A + a] = c;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- iteration best -> running best, MMAS bookkeeping (tsp/aco.py:79-88)
+    {
+        float bc = INFINITY;
+        int bi = 0x7fffffff;
+        for (int a = tid; a < A; a += nth) {
+            const float c = cs[a];
+            if (c < bc) { bc = c; bi = a; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const float oc = __shfl_xor_sync(DACO_FULL, bc, off);
+            const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
+            if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+        }
+        if (lane == 0) { s_c[warp] = bc; s_i[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bc = lane < W ? s_c[lane] : INFINITY;
+            bi = lane < W ? s_i[lane] : 0x7fffffff;
+            for (int off = 16; off > 0; off >>= 1) {
+                const float oc = __shfl_xor_sync(DACO_FULL, bc, off);
+                const int oi = __shfl_xor_sync(DACO_FULL, bi, off);
+                if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+            }
+            if (lane == 0) {
+                s_improved = bc < p.lowest[b];                                   // tsp/aco.py:81
+                s_first = p.min_max && !(p.ph_max[b] > 0.f);                     // MMAS max not set yet (marker 0)
+                s_bc = bc;
+                s_bi = bi;
+                s_scale = 1.0f;
+            }
+        }
+        __syncthreads();
+    }
+    float hi = p.min_max ? p.ph_max[b] : 0.f;
+    if (s_improved) {
+        const float bc = s_bc;
+        const uint16_t* t = T + (size_t)s_bi * n;
+        for (int k = tid; k < n; k += nth) p.shortest[(size_t)b * n + k] = (int64_t)t[k];
+        if (p.min_max) {
+            // max = problem_size / lowest_cost  ==  reciprocal(lowest) * n   (Tensor.__rtruediv__)
+            const float new_max = __fmul_rn(__fdiv_rn(1.0f, bc), (float)n);
+            if (s_first) {   // self.pheromone *= max / self.pheromone.max()
+                float m = -INFINITY;
+                for (int i = tid; i < n * n; i += nth) m = fmaxf(m, M[i]);
+                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(DACO_FULL, m, off));
+                if (lane == 0) s_m[warp] = m;
+                __syncthreads();
+                if (warp == 0) {
+                    m = lane < W ? s_m[lane] : -INFINITY;
+                    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(DACO_FULL, m, off));
+                    if (lane == 0) s_scale = __fdiv_rn(new_max, m);
+                }
+            }
+            hi = new_max;
+        }
+        __syncthreads();                                     // every thread has read lowest / ph_max before they change
+        if (tid == 0) {
+            p.lowest[b] = bc;
+            if (p.min_max) p.ph_max[b] = __fmul_rn(__fdiv_rn(1.0f, bc), (float)n);
+        }
+    }
+    __syncthreads();
+    // ---- evaporation (+ MMAS rescale), reciprocal costs, deposit chain
+    const float sc = s_scale;
+    for (int i = tid; i < n * n; i += nth) {
+        float x = M[i];
+        if (p.min_max) x = __fmul_rn(x, sc);
+        M[i] = __fmul_rn(x, p.decay);
+    }
+    for (int a = tid; a < A; a += nth) cs[a] = __fdiv_rn(1.0f, cs[a]);
+    const int a_lo = p.elitist ? s_bi : 0, a_hi = p.elitist ? s_bi + 1 : A;   // costs.min(dim=0): first index of the minimum
+    __syncthreads();
+    seq_deposit_chain(M, cs, ring, p.tours, b, n, A, a_lo, a_hi);
+    for (int i = tid; i < n * n; i += nth) {
+        float x = M[i];
+        if (p.min_max) {
+            // ph[(ph > 1e-9) * ph < min] = min ; ph[ph > max] = max   (tsp/aco.py:117-118)
+            const float gate = __fmul_rn(x > 1e-9f ? 1.0f : 0.0f, x);
+            if (gate < p.ph_min) x = p.ph_min;
+            if (x > hi) x = hi;
+        }
+        P[i] = x;
+        p.prod[(size_t)b * n * n + i] = __fmul_rn(x, p.heu[(size_t)b * n * n + i]);
     }
 }
 

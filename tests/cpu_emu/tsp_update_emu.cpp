@@ -93,6 +93,16 @@ extern "C" const char* emu_tsp_update_seq(float* ph, const uint16_t* tours, cons
     return nullptr;
 }
 
+// tsp_tail_kernel: cost + best tracking + ant-sequential update of one colony in one launch
+extern "C" const char* emu_tsp_tail(float* ph, const uint16_t* tours, const float* dist, const float* heu, float* prod, float* costs,
+                                    float* lowest, int64_t* shortest, float* ph_max, int n, int A, float decay, int elitist, int min_max,
+                                    float ph_min, int lbw, int vec) {
+    if (!ph || !tours || !dist || !heu || !prod || !costs || !lowest || !shortest || n < 3 || A < 1) return "bad arguments";
+    const TailParams p{ph, tours, dist, heu, prod, costs, lowest, shortest, ph_max, n, A, decay, elitist, min_max, ph_min, lbw, vec};
+    emu::launch(tsp_tail_kernel, p, 1, 1, 256, ((size_t)2 * n * n + A) * 4 + (size_t)2 * (16 * n + 2) * 2);
+    return nullptr;
+}
+
 // knn_refresh_kernel: candidate lists (columns of the 32 largest entries per row) from a product matrix [rows][n]
 extern "C" const char* emu_knn_refresh(const float* prod, uint8_t* knn, int n, int rows) {
     if (!prod || !knn || n <= 32 || n > 256 || rows < 1) return "bad arguments";

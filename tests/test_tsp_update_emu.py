@@ -154,6 +154,52 @@ def test_seq_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, 
     assert torch.equal(prod, ph * heu)
 
 
+@pytest.mark.parametrize("kw", [{}, {"elitist": True}, {"min_max": True}])
+@pytest.mark.parametrize("n,A", [(20, 8), (100, 40), (61, 130)])
+def test_tail_kernel_on_host_equals_cost_best_update_sequence(emu_u, n, A, kw):
+    """tsp_tail_kernel (cost + best tracking + MMAS bookkeeping + ant-sequential update in one launch) over three
+    iterations with fresh tours each: costs equal to the cost kernel's bits, lowest cost / best tour / MMAS max and the
+    pheromone equal to the reference's run loop (tsp/aco.py:76-90) restated with the oracle ops."""
+    emu_u.emu_tsp_tail.restype = ctypes.c_char_p
+    emu_u.emu_tsp_tail.argtypes = [vp] * 9 + [ci, ci, cf, ci, ci, cf, ci, ci]
+    from deepaco_b200 import _engine as E
+    elitist, min_max = kw.get("elitist", False), kw.get("min_max", False)
+    torch.manual_seed(n + A)
+    heu = (torch.rand(n, n) + 0.1).contiguous()
+    ph = (torch.ones(n, n) * (0.1 if min_max else 1.0)).contiguous()
+    ref_ph = ph.clone()
+    lowest, shortest, ph_max = torch.tensor([float("inf")]), torch.zeros(n, dtype=torch.int64), torch.zeros(1)
+    ref_low, ref_short, ref_max = float("inf"), None, None
+    bw, vec, _ = E.aten_sum_plan(n, A)
+    lbw = int(np.log2(min(bw, 32)))
+    for it in range(3):
+        dist, paths = _instance(n, A, 31 * it + n)
+        tours = paths.T.contiguous().to(torch.int16)
+        want_costs, _ = _costs(emu_u, dist, paths, "tile")
+        costs = torch.full((A,), float("nan"))
+        prod = torch.full((n, n), float("nan"))
+        err = emu_u.emu_tsp_tail(_ptr(ph), _ptr(tours), _ptr(dist), _ptr(heu), _ptr(prod), _ptr(costs), _ptr(lowest), _ptr(shortest),
+                                 _ptr(ph_max), n, A, 0.9, int(elitist), int(min_max), 0.1, lbw, int(vec))
+        assert err is None, err
+        assert torch.equal(costs, want_costs)
+        # the reference's run loop on the same costs (tsp/aco.py:79-90)
+        best_cost, best_idx = want_costs.min(dim=0)
+        if best_cost < ref_low:
+            ref_short, ref_low = paths[:, best_idx].clone(), best_cost.clone()
+            if min_max:
+                new_max = n / ref_low                                   # Tensor.__rtruediv__: reciprocal * n
+                if ref_max is None:
+                    ref_ph = ref_ph * (new_max / ref_ph.max())
+                ref_max = new_max
+        ref_ph = O.tsp_update_pheromone(ref_ph, paths, want_costs, decay=0.9, elitist=elitist, min_max=min_max, ph_min=0.1,
+                                        ph_max=ref_max)
+        assert torch.equal(ph, ref_ph), it
+        assert float(lowest) == float(ref_low) and torch.equal(shortest, ref_short)
+        assert torch.equal(prod, ph * heu)
+        if min_max:
+            assert float(ph_max) == float(ref_max)
+
+
 @pytest.mark.parametrize("n,rows", [(33, 5), (100, 100), (256, 19)])
 def test_knn_refresh_kernel_on_host_selects_the_32_largest_per_row(emu_u, n, rows):
     """knn_refresh_kernel: per row the columns of the 32 largest product entries, ties to the lower column (the floor
