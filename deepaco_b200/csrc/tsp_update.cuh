@@ -275,21 +275,43 @@ __device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const f
         if (blk + 1 < nblk) { if (aligned) fetch(blk + 1); else fetch16(blk + 1); }
         const uint16_t* tb = ring + (size_t)(blk & 1) * (2 * words);
         const int m = min(kBlk, count - blk * kBlk);
-        int u = on ? tb[k0] : 0, v = on ? tb[k1] : 0;
-        for (int i = 0; i < m; ++i) {
-            const float w = inv[a_lo + blk * kBlk + i];
-            int un = 0, vn = 0;
-            if (on && i + 1 < m) {                                    // next ant's edge, ahead of the barrier
-                un = tb[(i + 1) * n + k0];
-                vn = tb[(i + 1) * n + k1];
+        if (m == kBlk) {
+            // full block: the 16 cells of this thread (and their weights) go to registers first -- independent loads, no
+            // barrier between them -- and the dependent part of an ant step is load cell / add / store / barrier
+            int cu[kBlk], cv[kBlk];
+            float w[kBlk];
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) {
+                const int u = on ? tb[i * n + k0] : 0, v = on ? tb[i * n + k1] : 0;
+                cu[i] = u * n + v;
+                cv[i] = v * n + u;
+                w[i] = inv[a_lo + blk * kBlk + i];
             }
-            if (on) {
-                M[u * n + v] = __fadd_rn(M[u * n + v], w);
-                if (!split) M[v * n + u] = __fadd_rn(M[v * n + u], w);
+#pragma unroll
+            for (int i = 0; i < kBlk; ++i) {
+                if (on) {
+                    M[cu[i]] = __fadd_rn(M[cu[i]], w[i]);
+                    if (!split) M[cv[i]] = __fadd_rn(M[cv[i]], w[i]);
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            u = un;
-            v = vn;
+        } else {
+            int u = on ? tb[k0] : 0, v = on ? tb[k1] : 0;
+            for (int i = 0; i < m; ++i) {
+                const float w = inv[a_lo + blk * kBlk + i];
+                int un = 0, vn = 0;
+                if (on && i + 1 < m) {                                // next ant's edge, ahead of the barrier
+                    un = tb[(i + 1) * n + k0];
+                    vn = tb[(i + 1) * n + k1];
+                }
+                if (on) {
+                    M[u * n + v] = __fadd_rn(M[u * n + v], w);
+                    if (!split) M[v * n + u] = __fadd_rn(M[v * n + u], w);
+                }
+                __syncthreads();
+                u = un;
+                v = vn;
+            }
         }
         if (blk + 1 < nblk) park(blk + 1);                            // slot (blk + 1) & 1 was last read in block blk - 1
         __syncthreads();
@@ -387,6 +409,7 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
     __shared__ int s_i[8];
     __shared__ int s_improved, s_first, s_bi;
     __shared__ float s_bc, s_scale;
+    __shared__ uint64_t s_bar;
     const int n = p.n, A = p.A;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, W = nth >> 5, b = blockIdx.x;
     float* M = reinterpret_cast<float*>(smem);
@@ -396,13 +419,73 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
     float* P = p.ph + (size_t)b * n * n;
     const float* D = p.dist + (size_t)b * n * n;
     const uint16_t* T = p.tours + (size_t)b * A * n;
-    for (int i = tid; i < n * n; i += nth) {
-        M[i] = P[i];
-        Dm[i] = D[i];
+    const float* H = p.heu + (size_t)b * n * n;
+    // matrices move by TMA bulk copies when 16-byte granular (n even): pheromone and distances now; the heuristic later,
+    // into the distance matrix's place once the costs are done, so that its read hides behind the deposit chain
+    const uint32_t mat_bytes = (uint32_t)n * n * 4;
+    const bool bulk = (mat_bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(D) |
+                                                  reinterpret_cast<uintptr_t>(H)) & 15) == 0;
+    auto bulk_load = [&](float* dst, const float* src) {   // thread 0 only
+        constexpr uint32_t kChunk = 32768;
+        for (uint32_t off = 0; off < mat_bytes; off += kChunk)
+            tma_bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off,
+                         mat_bytes - off < kChunk ? mat_bytes - off : kChunk, &s_bar);
+    };
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_barrier_init();
+            mbar_expect_tx(&s_bar, 2 * mat_bytes);
+            bulk_load(M, P);
+            bulk_load(Dm, D);
+        }
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = tid; i < n * n; i += nth) {
+            M[i] = P[i];
+            Dm[i] = D[i];
+        }
     }
     __syncthreads();
-    // ---- costs: a warp per ant, its tour staged in the warp's slice of `ring`, the next ant's tour already in flight
-    {
+    // ---- costs: a warp per ant, the next ant's tour already in flight
+    if (!p.vec && p.lbw == 5) {
+        // 32 <= n < 128, ATen's plain plan: lane l sums elements l, l + 32, l + 64, l + 96 into one accumulator each
+        // (aten_row_sum_fn's non-vectorised branch) -- exactly the elements the lane loaded, so the tour stays in
+        // registers and the predecessor t[k - 1] comes from the lane below by shuffle
+        constexpr int KT = 4;
+        uint32_t nxt[KT];
+        auto load = [&](int a) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const int k = lane + 32 * j;
+                nxt[j] = (a < A && k < n) ? (uint32_t)T[(size_t)a * n + k] : 0u;
+            }
+        };
+        const int jl = (n - 1) >> 5, ll = (n - 1) & 31;
+        load(warp);
+        for (int a = warp; a < A; a += W) {
+            uint32_t cur[KT];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) cur[j] = nxt[j];
+            load(a + W);
+            uint32_t carry = __shfl_sync(DACO_FULL, jl == 0 ? cur[0] : jl == 1 ? cur[1] : jl == 2 ? cur[2] : cur[3], ll);   // t[n - 1]
+            float acc[KT];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const uint32_t up = __shfl_up_sync(DACO_FULL, cur[j], 1);
+                const uint32_t pred = lane == 0 ? carry : up;
+                carry = __shfl_sync(DACO_FULL, cur[j], 31);
+                acc[j] = lane + 32 * j < n ? __fadd_rn(0.f, Dm[cur[j] * (uint32_t)n + pred]) : 0.f;
+            }
+            const float c = warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
+            if (lane == 0) {
+                cs[a] = c;
+                p.costs[(size_t)b * A + a] = c;
+            }
+        }
+    } else {
+        // general plan: the tour staged in the warp's slice of `ring`
         uint16_t* tw = ring + (size_t)warp * n;
         constexpr int KT = 8;                               // n <= 224 < 8 * 32
         uint16_t nxt[KT];
@@ -430,6 +513,11 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
             }
             __syncwarp();
         }
+    }
+    __syncthreads();
+    if (bulk && tid == 0) {                                  // distances are done with: the heuristic takes their place
+        mbar_expect_tx(&s_bar, mat_bytes);
+        bulk_load(Dm, H);
     }
     __syncthreads();
     // ---- iteration best -> running best, MMAS bookkeeping (tsp/aco.py:79-88)
@@ -505,6 +593,8 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
     const int a_lo = p.elitist ? s_bi : 0, a_hi = p.elitist ? s_bi + 1 : A;   // costs.min(dim=0): first index of the minimum
     __syncthreads();
     seq_deposit_chain(M, cs, ring, p.tours, b, n, A, a_lo, a_hi);
+    if (bulk) mbar_wait(&s_bar, 1);
+    const float* Hs = bulk ? Dm : H;
     for (int i = tid; i < n * n; i += nth) {
         float x = M[i];
         if (p.min_max) {
@@ -514,7 +604,7 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
             if (x > hi) x = hi;
         }
         P[i] = x;
-        p.prod[(size_t)b * n * n + i] = __fmul_rn(x, p.heu[(size_t)b * n * n + i]);
+        p.prod[(size_t)b * n * n + i] = __fmul_rn(x, Hs[i]);
     }
 }
 

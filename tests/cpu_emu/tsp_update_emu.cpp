@@ -16,6 +16,13 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 #define DACO_DYN_SMEM16(name) unsigned char* name = emu::ctx.smem
 #define __shared__ static
 
+namespace deepaco {   // bulk-copy stand-ins (cuda_emu.h)
+static inline void mbar_init(uint64_t* bar, uint32_t) { emu_mbar_init(bar); }
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { emu_mbar_expect_tx(bar, bytes); }
+static inline void fence_barrier_init() {}
+static inline void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { emu_bulk_copy(dst, src, bytes, bar); }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) { emu_mbar_wait(bar, parity); }
+}  // namespace deepaco
 #include "../../deepaco_b200/csrc/tsp_update.cuh"
 #include "../../deepaco_b200/csrc/cvrp_update.cuh"
 #include "../../deepaco_b200/csrc/backward.cuh"
