@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(128) tsp_update_kernel(float* __restrict__ ph,
 // (Measured alternative, dropped: a node-major neighbour table per block in shared memory with thread u as the sole
 // writer of matrix row u -- one barrier per 16 ants instead of one per ant -- is slower: 16 x 2 dependent shared-memory
 // read-modify-writes per thread and block, plus building the table, cost more than 16 barriers.)
-__device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const float* __restrict__ inv, uint16_t* __restrict__ ring,
-                                                  const uint16_t* __restrict__ tours, int b, int n, int A, int a_lo, int a_hi) {
+template <bool SPLIT>
+__device__ __forceinline__ void seq_deposit_chain_impl(float* __restrict__ M, const float* __restrict__ inv, uint16_t* __restrict__ ring,
+                                                       const uint16_t* __restrict__ tours, int b, int n, int A, int a_lo, int a_hi) {
     const int tid = threadIdx.x, nth = blockDim.x;
     constexpr int kBlk = 16;
     const uint16_t* T = tours + ((size_t)b * A + a_lo) * n;          // ants [a_lo, a_hi) are contiguous
@@ -220,7 +221,7 @@ __device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const f
     const int words = (kBlk * n + 1) / 2;                             // 32-bit words per block (tour rows are contiguous)
     // thread roles: with at least 2n threads the lower half adds to cell (t_k, t_k+1) and the upper half to (t_k+1, t_k)
     // -- one load / add / store per thread and ant; with fewer, thread k does both cells of edge k
-    const bool split = nth >= 2 * n;
+    constexpr bool split = SPLIT;
     const int half = nth >> 1;
     const int ke = split ? (tid >= half ? tid - half : tid) : tid;   // edge index of this thread
     const bool flip = split && tid >= half;
@@ -278,21 +279,20 @@ __device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const f
         if (m == kBlk) {
             // full block: the 16 cells of this thread (and their weights) go to registers first -- independent loads, no
             // barrier between them -- and the dependent part of an ant step is load cell / add / store / barrier
-            int cu[kBlk], cv[kBlk];
+            float* cu[kBlk];
+            float* cv[kBlk];
             float w[kBlk];
 #pragma unroll
             for (int i = 0; i < kBlk; ++i) {
                 const int u = on ? tb[i * n + k0] : 0, v = on ? tb[i * n + k1] : 0;
-                cu[i] = u * n + v;
-                cv[i] = v * n + u;
+                cu[i] = M + (u * n + v);
+                cv[i] = M + (v * n + u);
                 w[i] = inv[a_lo + blk * kBlk + i];
             }
 #pragma unroll
             for (int i = 0; i < kBlk; ++i) {
-                if (on) {
-                    M[cu[i]] = __fadd_rn(M[cu[i]], w[i]);
-                    if (!split) M[cv[i]] = __fadd_rn(M[cv[i]], w[i]);
-                }
+                if (on) *cu[i] = __fadd_rn(*cu[i], w[i]);
+                if (!split && on) *cv[i] = __fadd_rn(*cv[i], w[i]);
                 __syncthreads();
             }
         } else {
@@ -316,6 +316,12 @@ __device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const f
         if (blk + 1 < nblk) park(blk + 1);                            // slot (blk + 1) & 1 was last read in block blk - 1
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ void seq_deposit_chain(float* __restrict__ M, const float* __restrict__ inv, uint16_t* __restrict__ ring,
+                                                  const uint16_t* __restrict__ tours, int b, int n, int A, int a_lo, int a_hi) {
+    if ((int)blockDim.x >= 2 * n) seq_deposit_chain_impl<true>(M, inv, ring, tours, b, n, A, a_lo, a_hi);
+    else seq_deposit_chain_impl<false>(M, inv, ring, tours, b, n, A, a_lo, a_hi);
 }
 
 // The same update the way the reference states it (tsp/aco.py:101-114): ants one after another, each ant's 2n cells in
