@@ -242,6 +242,20 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
         const int c = atoi(e);
         if (c >= 1 && c <= 8 && c <= B) { chunks = c; for (int k = 0; k <= c; ++k) cuts[k] = (int)((long)B * k / c); }
     }
+    if (const char* e = getenv("DEEPACO_HOST_CUTS")) {     // explicit ascending boundaries "16,72,224", for experiments
+        int c = 0, prev = 0;
+        bool ok = true;
+        int tmp[9] = {0};
+        for (const char* q = e; ok && *q && c < 7;) {
+            char* end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q || v <= prev || v >= B) { ok = false; break; }
+            tmp[++c] = prev = (int)v;
+            q = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') ok = false;
+        }
+        if (ok && c >= 1) { chunks = c + 1; tmp[chunks] = B; for (int k = 0; k <= chunks; ++k) cuts[k] = tmp[k]; }
+    }
     const size_t mat1 = (size_t)n * n;
     // the internal streams start after everything already queued on the caller's stream (the buffers may be in use)
     DACO_CHECK_CUDA(cudaEventRecord(aux.fork, st));

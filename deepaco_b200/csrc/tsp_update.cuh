@@ -459,35 +459,43 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
         // 32 <= n < 128, ATen's plain plan: lane l sums elements l, l + 32, l + 64, l + 96 into one accumulator each
         // (aten_row_sum_fn's non-vectorised branch) -- exactly the elements the lane loaded, so the tour stays in
         // registers and the predecessor t[k - 1] comes from the lane below by shuffle
-        constexpr int KT = 4;
-        uint32_t nxt[KT];
-        auto load = [&](int a) {
+        // Tours come straight from L2: kAhead ants per warp are in flight (one ant's arithmetic is ~150 cycles, the load
+        // latency several hundred).
+        constexpr int KT = 4, kAhead = 4;
+        uint32_t q[kAhead][KT];
+        auto load = [&](uint32_t (&dst)[KT], int a) {
 #pragma unroll
             for (int j = 0; j < KT; ++j) {
                 const int k = lane + 32 * j;
-                nxt[j] = (a < A && k < n) ? (uint32_t)T[(size_t)a * n + k] : 0u;
+                dst[j] = (a < A && k < n) ? (uint32_t)T[(size_t)a * n + k] : 0u;
             }
         };
         const int jl = (n - 1) >> 5, ll = (n - 1) & 31;
-        load(warp);
-        for (int a = warp; a < A; a += W) {
-            uint32_t cur[KT];
 #pragma unroll
-            for (int j = 0; j < KT; ++j) cur[j] = nxt[j];
-            load(a + W);
-            uint32_t carry = __shfl_sync(DACO_FULL, jl == 0 ? cur[0] : jl == 1 ? cur[1] : jl == 2 ? cur[2] : cur[3], ll);   // t[n - 1]
-            float acc[KT];
+        for (int d = 0; d < kAhead; ++d) load(q[d], warp + d * W);
+        for (int a0 = warp; a0 < A; a0 += kAhead * W) {
 #pragma unroll
-            for (int j = 0; j < KT; ++j) {
-                const uint32_t up = __shfl_up_sync(DACO_FULL, cur[j], 1);
-                const uint32_t pred = lane == 0 ? carry : up;
-                carry = __shfl_sync(DACO_FULL, cur[j], 31);
-                acc[j] = lane + 32 * j < n ? __fadd_rn(0.f, Dm[cur[j] * (uint32_t)n + pred]) : 0.f;
-            }
-            const float c = warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
-            if (lane == 0) {
-                cs[a] = c;
-                p.costs[(size_t)b * A + a] = c;
+            for (int d = 0; d < kAhead; ++d) {
+                const int a = a0 + d * W;
+                if (a >= A) break;                                  // warp-uniform
+                uint32_t cur[KT];
+#pragma unroll
+                for (int j = 0; j < KT; ++j) cur[j] = q[d][j];
+                load(q[d], a + kAhead * W);
+                uint32_t carry = __shfl_sync(DACO_FULL, jl == 0 ? cur[0] : jl == 1 ? cur[1] : jl == 2 ? cur[2] : cur[3], ll);   // t[n - 1]
+                float acc[KT];
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const uint32_t up = __shfl_up_sync(DACO_FULL, cur[j], 1);
+                    const uint32_t pred = lane == 0 ? carry : up;
+                    carry = __shfl_sync(DACO_FULL, cur[j], 31);
+                    acc[j] = lane + 32 * j < n ? __fadd_rn(0.f, Dm[cur[j] * (uint32_t)n + pred]) : 0.f;
+                }
+                const float c = warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
+                if (lane == 0) {
+                    cs[a] = c;
+                    p.costs[(size_t)b * A + a] = c;
+                }
             }
         }
     } else {

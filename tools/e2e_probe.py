@@ -47,3 +47,13 @@ for chunks in ("1", "2", "3", "4", "8", ""):
         t0 = time.perf_counter()
         t = timed(host_step, 20)
         print(f"run_host chunks={chunks or 'default'} pheromone={'host' if ph is not None else 'ones'}: {t * 1e3:.0f} us/step")
+
+os.environ.pop("DEEPACO_HOST_CHUNKS", None)
+for cuts in ("32,128,224", "16,72,224", "16,64,144,232", "16,56,128,200,240", "24,104,232", "16,80,160,240", "8,40,120,200,248"):
+    os.environ["DEEPACO_HOST_CUTS"] = cuts
+    def host_step():
+        r.run_host(1, 1234, d_h, heu_h, ph_h, low_h, sp_h, st["it"] * r.increment, offs, copy_back_pheromone=True)
+        st["it"] += 1
+    t = timed(host_step, 30)
+    print(f"run_host cuts={cuts} pheromone=host: {t * 1e3:.0f} us/step")
+os.environ.pop("DEEPACO_HOST_CUTS", None)
