@@ -233,10 +233,11 @@ extern "C" int deepaco_tsp_run_host(const deepaco_tsp_run_args* a, int n_iterati
         for (auto& e : aux.done) DACO_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const int B = a->n_colonies, n = a->n, A = a->n_ants;
-    // chunk boundaries: 1/8 | 3/8 | 3/8 | 1/8 of a large batch, halves of a medium one
+    // chunk boundaries: 1/16 | 4/16 | 5/16 | 5/16 | 1/16 of a large batch (the best of the measured partitions,
+    // profiles/r02_e2e_probe.txt), halves of a medium one
     int cuts[9] = {0, B, 0, 0, 0, 0, 0, 0, 0};
     int chunks = 1;
-    if (B >= 64) { chunks = 4; cuts[1] = B / 8; cuts[2] = B / 2; cuts[3] = B - B / 8; cuts[4] = B; }
+    if (B >= 64) { chunks = 5; cuts[1] = B / 16; cuts[2] = 5 * B / 16; cuts[3] = 10 * B / 16; cuts[4] = B - B / 16; cuts[5] = B; }
     else if (B >= 8) { chunks = 2; cuts[1] = B / 2; cuts[2] = B; }
     if (const char* e = getenv("DEEPACO_HOST_CHUNKS")) {   // equal chunks, for experiments
         const int c = atoi(e);

@@ -489,7 +489,10 @@ __global__ void __launch_bounds__(256) tsp_tail_kernel(const TailParams p) {
                     const uint32_t up = __shfl_up_sync(DACO_FULL, cur[j], 1);
                     const uint32_t pred = lane == 0 ? carry : up;
                     carry = __shfl_sync(DACO_FULL, cur[j], 31);
-                    acc[j] = lane + 32 * j < n ? __fadd_rn(0.f, Dm[cur[j] * (uint32_t)n + pred]) : 0.f;
+                    // branch-free: lanes past the end hold tour value 0, read cell (0, pred) and mask the bits to +0
+                    const uint32_t keep = (uint32_t)((lane + 32 * j - n) >> 31);       // all ones iff lane + 32 j < n
+                    const float e = Dm[cur[j] * (uint32_t)n + pred];
+                    acc[j] = __fadd_rn(0.f, __uint_as_float(__float_as_uint(e) & keep));
                 }
                 const float c = warp_tree_sum(__fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]));
                 if (lane == 0) {
