@@ -69,10 +69,10 @@ namespace deepaco {
 bool tsp_update_seq_ok(int n, int n_ants) {
     return n >= 3 && n <= 224 && n_ants <= 1024 && !getenv("DEEPACO_UPDATE_ROWS_ONLY");
 }
-// ... and worth it: the kernel is one sequential chain per colony (~400 cycles per ant), so it pays when many colonies
-// run side by side (several CTAs per SM: n <= 128) and loses to the row-parallel kernel when only a few do.
-// Measured on 256 x TSP-100 x 512: 100 us against 149 + the 20 us the cost kernel spends on the neighbour table; one
-// colony: 100 us against 15.
+// ... and worth it: the kernel is one sequential chain per colony (a shared-memory read-modify-write + barrier per ant),
+// so it pays when many colonies run side by side (several CTAs per SM: n <= 128) and loses to the row-parallel kernel
+// when only a few do.  Measured on 256 x TSP-100 x 512: the whole tail (costs + best + update, tsp_tail_kernel) 90 us
+// against 87 + 5 + 149 us for the three row-parallel launches; one colony: 69 us against 15 for the update alone.
 bool tsp_update_seq_preferred(int n, int n_ants, int n_colonies) {
     if (getenv("DEEPACO_UPDATE_SEQ")) return tsp_update_seq_ok(n, n_ants);
     return tsp_update_seq_ok(n, n_ants) && n <= 128 && n_colonies >= 64;
