@@ -35,7 +35,7 @@ def dev_step():
 
 
 print(f"device-resident step: {timed(dev_step, 20) * 1e3:.0f} us")
-for chunks in ("1", "2", "3", "4", "8", ""):
+for chunks in (("",) if os.environ.get("E2E_PROBE_CUTS") else ("1", "2", "3", "4", "8", "")):
     if chunks:
         os.environ["DEEPACO_HOST_CHUNKS"] = chunks
     else:
@@ -49,7 +49,8 @@ for chunks in ("1", "2", "3", "4", "8", ""):
         print(f"run_host chunks={chunks or 'default'} pheromone={'host' if ph is not None else 'ones'}: {t * 1e3:.0f} us/step")
 
 os.environ.pop("DEEPACO_HOST_CHUNKS", None)
-for cuts in ("32,128,224", "16,72,224", "16,64,144,232", "16,56,128,200,240", "24,104,232", "16,80,160,240", "8,40,120,200,248"):
+CUTS = os.environ.get("E2E_PROBE_CUTS", "32,128,224;16,72,224;16,64,144,232;16,56,128,200,240;24,104,232;16,80,160,240;8,40,120,200,248").split(";")
+for cuts in CUTS:
     os.environ["DEEPACO_HOST_CUTS"] = cuts
     def host_step():
         r.run_host(1, 1234, d_h, heu_h, ph_h, low_h, sp_h, st["it"] * r.increment, offs, copy_back_pheromone=True)
