@@ -155,7 +155,7 @@ def test_seq_update_kernel_on_host_is_bit_identical_to_the_reference_ops(emu_u, 
 
 
 @pytest.mark.parametrize("kw", [{}, {"elitist": True}, {"min_max": True}])
-@pytest.mark.parametrize("n,A", [(20, 8), (100, 40), (61, 130), (136, 40), (33, 16)])
+@pytest.mark.parametrize("n,A", [(20, 8), (100, 40), (61, 130), (136, 40), (33, 16), (32, 17), (127, 33), (128, 20)])
 def test_tail_kernel_on_host_equals_cost_best_update_sequence(emu_u, n, A, kw):
     """tsp_tail_kernel (cost + best tracking + MMAS bookkeeping + ant-sequential update in one launch) over three
     iterations with fresh tours each: costs equal to the cost kernel's bits, lowest cost / best tour / MMAS max and the
