@@ -345,6 +345,36 @@ class TspRunner:
 
 
 # ---- local search -------------------------------------------------------------------------------
+def knn_graph(coords=None, distances=None, k=0, *, diag=1e9, want_distances=True, want_neighbours=True, want_edge_index=False):
+    """deepaco_knn_graph: distance matrix and k-nearest-neighbour edges of one instance ([n, 2] | [n, n]) or a batch
+    ([B, n, 2] | [B, n, n]) in one launch (tsp/utils.py:4-36: torch.norm + diagonal, torch.topk(largest=False), edge_index).
+    Pass `coords` (distances are computed, diagonal = diag) or `distances` (taken as is).
+    Returns (distances | None, nbr_index int32 [.., n, k] | None, nbr_value f32 [.., n, k] | None, edge_index int64 [.., 2, n*k] | None)."""
+    if (coords is None) == (distances is None):
+        raise _lib.DeepAcoError("knn_graph: pass coords or distances, not both")
+    src = f32c(require_cuda(coords if coords is not None else distances, "coords" if coords is not None else "distances"))
+    batched = src.dim() == 3
+    if not batched:
+        src = src[None]
+    B, n = src.shape[0], src.shape[1]
+    if src.shape[2] != (2 if coords is not None else n):
+        raise _lib.DeepAcoError("knn_graph: coords must be [.., n, 2], distances [.., n, n]")
+    k = int(k)
+    dev = src.device
+    want_distances = bool(want_distances) and coords is not None
+    d_out = torch.empty((B, n, n), dtype=torch.float32, device=dev) if want_distances else None
+    idx = torch.empty((B, n, k), dtype=torch.int32, device=dev) if (k > 0 and want_neighbours) else None
+    val = torch.empty((B, n, k), dtype=torch.float32, device=dev) if (k > 0 and want_neighbours) else None
+    ei = torch.empty((B, 2, n * k), dtype=torch.int64, device=dev) if (k > 0 and want_edge_index) else None
+    with torch.cuda.device(dev):
+        check(lib().deepaco_knn_graph(ptr(src) if coords is not None else None, ptr(src) if coords is None else None, n, B, k,
+                                      float(diag), ptr(d_out), ptr(idx), ptr(val), ptr(ei), stream_ptr(dev)), "deepaco_knn_graph")
+    if coords is None:
+        d_out = src
+    pick = (lambda t: t) if batched else (lambda t: None if t is None else t[0])
+    return pick(d_out), pick(idx), pick(val), pick(ei)
+
+
 def paths_to_tours(paths):
     """int64 [n, A] | [B, n, A] -> uint16 [A, n] | [B, A, n]."""
     paths = require_cuda(paths, "paths").to(torch.int64).contiguous()

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "deepaco_tsp_nls": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deepaco_paths_to_tours": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "deepaco_tours_to_paths": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "deepaco_knn_graph": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "deepaco_gnn_weight_count": (_i64, [_i32]),
     "deepaco_gnn_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp]),
     "deepaco_cvrp_sample": (_i32, [_vp, _vp, _vp, _f32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

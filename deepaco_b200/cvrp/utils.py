@@ -10,6 +10,11 @@ DEPOT_COOR = [0.5, 0.5]
 
 
 def gen_distance_matrix(tsp_coordinates):
+    '''cvrp/utils.py:18-22: Euclidean distances with 1e-10 on the diagonal.  CUDA coordinates: one deepaco_knn_graph launch
+    (same bits); host coordinates: the op chain on the host, as in the reference.'''
+    if tsp_coordinates.is_cuda:
+        from .. import _engine as E
+        return E.knn_graph(coords=tsp_coordinates, k=0, diag=1e-10)[0]
     n = len(tsp_coordinates)
     d = torch.norm(tsp_coordinates[:, None] - tsp_coordinates, dim=2, p=2)
     d[torch.arange(n), torch.arange(n)] = 1e-10      # cvrp/utils.py:21

@@ -164,15 +164,17 @@ def knn_heuristic_matrices(weights, feats, node_features, distances, k_sparse, e
     """Batched instance -> graph -> network -> dense heuristic front end for k-nearest-neighbour TSP graphs
     (tsp/utils.py:16-36 + tsp/net.py:84-102 + the `+ EPS` of tsp/test.ipynb cell 1) without any per-instance
     Python: node_features [B, n, feats], distances [B, n, n] -> heuristic [B, n, n]."""
+    from . import _engine
     B, n = distances.shape[0], distances.shape[1]
     dev = distances.device
-    near_d, near_i = torch.topk(distances, k=k_sparse, dim=2, largest=False)       # sorted by source, constant degree
+    # torch.topk(distances, k, dim=2, largest=False) by deepaco_knn_graph: edges sorted by source, constant degree
+    _, near_i, near_d, _ = _engine.knn_graph(distances=distances, k=k_sparse)
     E = n * k_sparse
     row_ptr = (torch.arange(n + 1, device=dev, dtype=torch.int32) * k_sparse).expand(B, n + 1).contiguous()
     order = torch.arange(E, device=dev, dtype=torch.int32).expand(B, E).contiguous()
     src_s = (order // k_sparse).contiguous()                                          # constant degree: source = e // k
     _, dense = _launch_gnn(weights, feats, node_features.to(torch.float32).contiguous(), row_ptr,
-                           near_i.reshape(B, E).to(torch.int32).contiguous(), near_d.reshape(B, E).to(torch.float32).contiguous(),
+                           near_i.reshape(B, E), near_d.reshape(B, E),
                            order, False, eps, src_s)
     return dense
 

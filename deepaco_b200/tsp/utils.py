@@ -6,7 +6,12 @@ from ..net import Data
 
 
 def gen_distance_matrix(tsp_coordinates):
-    '''[n, 2] coordinates -> [n, n] Euclidean distances with 1e9 on the diagonal (tsp/utils.py:4-14).'''
+    '''[n, 2] coordinates -> [n, n] Euclidean distances with 1e9 on the diagonal (tsp/utils.py:4-14).
+    CUDA coordinates: one launch of deepaco_knn_graph (bit-identical to the op chain below, tests/test_gpu_graph.py);
+    host coordinates: the reference's op chain on the host, as there.'''
+    if tsp_coordinates.is_cuda:
+        from .. import _engine as E
+        return E.knn_graph(coords=tsp_coordinates, k=0, diag=1e9)[0]
     n = len(tsp_coordinates)
     d = torch.norm(tsp_coordinates[:, None] - tsp_coordinates, dim=2, p=2)
     d[torch.arange(n), torch.arange(n)] = 1e9
@@ -14,12 +19,17 @@ def gen_distance_matrix(tsp_coordinates):
 
 
 def knn_graph(tsp_coordinates, k_sparse, start_node=None):
-    '''k-nearest-neighbour graph (tsp/utils.py:16-36; start_node one-hot node feature as tsp_nls/utils.py:37-43).'''
+    '''k-nearest-neighbour graph (tsp/utils.py:16-36; start_node one-hot node feature as tsp_nls/utils.py:37-43).
+    CUDA coordinates: distances, topk and edge_index come out of one deepaco_knn_graph launch.'''
     n = len(tsp_coordinates)
-    distances = gen_distance_matrix(tsp_coordinates)
-    near_d, near_i = torch.topk(distances, k=k_sparse, dim=1, largest=False)
-    src = torch.arange(n, device=near_i.device).repeat_interleave(k_sparse)
-    edge_index = torch.stack([src, near_i.flatten()])
+    if tsp_coordinates.is_cuda:
+        from .. import _engine as E
+        distances, _, near_d, edge_index = E.knn_graph(coords=tsp_coordinates, k=k_sparse, diag=1e9, want_edge_index=True)
+    else:
+        distances = gen_distance_matrix(tsp_coordinates)
+        near_d, near_i = torch.topk(distances, k=k_sparse, dim=1, largest=False)
+        src = torch.arange(n, device=near_i.device).repeat_interleave(k_sparse)
+        edge_index = torch.stack([src, near_i.flatten()])
     if start_node is None:
         x = tsp_coordinates
     else:

@@ -215,6 +215,17 @@ int deepaco_tsp_nls(const float* distances, const float* heuristic_dist, uint16_
 int deepaco_paths_to_tours(const int64_t* paths, uint16_t* tours, int n, int n_ants, int n_colonies, void* stream);
 int deepaco_tours_to_paths(const uint16_t* tours, int64_t* paths, int n, int n_ants, int n_colonies, void* stream);
 
+/* ---- instance -> graph front end (gen_distance_matrix + gen_pyg_data's topk / edge_index: tsp/utils.py:4-36,
+ * tsp_nls/utils.py:5-46; the distance part also cvrp/utils.py:18-22) for a batch of instances in one launch.
+ * Input: coords f32 [B][n][2] (distances computed with ATen's rounding: sqrt(fl(fl(dx*dx) + fl(dy*dy))), diagonal := diag,
+ * 1e9 for TSP / 1e-10 for CVRP) OR distances_in f32 [B][n][n] (taken as is) -- exactly one of them.
+ * Outputs, each optional: distances_out f32 [B][n][n]; the k smallest entries of every row in ascending order
+ * (torch.topk(distances, k, dim=1, largest=False)) as nbr_index int32 [B][n][k] / nbr_value f32 [B][n][k]; edge_index
+ * int64 [B][2][n*k] (row 0: repeat_interleave(arange(n), k), row 1: the flattened neighbour indices).  Bit-equal distances
+ * within a row: lowest column first (torch's order among equal values is unspecified).  0 <= k <= n <= 8192. */
+int deepaco_knn_graph(const float* coords, const float* distances_in, int n, int n_instances, int k, float diag,
+                      float* distances_out, int32_t* nbr_index, float* nbr_value, int64_t* edge_index, void* stream);
+
 /* ---- heuristic network forward, eval mode (Net.forward, tsp/net.py:84-88 -> EmbNet :27-45 -> ParNet :74-75)
  * Graph per instance in CSR-by-source form: row_ptr int32 [B][n+1]; for the edges sorted by source:
  * dst_sorted int32 [B][E], attr_sorted f32 [B][E], order int32 [B][E] (original edge id, used to write

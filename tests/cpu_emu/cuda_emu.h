@@ -211,6 +211,7 @@ static inline void emu_mbar_wait(uint64_t* bar, uint32_t parity) {   // done whe
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline float __fadd_rn(float a, float b) { return a + b; }      // built with -ffp-contract=off
 static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 
 namespace deepaco {
 namespace gnnt {

@@ -26,6 +26,7 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) { emu_mbar_wait(bar
 #include "../../deepaco_b200/csrc/tsp_update.cuh"
 #include "../../deepaco_b200/csrc/cvrp_update.cuh"
 #include "../../deepaco_b200/csrc/backward.cuh"
+#include "../../deepaco_b200/csrc/knn_graph.cuh"
 
 using namespace deepaco;
 
@@ -116,6 +117,16 @@ extern "C" const char* emu_knn_refresh(const float* prod, uint8_t* knn, int n, i
     struct A { const float* p; uint8_t* k; int n, rows; };
     const A a{prod, knn, n, rows};
     emu::launch([](const A& q) { knn_refresh_kernel(q.p, q.k, q.n, q.rows); }, a, (rows + 7) / 8, 1, 256, 16);
+    return nullptr;
+}
+
+// knn_graph_kernel: distance matrix + k smallest entries per row + edge_index for a batch (one warp per row)
+extern "C" const char* emu_knn_graph(const float* coords, const float* dist_in, int n, int B, int k, float diag, float* dist_out,
+                                     int32_t* idx, float* val, int64_t* edge_index) {
+    if ((coords != nullptr) == (dist_in != nullptr) || n < 1 || B < 1 || k < 0 || k > n) return "bad arguments";
+    const KnnGraphParams p{coords, dist_in, dist_out, idx, val, edge_index, n, B, k, diag};
+    const long rows = (long)B * n;
+    emu::launch(knn_graph_kernel, p, (int)((rows + 7) / 8), 1, 256, (size_t)8 * n * 4);
     return nullptr;
 }
 
