@@ -326,10 +326,10 @@ def leg_gnn_front_end(dev, steps):
     E = n * k
     flops = B * (12 * (2 * E * 32 * 32 + 4 * 2 * n * 32 * 32) + 2 * 2 * E * 32 * 32)
     bytes_alg = B * 12 * (2 * 128 * E + 3 * 128 * E + 20 * 1024)          # edge state r/w + gathers + weights
-    out = {"workload": f"{B} x TSP-{n}, k={k}: topk + Net.forward (eval) + reshape + EPS", "ms_per_batch": ms,
+    out = {"workload": f"{B} x TSP-{n}, k={k}: k-nearest-neighbour graph (deepaco_knn_graph) + Net.forward (eval) + reshape + EPS", "ms_per_batch": ms,
            "us_per_instance": ms / B * 1e3, "tflops_linear": flops / (ms * 1e-3) / 1e12,
            "roofline": roofline("K3 gnn_forward_kernel (mma.sync TF32 split tiles)", bytes_alg, ms,
-                                "edge state streams through L2 once per layer; whole front end timed (topk included)")}
+                                "edge state streams through L2 once per layer; whole front end timed (graph launch included)")}
     return out
 
 
