@@ -12,7 +12,7 @@ DEPOT_COOR = [0.5, 0.5]
 def gen_distance_matrix(tsp_coordinates):
     '''cvrp/utils.py:18-22: Euclidean distances with 1e-10 on the diagonal.  CUDA coordinates: one deepaco_knn_graph launch
     (same bits); host coordinates: the op chain on the host, as in the reference.'''
-    if tsp_coordinates.is_cuda:
+    if tsp_coordinates.is_cuda and tsp_coordinates.dtype == torch.float32:
         from .. import _engine as E
         return E.knn_graph(coords=tsp_coordinates, k=0, diag=1e-10)[0]
     n = len(tsp_coordinates)

@@ -7,9 +7,9 @@ from ..net import Data
 
 def gen_distance_matrix(tsp_coordinates):
     '''[n, 2] coordinates -> [n, n] Euclidean distances with 1e9 on the diagonal (tsp/utils.py:4-14).
-    CUDA coordinates: one launch of deepaco_knn_graph (bit-identical to the op chain below, tests/test_gpu_graph.py);
-    host coordinates: the reference's op chain on the host, as there.'''
-    if tsp_coordinates.is_cuda:
+    fp32 CUDA coordinates: one launch of deepaco_knn_graph (bit-identical to the op chain below, tests/test_gpu_graph.py);
+    host (or non-fp32) coordinates: the reference's op chain where the tensor lives, as there.'''
+    if tsp_coordinates.is_cuda and tsp_coordinates.dtype == torch.float32:
         from .. import _engine as E
         return E.knn_graph(coords=tsp_coordinates, k=0, diag=1e9)[0]
     n = len(tsp_coordinates)
@@ -22,7 +22,7 @@ def knn_graph(tsp_coordinates, k_sparse, start_node=None):
     '''k-nearest-neighbour graph (tsp/utils.py:16-36; start_node one-hot node feature as tsp_nls/utils.py:37-43).
     CUDA coordinates: distances, topk and edge_index come out of one deepaco_knn_graph launch.'''
     n = len(tsp_coordinates)
-    if tsp_coordinates.is_cuda:
+    if tsp_coordinates.is_cuda and tsp_coordinates.dtype == torch.float32:
         from .. import _engine as E
         distances, _, near_d, edge_index = E.knn_graph(coords=tsp_coordinates, k=k_sparse, diag=1e9, want_edge_index=True)
     else:
